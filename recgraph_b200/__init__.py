@@ -1,0 +1,6 @@
+"""recgraph_b200 — B200-native RecGraph aligner (sequence-to-graph DP on sm_100a behind a C ABI).
+
+Python is only the harness around the C ABI (include/recgraph_b200.h): `Aligner` wraps one context,
+`run_cli` calls the `recgraph` command line in-process. Nothing here computes alignments on the CPU.
+"""
+from .api import Aligner, RecGraphError, encode_read, run_cli  # noqa: F401

@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference's interface over the C ABI (see include/recgraph_b200.h).
+
+`run_cli(argv)` == the reference binary's `main` (main.rs:25-329); `Aligner` == one device context with the
+graph resident in HBM, exposing the batch form of the exec functions that main.rs loops over.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+CODES = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 4}
+_LUT = np.full(256, 255, dtype=np.uint8)
+for _c, _v in CODES.items():
+    _LUT[ord(_c)] = _v
+    _LUT[ord(_c.lower())] = _v
+_LUT[ord("-")] = 4  # sequences.rs:17-19: '-' -> 'N'
+
+
+class RecGraphError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"recgraph_b200 status {status}: {msg}")
+        self.status = status
+
+
+def encode_read(seq: str) -> np.ndarray:
+    codes = _LUT[np.frombuffer(seq.encode(), dtype=np.uint8)]
+    if (codes == 255).any():
+        raise RecGraphError(-5, "read character outside A,C,G,T,N")
+    return codes
+
+
+def run_cli(argv):
+    """`recgraph <argv...>` in-process. Returns (exit_code, stdout_text, stderr_text)."""
+    lib = _lib.load()
+    args = [b"recgraph"] + [str(a).encode() for a in argv]
+    arr = (ctypes.c_char_p * len(args))(*args)
+    out, err = ctypes.c_void_p(), ctypes.c_void_p()
+    rc = lib.rg_cli_main(len(args), arr, ctypes.byref(out), ctypes.byref(err))
+    o = ctypes.string_at(out).decode() if out else ""
+    e = ctypes.string_at(err).decode() if err else ""
+    lib.rg_free(out)
+    lib.rg_free(err)
+    return rc, o, e
+
+
+class Aligner:
+    """One rg_ctx: one CUDA device, one stream, one resident graph."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.ctx = ctypes.c_void_p()
+        rc = self.lib.rg_init(device, ctypes.byref(self.ctx))
+        if rc != 0:
+            raise RecGraphError(rc, self.lib.rg_strerror(rc).decode())
+        self.scoring = _lib.Scoring()
+        self.lib.rg_default_scoring(ctypes.byref(self.scoring))
+        self._keep = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.rg_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RecGraphError(rc, self.lib.rg_last_error(self.ctx).decode() or self.lib.rg_strerror(rc).decode())
+
+    # ---- graph
+    def load_gfa(self, path):
+        self._check(self.lib.rg_load_gfa_file(self.ctx, str(path).encode()))
+
+    def load_gfa_text(self, text):
+        b = text.encode()
+        self._check(self.lib.rg_load_gfa_text(self.ctx, b, len(b)))
+
+    def set_lnz_graph(self, lnz, nwp_idx, pred_hash, seg_id=None):
+        """Hand-built LnzGraph as in the reference's inline tests: lnz chars incl. '$' and 'F'."""
+        n = len(lnz)
+        codes = np.array([CODES.get(c, 0) for c in lnz], dtype=np.uint8)
+        nwp = np.zeros(n, dtype=np.uint8)
+        nwp[list(nwp_idx)] = 1
+        off = [0]
+        idx = []
+        for i in range(n):
+            idx += list(pred_hash.get(i, []))
+            off.append(len(idx))
+        off = np.array(off, dtype=np.uint32)
+        idx = np.array(idx if idx else [0], dtype=np.uint32)
+        sid = None if seg_id is None else np.array(seg_id, dtype=np.uint64)
+        self._check(self.lib.rg_set_lnz_graph(self.ctx, n, codes.ctypes.data, nwp.ctypes.data, off.ctypes.data,
+                                              idx.ctypes.data, None if sid is None else sid.ctypes.data))
+
+    def graph_info(self):
+        n, s, p = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(self.lib.rg_graph_info(self.ctx, ctypes.byref(n), ctypes.byref(s), ctypes.byref(p)))
+        return n.value, s.value, p.value
+
+    # ---- scoring
+    def set_scoring(self, match=2, mismatch=4, gap_open=4, gap_ext=2, matrix="none", base_rec_cost=4,
+                    multi_rec_cost=0.1, rec_band_width=1.0, extra_b=1, extra_f=0.01, fixed_bta=-1, kind=None,
+                    table=None):
+        """CLI-style parameters (penalties positive, as on the reference command line)."""
+        s = self.scoring
+        if table is not None:
+            for i in range(6):
+                for j in range(6):
+                    s.score[i][j] = int(table[i][j])
+        else:
+            if kind is None:
+                kind = {"none": 0, "HOXD55": 2, "HOXD55.mtx": 2, "HOXD70": 3, "HOXD70.mtx": 3}[matrix]
+            self._check(self.lib.rg_make_score_matrix(kind, match, -mismatch, ctypes.byref(s)))
+        s.gap_open, s.gap_ext = -gap_open, -gap_ext
+        s.base_rec_cost, s.multi_rec_cost, s.rec_band_width = base_rec_cost, multi_rec_cost, rec_band_width
+        s.extra_b, s.extra_f, s.fixed_bta = float(extra_b), extra_f, fixed_bta
+        self._check(self.lib.rg_set_scoring(self.ctx, ctypes.byref(s)))
+
+    # ---- alignment
+    @staticmethod
+    def pack_reads(reads):
+        """list of str / uint8 code arrays -> (codes, offsets) numpy arrays."""
+        arrs = [encode_read(r) if isinstance(r, str) else np.asarray(r, dtype=np.uint8) for r in reads]
+        off = np.zeros(len(arrs) + 1, dtype=np.uint64)
+        if arrs:
+            off[1:] = np.cumsum([len(a) for a in arrs])
+        codes = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.uint8)
+        return np.ascontiguousarray(codes), off
+
+    def align_packed(self, mode, codes, off):
+        """rg_align_batch: host buffers in, records out (H2D + kernels + D2H)."""
+        res = _lib.BatchResult()
+        self._keep = (codes, off)
+        self._check(self.lib.rg_align_batch(self.ctx, mode, len(off) - 1, codes.ctypes.data, off.ctypes.data,
+                                            ctypes.byref(res)))
+        return res
+
+    def upload(self, codes, off):
+        self._keep = (codes, off)
+        self._check(self.lib.rg_upload_reads(self.ctx, len(off) - 1, codes.ctypes.data, off.ctypes.data))
+
+    def align_staged(self, mode):
+        self._check(self.lib.rg_align_staged(self.ctx, mode))
+
+    def fetch(self):
+        res = _lib.BatchResult()
+        self._check(self.lib.rg_fetch_results(self.ctx, ctypes.byref(res)))
+        return res
+
+    def kernel_stats(self):
+        ms, launches, cells = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64()
+        self.lib.rg_last_kernel_stats(self.ctx, ctypes.byref(ms), ctypes.byref(launches), ctypes.byref(cells))
+        return ms.value, launches.value, cells.value
+
+    def format_gaf(self, mode, res, index, name, read_len, amb_mode=False):
+        buf = ctypes.create_string_buffer(1 << 16)
+        need = self.lib.rg_format_gaf(self.ctx, mode, ctypes.byref(res), index, name.encode(), read_len,
+                                      int(amb_mode), buf, len(buf))
+        if need < 0:
+            raise RecGraphError(need, "rg_format_gaf failed")
+        if need >= len(buf):
+            buf = ctypes.create_string_buffer(need + 1)
+            self.lib.rg_format_gaf(self.ctx, mode, ctypes.byref(res), index, name.encode(), read_len, int(amb_mode),
+                                   buf, len(buf))
+        return buf.value.decode()
+
+    def align(self, mode, reads, names=None):
+        """Align a list of reads; returns (records, gaf_text)."""
+        codes, off = self.pack_reads(reads)
+        res = self.align_packed(mode, codes, off)
+        names = names or [f"read{i}" for i in range(len(reads))]
+        text = "".join(self.format_gaf(mode, res, i, names[i], int(off[i + 1] - off[i])) for i in range(len(reads)))
+        recs = [res.reads[i] for i in range(res.n_reads)]
+        return recs, text
+
+    def int_peak(self):
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self._check(self.lib.rg_int_peak(self.ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"iadd3_gops": a.value, "vimnmx_gops": b.value, "viaddmnmx_gops": c.value}

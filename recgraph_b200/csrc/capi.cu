@@ -1,0 +1,544 @@
+// C-ABI implementation (include/recgraph_b200.h): context, graph upload, batch alignment, result fetch.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "device.h"
+#include "host.h"
+
+using namespace rg;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    bool ensure(size_t n) {
+        if (n <= cap && p) return true;
+        release();
+        if (n == 0) n = 1;
+        if (cudaMalloc((void**)&p, n * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return false;
+        }
+        cap = n;
+        return true;
+    }
+    bool upload(const std::vector<T>& v, cudaStream_t st) {
+        if (!ensure(v.size())) return false;
+        if (v.empty()) return true;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    }
+};
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() { release(); }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    bool ensure(size_t n) {
+        if (n <= cap && p) return true;
+        release();
+        if (n == 0) n = 1;
+        if (cudaMallocHost((void**)&p, n * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return false;
+        }
+        cap = n;
+        return true;
+    }
+};
+
+}  // namespace
+
+struct rg_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string last_error;
+    // graph
+    bool has_graph = false;
+    FlatGraph fg;
+    DevBuf<uint8_t> d_lnz, d_rowflags, d_min_pred_slot, d_prev_slot;
+    DevBuf<uint32_t> d_pred_off, d_pred_idx, d_min_pred;
+    DevBuf<int32_t> d_r_values;
+    DevGraph dg{};
+    // scoring
+    bool has_scoring = false;
+    rg_scoring scoring{};
+    DevScoring ds{};
+    // staged reads
+    int32_t n_reads = 0;
+    uint64_t total_len = 0;
+    uint32_t max_len = 0;
+    std::vector<uint64_t> h_off;
+    DevBuf<uint8_t> d_reads;
+    DevBuf<uint64_t> d_read_off;
+    DevBuf<int32_t> d_order;
+    // workspace
+    DevBuf<RowMeta> d_rowmeta;
+    DevBuf<int32_t> d_ring_m, d_ring_y;
+    DevBuf<uint8_t> d_trace;
+    DevBuf<rg_run> d_slot_runs, d_out_runs;
+    DevBuf<rg_read_result> d_results;
+    DevBuf<unsigned long long> d_counters;
+    // results on the host
+    PinnedBuf<rg_read_result> h_results;
+    PinnedBuf<rg_run> h_runs;
+    uint64_t n_runs_total = 0;
+    int last_mode = -1;
+    bool results_ready = false;
+    double kernel_ms = 0;
+    uint64_t launches = 0, cells = 0;
+    double trace_scale = 1.0;  // grown after an overflow
+
+    int fail(int code, const std::string& msg) {
+        last_error = msg;
+        return code;
+    }
+    int cuda_fail(const char* what) {
+        cudaError_t e = cudaGetLastError();
+        last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        return RG_ERR_CUDA;
+    }
+};
+
+static int upload_graph(rg_ctx* c) {
+    FlatGraph& f = c->fg;
+    cudaStream_t st = c->stream;
+    std::vector<uint8_t> rowflags(f.n, 0);
+    for (uint32_t i = 0; i < f.n; i++) rowflags[i] = (f.nwp[i] ? RF_NWP : 0) | (f.is_pred_row[i] ? RF_IS_PRED : 0);
+    for (uint32_t k = f.pred_off[f.n - 1]; k < f.pred_off[f.n]; k++) rowflags[f.pred_idx[k]] |= RF_F_PRED;
+    bool ok = c->d_lnz.upload(f.lnz, st) && c->d_rowflags.upload(rowflags, st) &&
+              c->d_pred_off.upload(f.pred_off, st) && c->d_pred_idx.upload(f.pred_idx, st) &&
+              c->d_min_pred.upload(f.min_pred, st) && c->d_min_pred_slot.upload(f.min_pred_slot, st) &&
+              c->d_prev_slot.upload(f.prev_slot, st) && c->d_r_values.upload(f.r_values, st);
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) return c->cuda_fail("graph upload");
+    uint32_t ring = 2;
+    while (ring <= f.max_lookback) ring <<= 1;
+    c->dg.n = f.n;
+    c->dg.lnz = c->d_lnz.p;
+    c->dg.rowflags = c->d_rowflags.p;
+    c->dg.pred_off = c->d_pred_off.p;
+    c->dg.pred_idx = c->d_pred_idx.p;
+    c->dg.min_pred = c->d_min_pred.p;
+    c->dg.min_pred_slot = c->d_min_pred_slot.p;
+    c->dg.prev_slot = c->d_prev_slot.p;
+    c->dg.r_values = c->d_r_values.p;
+    c->dg.ring = ring;
+    c->has_graph = true;
+    c->results_ready = false;
+    return RG_OK;
+}
+
+extern "C" {
+
+const char* rg_strerror(int s) {
+    switch (s) {
+        case RG_OK: return "ok";
+        case RG_ERR_INVALID: return "invalid argument or call order";
+        case RG_ERR_CUDA: return "CUDA error";
+        case RG_ERR_NO_DEVICE: return "no CUDA device (recgraph_b200 has no CPU fallback)";
+        case RG_ERR_IO: return "I/O or format error";
+        case RG_ERR_BAD_CHAR: return "character outside A,C,G,T,N";
+        case RG_ERR_UNSUPPORTED: return "input outside the supported domain";
+        case RG_ERR_REF_PANIC: return "the reference implementation panics on this input";
+        case RG_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+const char* rg_last_error(const rg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null ctx"; }
+
+int rg_init(int device, rg_ctx** out) {
+    if (!out) return RG_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return RG_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return RG_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        return RG_ERR_CUDA;
+    }
+    rg_ctx* c = new (std::nothrow) rg_ctx();
+    if (!c) return RG_ERR_NOMEM;
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return RG_ERR_CUDA;
+    }
+    rg_default_scoring(&c->scoring);
+    rg_set_scoring(c, &c->scoring);
+    *out = c;
+    return RG_OK;
+}
+
+void rg_destroy(rg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rg_load_gfa_text(rg_ctx* c, const char* text, size_t len) {
+    if (!c || !text) return RG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    GfaGraph g;
+    std::string err;
+    if (!parse_gfa(text, len, g, err)) return c->fail(err.find("outside the supported") != std::string::npos ? RG_ERR_UNSUPPORTED : RG_ERR_IO, err);
+    int rc = flatten_graph(g, c->fg, err);
+    if (rc != RG_OK) return c->fail(rc, err);
+    return upload_graph(c);
+}
+
+int rg_load_gfa_file(rg_ctx* c, const char* path) {
+    if (!c || !path) return RG_ERR_INVALID;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return c->fail(RG_ERR_IO, std::string("cannot open ") + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    std::string s = ss.str();
+    return rg_load_gfa_text(c, s.data(), s.size());
+}
+
+int rg_set_lnz_graph(rg_ctx* c, uint32_t n, const uint8_t* lnz_codes, const uint8_t* nwp, const uint32_t* pred_off,
+                     const uint32_t* pred_idx, const uint64_t* seg_id) {
+    if (!c || !lnz_codes || !nwp || !pred_off || !pred_idx) return RG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    std::string err;
+    int rc = flat_from_lnz(n, lnz_codes, nwp, pred_off, pred_idx, seg_id, c->fg, err);
+    if (rc != RG_OK) return c->fail(rc, err);
+    return upload_graph(c);
+}
+
+int rg_graph_info(const rg_ctx* c, uint32_t* n, uint32_t* n_segments, uint32_t* n_paths) {
+    if (!c || !c->has_graph) return RG_ERR_INVALID;
+    if (n) *n = c->fg.n;
+    if (n_segments) *n_segments = c->fg.n_segments;
+    if (n_paths) *n_paths = c->fg.P;
+    return RG_OK;
+}
+
+int rg_make_score_matrix(int kind, int32_t match, int32_t mismatch, rg_scoring* s) {
+    return make_score_matrix(kind, match, mismatch, s);
+}
+
+void rg_default_scoring(rg_scoring* s) {
+    if (!s) return;
+    make_score_matrix(0, 2, -4, s);
+    s->gap_open = -4;
+    s->gap_ext = -2;
+    s->base_rec_cost = 4;
+    s->multi_rec_cost = 0.1f;
+    s->rec_band_width = 1.0f;
+    s->extra_b = 1.0f;
+    s->extra_f = 0.01f;
+    s->fixed_bta = -1;
+}
+
+int rg_set_scoring(rg_ctx* c, const rg_scoring* s) {
+    if (!c || !s) return RG_ERR_INVALID;
+    c->scoring = *s;
+    memset(&c->ds, 0, sizeof c->ds);
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) c->ds.sc[i][j] = s->score[i][j];
+    c->ds.o = s->gap_open;
+    c->ds.e = s->gap_ext;
+    c->ds.b = s->extra_b;
+    c->ds.f = s->extra_f;
+    c->ds.fixed_bta = s->fixed_bta;
+    c->has_scoring = true;
+    return RG_OK;
+}
+
+int rg_upload_reads(rg_ctx* c, int32_t n_reads, const uint8_t* read_codes, const uint64_t* read_off) {
+    if (!c || n_reads < 0 || !read_off || (n_reads > 0 && !read_codes)) return RG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    c->results_ready = false;
+    c->n_reads = n_reads;
+    c->h_off.assign(read_off, read_off + n_reads + 1);
+    c->total_len = read_off[n_reads] - read_off[0];
+    uint32_t mx = 0;
+    for (int32_t i = 0; i < n_reads; i++) {
+        uint64_t l = read_off[i + 1] - read_off[i];
+        if (l == 0) return c->fail(RG_ERR_INVALID, "empty read (the reference's FASTA reader never yields one)");
+        if (l > 0x0fffffff) return c->fail(RG_ERR_UNSUPPORTED, "read too long");
+        mx = std::max<uint32_t>(mx, (uint32_t)l);
+    }
+    c->max_len = mx;
+    for (uint64_t k = read_off[0]; k < read_off[n_reads]; k++)
+        if (read_codes[k] > RG_N) return c->fail(RG_ERR_BAD_CHAR, "read code outside 0..4 (A,C,G,T,N)");
+    // longest reads first: the persistent kernel hands reads out in this order (load balance)
+    std::vector<int32_t> order(n_reads);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return read_off[a + 1] - read_off[a] > read_off[b + 1] - read_off[b];
+    });
+    std::vector<uint64_t> off0(n_reads + 1);
+    for (int32_t i = 0; i <= n_reads; i++) off0[i] = read_off[i] - read_off[0];
+    if (!c->d_reads.ensure(c->total_len + 16) || !c->d_read_off.ensure(n_reads + 1) || !c->d_order.ensure(n_reads + 1))
+        return c->fail(RG_ERR_NOMEM, "device allocation for reads failed");
+    cudaStream_t st = c->stream;
+    if (c->total_len)
+        cudaMemcpyAsync(c->d_reads.p, read_codes + read_off[0], c->total_len, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(c->d_read_off.p, off0.data(), (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+    if (n_reads) cudaMemcpyAsync(c->d_order.p, order.data(), n_reads * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return c->cuda_fail("read upload");
+    return RG_OK;
+}
+
+static int align_poa(rg_ctx* c, int mode) {
+    const FlatGraph& f = c->fg;
+    const uint32_t n = f.n;
+    const uint32_t Lmax = c->max_len + 1;
+    const int trace_bytes = f.max_indeg <= 4 ? 1 : 2;
+    if (f.max_indeg > 64) return c->fail(RG_ERR_UNSUPPORTED, "in-degree above 64 is outside the trace-code domain");
+    const uint32_t wstride = (Lmax + 31) & ~31u;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // band half-width of the longest read, for the trace estimate
+    uint32_t bta = c->scoring.fixed_bta >= 0 ? (uint32_t)c->scoring.fixed_bta
+                                             : bases_to_add(c->scoring.extra_b, c->scoring.extra_f, Lmax);
+    const uint64_t full = (uint64_t)n * Lmax;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        double est = ((double)n * (2.0 * std::min<uint32_t>(bta, Lmax) + 24.0) + 1.5 * (double)Lmax * Lmax) * c->trace_scale;
+        uint64_t trace_cap = (uint64_t)std::min<double>((double)full, est);
+        trace_cap = std::max<uint64_t>(trace_cap, 4096);
+        trace_cap = std::min<uint64_t>(trace_cap, 0x7fffff00ull);
+        trace_cap = (trace_cap + 255) & ~255ull;
+        const uint32_t run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)(n / 4 + 2 * Lmax)), 1u << 22);
+        const size_t per_slot = (size_t)n * sizeof(RowMeta) + (size_t)c->dg.ring * wstride * 8 +
+                                trace_cap * trace_bytes + (size_t)run_cap * sizeof(rg_run);
+        uint32_t want_slots = (uint32_t)c->sms * 32;  // 4 blocks of 8 warps per SM
+        want_slots = std::min<uint32_t>(want_slots, (uint32_t)((c->n_reads + 7) / 8 * 8));
+        want_slots = std::max<uint32_t>(want_slots, 8);
+        size_t budget = (size_t)(free_b * 0.80);
+        size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(run_cap, 16384), (budget / 4) / sizeof(rg_run));
+        out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
+        size_t avail = budget - out_runs_cap * sizeof(rg_run);
+        uint32_t slots = (uint32_t)std::min<size_t>(want_slots, avail / per_slot);
+        slots = slots / 8 * 8;
+        if (slots < 8) return c->fail(RG_ERR_NOMEM, "not enough device memory for one block of reads in flight");
+        bool ok = c->d_rowmeta.ensure((size_t)slots * n) && c->d_ring_m.ensure((size_t)slots * c->dg.ring * wstride) &&
+                  c->d_ring_y.ensure((size_t)slots * c->dg.ring * wstride) &&
+                  c->d_trace.ensure((size_t)slots * trace_cap * trace_bytes) &&
+                  c->d_slot_runs.ensure((size_t)slots * run_cap) && c->d_out_runs.ensure(out_runs_cap) &&
+                  c->d_results.ensure(c->n_reads + 1) && c->d_counters.ensure(4);
+        if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
+        PoaWorkspace ws{};
+        ws.rowmeta = c->d_rowmeta.p;
+        ws.ring_m = c->d_ring_m.p;
+        ws.ring_y = c->d_ring_y.p;
+        ws.trace = c->d_trace.p;
+        ws.runs = c->d_slot_runs.p;
+        ws.trace_cap = trace_cap;
+        ws.run_cap = run_cap;
+        ws.wstride = wstride;
+        ws.slots = slots;
+        PoaBatch b{};
+        b.reads = c->d_reads.p;
+        b.read_off = c->d_read_off.p;
+        b.n_reads = c->n_reads;
+        b.order = c->d_order.p;
+        b.results = c->d_results.p;
+        b.out_runs = c->d_out_runs.p;
+        b.out_run_cap = out_runs_cap;
+        b.counters = c->d_counters.p;
+        cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
+        cudaEventRecord(c->ev0, c->stream);
+        int rc = launch_poa(mode, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), 256, c->stream);
+        cudaEventRecord(c->ev1, c->stream);
+        if (rc == -2) return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
+        if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("alignment kernel");
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->kernel_ms += ms;
+        c->launches += 1;
+        // overflow check needs the statuses: cheap D2H of the records
+        if (!c->h_results.ensure(c->n_reads + 1)) return c->fail(RG_ERR_NOMEM, "pinned allocation failed");
+        cudaMemcpyAsync(c->h_results.p, c->d_results.p, (size_t)c->n_reads * sizeof(rg_read_result), cudaMemcpyDeviceToHost, c->stream);
+        unsigned long long counters[4];
+        cudaMemcpyAsync(counters, c->d_counters.p, sizeof counters, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("result copy");
+        bool overflow = false;
+        for (int32_t i = 0; i < c->n_reads; i++)
+            if (c->h_results.p[i].status & RG_READ_TRACE_OVERFLOW) overflow = true;
+        c->n_runs_total = std::min<uint64_t>(counters[1], out_runs_cap);
+        if (!overflow) return RG_OK;
+        if (trace_cap >= full && counters[1] <= out_runs_cap && run_cap >= (1u << 22))
+            return c->fail(RG_ERR_NOMEM, "trace buffers overflow at maximum size");
+        c->trace_scale *= 4.0;  // whole batch is re-run with larger per-slot buffers (rare; sizes are then remembered)
+    }
+    return c->fail(RG_ERR_NOMEM, "trace buffers still overflow after retries");
+}
+
+int rg_align_staged(rg_ctx* c, int mode) {
+    if (!c) return RG_ERR_INVALID;
+    if (!c->has_graph) return c->fail(RG_ERR_INVALID, "no graph loaded");
+    cudaSetDevice(c->device);
+    c->results_ready = false;
+    c->kernel_ms = 0;
+    c->launches = 0;
+    c->cells = 0;
+    c->n_runs_total = 0;
+    c->last_mode = mode;
+    if (c->n_reads == 0) {
+        c->results_ready = true;
+        return RG_OK;
+    }
+    int rc;
+    switch (mode) {
+        case RG_MODE_GAP_GLOBAL: rc = align_poa(c, mode); break;
+        default: return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
+    }
+    if (rc != RG_OK) return rc;
+    c->results_ready = true;
+    return RG_OK;
+}
+
+int rg_fetch_results(rg_ctx* c, rg_batch_result* out) {
+    if (!c || !out) return RG_ERR_INVALID;
+    if (!c->results_ready) return c->fail(RG_ERR_INVALID, "no results to fetch");
+    cudaSetDevice(c->device);
+    memset(out, 0, sizeof *out);
+    out->n_reads = c->n_reads;
+    if (c->n_reads) {
+        if (!c->h_results.ensure(c->n_reads + 1) || !c->h_runs.ensure(c->n_runs_total + 1))
+            return c->fail(RG_ERR_NOMEM, "pinned allocation failed");
+        cudaMemcpyAsync(c->h_results.p, c->d_results.p, (size_t)c->n_reads * sizeof(rg_read_result), cudaMemcpyDeviceToHost, c->stream);
+        if (c->n_runs_total)
+            cudaMemcpyAsync(c->h_runs.p, c->d_out_runs.p, c->n_runs_total * sizeof(rg_run), cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("result fetch");
+        uint64_t cells = 0;
+        for (int32_t i = 0; i < c->n_reads; i++) cells += c->h_results.p[i].cells;
+        c->cells = cells;
+    }
+    out->reads = c->h_results.p;
+    out->runs = c->h_runs.p;
+    out->n_runs_total = c->n_runs_total;
+    out->kernel_ms = c->kernel_ms;
+    out->gpu_launches = c->launches;
+    return RG_OK;
+}
+
+int rg_align_batch(rg_ctx* c, int mode, int32_t n_reads, const uint8_t* read_codes, const uint64_t* read_off,
+                   rg_batch_result* out) {
+    int rc = rg_upload_reads(c, n_reads, read_codes, read_off);
+    if (rc != RG_OK) return rc;
+    rc = rg_align_staged(c, mode);
+    if (rc != RG_OK) return rc;
+    return rg_fetch_results(c, out);
+}
+
+int rg_last_kernel_stats(const rg_ctx* c, double* kernel_ms, uint64_t* launches, uint64_t* cells) {
+    if (!c) return RG_ERR_INVALID;
+    if (kernel_ms) *kernel_ms = c->kernel_ms;
+    if (launches) *launches = c->launches;
+    if (cells) *cells = c->cells;
+    return RG_OK;
+}
+
+int64_t rg_format_gaf(rg_ctx* c, int mode, const rg_batch_result* res, int32_t read_index, const char* read_name,
+                      uint32_t read_len, int amb_mode, char* buf, size_t cap) {
+    if (!c || !res || read_index < 0 || read_index >= res->n_reads || !c->has_graph) return RG_ERR_INVALID;
+    std::string s;
+    format_gaf(c->fg, mode, res->reads[read_index], res->runs, read_name ? read_name : "", read_len, amb_mode != 0, s);
+    if (buf && cap) {
+        size_t k = std::min(cap - 1, s.size());
+        memcpy(buf, s.data(), k);
+        buf[k] = 0;
+    }
+    return (int64_t)s.size();
+}
+
+static int fill_reads(std::vector<std::string>& names, std::vector<uint8_t>& codes, std::vector<uint64_t>& off, rg_reads* out) {
+    out->n_reads = (int32_t)names.size();
+    out->codes = (uint8_t*)malloc(codes.size() + 1);
+    out->off = (uint64_t*)malloc(off.size() * sizeof(uint64_t));
+    out->names = (char**)malloc((names.size() + 1) * sizeof(char*));
+    if (!out->codes || !out->off || !out->names) return RG_ERR_NOMEM;
+    memcpy(out->codes, codes.data(), codes.size());
+    memcpy(out->off, off.data(), off.size() * sizeof(uint64_t));
+    for (size_t i = 0; i < names.size(); i++) out->names[i] = strdup(names[i].c_str());
+    return RG_OK;
+}
+
+int rg_read_fasta_text(const char* text, size_t len, rg_reads* out, char* errbuf, size_t errcap) {
+    if (!text || !out) return RG_ERR_INVALID;
+    memset(out, 0, sizeof *out);
+    std::vector<std::string> names;
+    std::vector<uint8_t> codes;
+    std::vector<uint64_t> off;
+    std::string err;
+    int status = RG_OK;
+    if (!parse_fasta(text, len, names, codes, off, err, &status)) {
+        if (errbuf && errcap) snprintf(errbuf, errcap, "%s", err.c_str());
+        return status;
+    }
+    return fill_reads(names, codes, off, out);
+}
+
+int rg_read_fasta_file(const char* path, rg_reads* out, char* errbuf, size_t errcap) {
+    if (!path || !out) return RG_ERR_INVALID;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) {
+        if (errbuf && errcap) snprintf(errbuf, errcap, "cannot open %s", path);
+        return RG_ERR_IO;
+    }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    std::string s = ss.str();
+    return rg_read_fasta_text(s.data(), s.size(), out, errbuf, errcap);
+}
+
+void rg_free_reads(rg_reads* r) {
+    if (!r) return;
+    free(r->codes);
+    free(r->off);
+    if (r->names) {
+        for (int32_t i = 0; i < r->n_reads; i++) free(r->names[i]);
+        free(r->names);
+    }
+    memset(r, 0, sizeof *r);
+}
+
+void rg_free(void* p) { free(p); }
+
+int rg_int_peak(rg_ctx* c, double* iadd, double* imnmx, double* viaddmnmx) {
+    if (!c || !iadd || !imnmx || !viaddmnmx) return RG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return launch_int_peak(iadd, imnmx, viaddmnmx, c->stream) == 0 ? RG_OK : RG_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Device-side data layout shared by the kernels and the C-ABI implementation.
+#pragma once
+#include <cstdint>
+
+#include "../../include/recgraph_b200.h"
+
+namespace rg {
+
+// rowflags bits
+enum : uint8_t { RF_NWP = 1, RF_IS_PRED = 2, RF_F_PRED = 4 };
+
+// Graph arrays resident in HBM (one copy per device; read-only during alignment).
+struct DevGraph {
+    uint32_t n;
+    const uint8_t* lnz;        // n codes
+    const uint8_t* rowflags;   // n
+    const uint32_t* pred_off;  // n+1
+    const uint32_t* pred_idx;
+    const uint32_t* min_pred;       // n  (best_p)
+    const uint8_t* min_pred_slot;   // n
+    const uint8_t* prev_slot;       // n
+    const int32_t* r_values;        // n
+    uint32_t ring;                  // power of two > max look-back: depth of the predecessor-row ring
+};
+
+struct DevScoring {
+    int32_t sc[6][8];  // [graph/first key][read/second key], padded rows
+    int32_t o, e;
+    float b, f;
+    int32_t fixed_bta;
+};
+
+// Per-row record kept for every row of the read in flight: trace base (offset of column 0 of the row inside the
+// slot's trace region, i.e. row offset - left), band [left,right) and the row's best scoring column.
+struct RowMeta {
+    int32_t base;
+    uint32_t left, right, bsp;
+};
+
+// Work-space of one slot (= one warp): everything a read in flight needs. Reused read after read.
+struct PoaWorkspace {
+    RowMeta* rowmeta;    // slots * n
+    int32_t* ring_m;     // slots * ring * wstride
+    int32_t* ring_y;     // slots * ring * wstride   (affine modes)
+    uint8_t* trace;      // slots * trace_cap * trace_bytes
+    rg_run* runs;        // slots * run_cap
+    uint64_t trace_cap;  // cells per slot
+    uint32_t run_cap;    // runs per slot
+    uint32_t wstride;    // ints per ring row (>= max L, multiple of 32)
+    uint32_t slots;
+};
+
+struct PoaBatch {
+    const uint8_t* reads;      // concatenated codes
+    const uint64_t* read_off;  // n_reads+1
+    int32_t n_reads;
+    const int32_t* order;      // processing order (longest first) or nullptr
+    rg_read_result* results;   // n_reads
+    rg_run* out_runs;          // global run output
+    uint64_t out_run_cap;
+    unsigned long long* counters;  // [0] next read, [1] runs used
+};
+
+// launchers (poa_kernels.cu)
+int launch_poa(int mode, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
+               int trace_bytes, int blocks, int threads, void* stream);
+int launch_int_peak(double* iadd, double* imnmx, double* viaddmnmx, void* stream);
+
+}  // namespace rg

@@ -1,0 +1,98 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle — byte-exact GAF."""
+import os
+
+import pytest
+
+from recgraph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXAMPLE = os.path.join(ROOT, "tests", "golden", "example")
+
+IMPLEMENTED = {2}
+
+
+def _both(args):
+    from recgraph_b200 import run_cli
+    from tests import oracle_lib
+    rc, out, err = run_cli(args)
+    orc, oout, oerr = oracle_lib.run_cli(args)
+    return (rc, out, err), (orc, oout, oerr)
+
+
+def _assert_same(args):
+    (rc, out, err), (orc, oout, oerr) = _both(args)
+    assert orc == 0, oerr
+    assert rc == 0, err
+    if out != oout:
+        a, b = out.splitlines(), oout.splitlines()
+        for k, (x, y) in enumerate(zip(a, b)):
+            if x != y:
+                raise AssertionError(f"{args}: first difference at line {k}:\n GPU: {x[:600]}\n REF: {y[:600]}")
+        raise AssertionError(f"{args}: line count differs: {len(a)} vs {len(b)}")
+
+
+@pytest.fixture(scope="module")
+def synth_files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("synth")
+    out = {}
+    for name, (bp, paths, nreads, rlen, err, seed) in {
+        "small": (1200, 5, 24, 150, 0.05, 21),
+        "mid": (6000, 8, 16, 700, 0.05, 22),
+        "short_reads": (800, 4, 20, 31, 0.1, 23),
+        "long_read": (900, 3, 6, 1400, 0.03, 24),
+    }.items():
+        g = synth.make_graph(bp, paths, seed=seed)
+        reads = synth.make_reads(g, nreads, rlen, err=err, seed=seed + 100)
+        gfa, fa = d / f"{name}.gfa", d / f"{name}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        out[name] = (str(fa), str(gfa))
+    return out
+
+
+@pytest.mark.parametrize("extra", [[], ["-b", "50"], ["-b", "1000"], ["-b", "0", "-f", "0.2"], ["-O", "10", "-E", "1"],
+                                   ["-O", "0", "-E", "3"], ["-M", "1", "-X", "1", "-O", "2", "-E", "1"],
+                                   ["-t", "HOXD70", "-O", "400", "-E", "30"], ["-t", "HOXD55", "-O", "100", "-E", "20"]])
+def test_mode2_example(extra):
+    _assert_same(["-m", "2"] + extra + [os.path.join(EXAMPLE, "reads.fa"), os.path.join(EXAMPLE, "graph.gfa")])
+
+
+@pytest.mark.parametrize("name", ["small", "mid", "short_reads", "long_read"])
+@pytest.mark.parametrize("extra", [[], ["-b", "5", "-f", "0.1"], ["-b", "3000"], ["-O", "6", "-E", "1"]])
+def test_mode2_synthetic(synth_files, name, extra):
+    fa, gfa = synth_files[name]
+    _assert_same(["-m", "2"] + extra + [fa, gfa])
+
+
+def test_mode2_reference_unit_vectors():
+    """The reference's inline tests (gap_global_abpoa.rs:465-756) through rg_set_lnz_graph on the GPU."""
+    from recgraph_b200 import Aligner
+    from tests.test_oracle_golden import POA_CASES
+    al = Aligner()
+    for variant, (lnz, nwp, preds), read, scores, o, e, bta, expected, cite in POA_CASES:
+        if variant != 2:
+            continue
+        table = [[0] * 6 for _ in range(6)]
+        idx = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 4, "-": 5}
+        for (a, b), v in scores.items():
+            table[idx[a]][idx[b]] = v
+        al.set_lnz_graph(lnz, nwp, preds)
+        al.set_scoring(table=table, gap_open=-o, gap_ext=-e, fixed_bta=bta)
+        recs, _ = al.align(2, [read[1:]])
+        assert recs[0].status & 4 == 0, cite
+        assert recs[0].score == expected, cite
+
+
+def test_empty_batch_and_errors():
+    from recgraph_b200 import Aligner, RecGraphError
+    import numpy as np
+    al = Aligner()
+    with pytest.raises(RecGraphError):
+        al.align(2, ["ACGT"])  # no graph yet
+    al.load_gfa(os.path.join(EXAMPLE, "graph.gfa"))
+    res = al.align_packed(2, np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    assert res.n_reads == 0
+    with pytest.raises(RecGraphError):
+        al.align(2, ["ACGTXX"])
