@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of recgraph_b200 (contract in the task statement, tier framing ④).
+
+Workload (BASELINE.json configs[1], "C2"): `-m 2` affine-gap adaptive-banded POA, synthetic 100 kbp graph,
+10 000 reads of 1 kbp at 5 % error, CLI-default scoring (M=2 X=4 O=4 E=2 b=1 f=0.01). One step = one pass of
+the hot path (DP + traceback kernels) over the whole batch. Weak scaling: every rank aligns its own 10 000 reads
+against its own replica of the graph; no collective on the data path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R] [--graph-bp B]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODE = 2
+METRIC = "reads/s, -m 2 (affine-gap banded POA), synthetic 100 kbp graph, 10k x 1 kbp reads"
+
+
+def build_workload(args, rank):
+    from recgraph_b200 import synth
+    g = synth.make_graph(args.graph_bp, 8, seed=1)
+    reads = synth.make_reads(g, args.reads, args.read_len, err=0.05, seed=3 + rank)
+    return g, reads
+
+
+def clocks_sampler(stop, out, device_index):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(device_index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 7:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(int(float(s[0])) for s in samples)
+    reasons = set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for s in samples:
+        for k, nm in enumerate(names):
+            if s[3 + k].lower().startswith("active"):
+                reasons.add(nm)
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(samples[0][1])), "reasons": sorted(reasons),
+            "samples": len(samples)}
+
+
+def cpu_oracle_run(gfa_path, reads, cores, per_core, tmpdir, tag):
+    """Time the CPU oracle (oracle/_build/recgraph_oracle, a faithful single-threaded port of the reference, which
+    cannot be compiled here) with one process per host core over read shards. Returns (reads, seconds)."""
+    from tests import oracle_lib
+    oracle_lib.build()
+    exe = os.path.join(ROOT, "oracle", "_build", "recgraph_oracle")
+    from recgraph_b200 import synth
+    procs = []
+    n = 0
+    for c in range(cores):
+        shard = reads[c * per_core:(c + 1) * per_core]
+        if not shard:
+            break
+        fa = os.path.join(tmpdir, f"{tag}_{c}.fa")
+        with open(fa, "w") as f:
+            f.write(synth.fasta(shard))
+        n += len(shard)
+        procs.append((fa,))
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([exe, "-m", str(MODE), fa, gfa_path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+          for (fa,) in procs]
+    for p in ps:
+        p.wait()
+    dt = time.perf_counter() - t0
+    if any(p.returncode != 0 for p in ps):
+        raise RuntimeError("oracle process failed")
+    return n, dt
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores. The Rust reference
+    cannot be built in this image (no cargo/rustc, un-vendored crates), so this times the oracle port."""
+    if rank != 0:
+        return
+    g, reads = build_workload(args, 0)
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as d:
+        gfa = os.path.join(d, "g.gfa")
+        open(gfa, "w").write(g.gfa())
+        per_core = 1
+        for w in range(args.warmup):
+            cpu_oracle_run(gfa, reads[:cores], cores, per_core, d, f"w{w}")
+            if args.warmup > 1:
+                break  # one warm-up pass is enough to page the binary in; keep the run bounded
+        tot_n, tot_t = 0, 0.0
+        for k in range(args.steps):
+            lo = (k * cores * per_core) % max(1, len(reads) - cores * per_core)
+            n, dt = cpu_oracle_run(gfa, reads[lo:lo + cores * per_core], cores, per_core, d, f"s{k}")
+            tot_n += n
+            tot_t += dt
+    value = tot_n / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} reads per step (1 per core, one oracle process per core), {args.steps} steps"},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"C2: -m 2, synthetic {args.graph_bp} bp graph (SNP/indel bubbles), {args.reads} reads x "
+                        f"{args.read_len} bp, 5% error, M=2 X=4 O=4 E=2 b=1 f=0.01",
+            "reads_per_gpu": args.reads, "graph_bp": args.graph_bp, "read_len": args.read_len,
+            "l2_policy": "inputs larger than L2: every step rewrites > 100 GB of traceback work-space, nothing of a "
+                         "previous step can stay in the 126 MB L2",
+            "parallelism": "read-sharded, graph replicated per GPU, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--reads", type=int, default=10000)
+    ap.add_argument("--read-len", type=int, default=1000)
+    ap.add_argument("--graph-bp", type=int, default=100000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (recgraph_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from recgraph_b200 import Aligner
+    g, reads = build_workload(args, rank)
+    al = Aligner(local_rank)
+    al.load_gfa_text(g.gfa())
+    al.set_scoring()
+    codes, off = al.pack_reads(reads)
+    # pinned host staging for the end-to-end leg
+    codes_pin = torch.from_numpy(codes).pin_memory()
+    off_pin = torch.from_numpy(off.view(np.int64)).pin_memory()
+    codes_h, off_h = codes_pin.numpy(), off_pin.numpy().view(np.uint64)
+
+    al.upload(codes_h, off_h)
+    for _ in range(max(args.warmup, 3)):
+        al.align_staged(MODE)
+    res = al.fetch()
+    cells_per_step = sum(res.reads[i].cells for i in range(res.n_reads))
+    bad = sum(1 for i in range(res.n_reads) if res.reads[i].status & ~1)
+    runs_per_step = int(res.n_runs_total)
+    if bad:
+        raise SystemExit(f"{bad} reads ended with an error status")
+
+    # ---- timed: inputs resident in HBM
+    samples, stop = [], threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
+    th.start()
+    barrier()
+    t0 = time.perf_counter()
+    kernel_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        al.align_staged(MODE)
+        ms, nl, _c = al.kernel_stats()
+        kernel_ms += ms
+        launches += nl
+    barrier()
+    t1 = time.perf_counter()
+    stop.set()
+    th.join()
+    dt = t1 - t0
+
+    # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H of records and runs)
+    al.align_packed(MODE, codes_h, off_h)  # warm
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        r2 = al.align_packed(MODE, codes_h, off_h)
+    barrier()
+    e1 = time.perf_counter()
+    de = e1 - e0
+    h2d = int(codes_h.nbytes + off_h.nbytes + 4 * args.reads)
+    d2h = int(args.reads * 80 + int(r2.n_runs_total) * 8)
+
+    tdev = torch.tensor([dt, de, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tdev, op=dist.ReduceOp.MAX)
+    dt, de, kernel_ms = [float(x) for x in tdev.tolist()]
+    total_reads = args.reads * world * args.steps
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    line = None
+    if rank == 0:
+        ip = al.int_peak()
+        int_peak_gops = max(ip["iadd3_gops"], ip["vimnmx_gops"], 2 * ip["viaddmnmx_gops"])
+        cells_s = cells_per_step * args.steps / (kernel_ms * 1e-3)  # per GPU, device time of the dominant kernel
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_poa_gap_global")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": total_reads / dt, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args),
+            "gcups": cells_per_step * world * args.steps / dt / 1e9,
+            "cells_per_step_per_gpu": cells_per_step,
+            "e2e": {"value": total_reads / de, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * de / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": summarize_clocks(samples),
+            "roofline": {"bound": "hbm", "achieved": cells_s * 1.0 / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": cells_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k_poa_gap_global",
+                         "note": "algorithmic bytes = 1 B traceback code per DP cell (SURVEY 8d); the kernel is "
+                                 "INT32-issue bound, see roofline_int32"},
+            "roofline_int32": {"bound": "int32_alu", "achieved": cells_s * 9 / 1e9, "peak": int_peak_gops,
+                               "unit": "Gop/s", "frac": cells_s * 9 / 1e9 / int_peak_gops,
+                               "ops_per_cell": 9, "peak_source": "rg_int_peak microbenchmark on this GPU "
+                               "(max of IADD3, VIMNMX, 2 x VIADDMNMX rates)", "int_peak": ip,
+                               "kernel_ms_per_step": kernel_ms / args.steps},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            with tempfile.TemporaryDirectory() as d:
+                gfa = os.path.join(d, "g.gfa")
+                open(gfa, "w").write(g.gfa())
+                per_core = 2
+                n, t = cpu_oracle_run(gfa, reads[:cores * per_core], cores, per_core, d, "cb")
+            line["cpu_baseline"] = {"value": n / t, "unit": "reads/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {n} reads of the workload, {per_core} per core, one "
+                                              f"single-threaded oracle process per core ({t:.1f} s wall)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

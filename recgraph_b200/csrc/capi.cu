@@ -112,7 +112,8 @@ struct rg_ctx {
     bool results_ready = false;
     double kernel_ms = 0;
     uint64_t launches = 0, cells = 0;
-    double trace_scale = 1.0;  // grown after an overflow
+    uint32_t slots_used = 0;
+    PinnedBuf<unsigned long long> h_counters;
 
     int fail(int code, const std::string& msg) {
         last_error = msg;
@@ -197,6 +198,10 @@ int rg_init(int device, rg_ctx** out) {
     }
     rg_default_scoring(&c->scoring);
     rg_set_scoring(c, &c->scoring);
+    if (!c->h_counters.ensure(4)) {
+        delete c;
+        return RG_ERR_NOMEM;
+    }
     *out = c;
     return RG_OK;
 }
@@ -325,31 +330,42 @@ static int align_poa(rg_ctx* c, int mode) {
     const int trace_bytes = f.max_indeg <= 4 ? 1 : 2;
     if (f.max_indeg > 64) return c->fail(RG_ERR_UNSUPPORTED, "in-degree above 64 is outside the trace-code domain");
     const uint32_t wstride = (Lmax + 31) & ~31u;
+    int ws_cols = 64, blocks_per_sm = 1;
+    int lc = poa_launch_config(mode, trace_bytes, Lmax, &ws_cols, &blocks_per_sm);
+    if (lc == -2) return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
+    if (lc != 0) return c->cuda_fail("kernel configuration");
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // band half-width of the longest read, for the trace estimate
-    uint32_t bta = c->scoring.fixed_bta >= 0 ? (uint32_t)c->scoring.fixed_bta
-                                             : bases_to_add(c->scoring.extra_b, c->scoring.extra_f, Lmax);
-    const uint64_t full = (uint64_t)n * Lmax;
-    for (int attempt = 0; attempt < 6; attempt++) {
-        double est = ((double)n * (2.0 * std::min<uint32_t>(bta, Lmax) + 24.0) + 1.5 * (double)Lmax * Lmax) * c->trace_scale;
-        uint64_t trace_cap = (uint64_t)std::min<double>((double)full, est);
-        trace_cap = std::max<uint64_t>(trace_cap, 4096);
-        trace_cap = std::min<uint64_t>(trace_cap, 0x7fffff00ull);
-        trace_cap = (trace_cap + 255) & ~255ull;
-        const uint32_t run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)(n / 4 + 2 * Lmax)), 1u << 22);
-        const size_t per_slot = (size_t)n * sizeof(RowMeta) + (size_t)c->dg.ring * wstride * 8 +
-                                trace_cap * trace_bytes + (size_t)run_cap * sizeof(rg_run);
-        uint32_t want_slots = (uint32_t)c->sms * 32;  // 4 blocks of 8 warps per SM
-        want_slots = std::min<uint32_t>(want_slots, (uint32_t)((c->n_reads + 7) / 8 * 8));
-        want_slots = std::max<uint32_t>(want_slots, 8);
-        size_t budget = (size_t)(free_b * 0.80);
-        size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(run_cap, 16384), (budget / 4) / sizeof(rg_run));
-        out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
-        size_t avail = budget - out_runs_cap * sizeof(rg_run);
-        uint32_t slots = (uint32_t)std::min<size_t>(want_slots, avail / per_slot);
-        slots = slots / 8 * 8;
-        if (slots < 8) return c->fail(RG_ERR_NOMEM, "not enough device memory for one block of reads in flight");
+    // memory already held by this ctx's work-space is reusable
+    free_b += (c->d_rowmeta.cap * sizeof(RowMeta)) + (c->d_ring_m.cap + c->d_ring_y.cap) * 4 + c->d_trace.cap +
+              (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
+    const uint64_t full = std::min<uint64_t>((uint64_t)n * Lmax, 0x7fffff00ull);  // the band can open to the whole row
+    const uint32_t run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)(n / 4 + 2 * Lmax)), 1u << 22);
+    const size_t per_slot_fixed = (size_t)n * sizeof(RowMeta) + (size_t)c->dg.ring * wstride * 8 + (size_t)run_cap * sizeof(rg_run);
+    const size_t budget_all = (size_t)(free_b * 0.85);
+    size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(run_cap, 16384), (budget_all / 8) / sizeof(rg_run));
+    out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
+    const size_t budget = budget_all - out_runs_cap * sizeof(rg_run);
+    const uint32_t reads8 = (uint32_t)((c->n_reads + 7) / 8 * 8);
+    uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * blocks_per_sm * 8, reads8);
+    for (int attempt = 0; attempt < 8; attempt++) {
+        // Reads in flight are limited by trace memory: prefer the full n x L trace per slot (never overflows),
+        // shrink the number of slots down to one block per SM before shrinking the trace.
+        uint64_t trace_cap = full;
+        size_t per_slot = per_slot_fixed + (size_t)trace_cap * trace_bytes;
+        if ((size_t)slots * per_slot > budget) {
+            uint32_t min_slots = std::min<uint32_t>(slots, std::max<uint32_t>(8, (uint32_t)c->sms * 8 >> attempt));
+            uint32_t fit = (uint32_t)std::min<size_t>(budget / per_slot, 1u << 20) / 8 * 8;
+            if (fit >= min_slots) {
+                slots = fit;
+            } else {
+                slots = min_slots;
+                size_t each = budget / slots;
+                if (each <= per_slot_fixed + 4096) return c->fail(RG_ERR_NOMEM, "not enough device memory for the alignment work-space");
+                trace_cap = std::min<uint64_t>(full, (each - per_slot_fixed) / trace_bytes);
+            }
+        }
+        trace_cap &= ~255ull;
         bool ok = c->d_rowmeta.ensure((size_t)slots * n) && c->d_ring_m.ensure((size_t)slots * c->dg.ring * wstride) &&
                   c->d_ring_y.ensure((size_t)slots * c->dg.ring * wstride) &&
                   c->d_trace.ensure((size_t)slots * trace_cap * trace_bytes) &&
@@ -377,28 +393,28 @@ static int align_poa(rg_ctx* c, int mode) {
         b.counters = c->d_counters.p;
         cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
         cudaEventRecord(c->ev0, c->stream);
-        int rc = launch_poa(mode, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), 256, c->stream);
+        int rc = launch_poa(mode, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), ws_cols, c->stream);
         cudaEventRecord(c->ev1, c->stream);
-        if (rc == -2) return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
         if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("alignment kernel");
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         c->kernel_ms += ms;
         c->launches += 1;
+        c->slots_used = slots;
         // overflow check needs the statuses: cheap D2H of the records
         if (!c->h_results.ensure(c->n_reads + 1)) return c->fail(RG_ERR_NOMEM, "pinned allocation failed");
         cudaMemcpyAsync(c->h_results.p, c->d_results.p, (size_t)c->n_reads * sizeof(rg_read_result), cudaMemcpyDeviceToHost, c->stream);
-        unsigned long long counters[4];
-        cudaMemcpyAsync(counters, c->d_counters.p, sizeof counters, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("result copy");
         bool overflow = false;
         for (int32_t i = 0; i < c->n_reads; i++)
             if (c->h_results.p[i].status & RG_READ_TRACE_OVERFLOW) overflow = true;
-        c->n_runs_total = std::min<uint64_t>(counters[1], out_runs_cap);
+        c->n_runs_total = std::min<uint64_t>(c->h_counters.p[1], out_runs_cap);
         if (!overflow) return RG_OK;
-        if (trace_cap >= full && counters[1] <= out_runs_cap && run_cap >= (1u << 22))
-            return c->fail(RG_ERR_NOMEM, "trace buffers overflow at maximum size");
-        c->trace_scale *= 4.0;  // whole batch is re-run with larger per-slot buffers (rare; sizes are then remembered)
+        // rare: the whole batch is re-run with fewer reads in flight / larger run buffers
+        if (c->h_counters.p[1] > out_runs_cap) out_runs_cap = std::min<size_t>(c->h_counters.p[1] * 2, (budget_all / 2) / sizeof(rg_run));
+        if (slots <= 8 && trace_cap >= (full & ~255ull)) return c->fail(RG_ERR_NOMEM, "trace buffers overflow at maximum size");
+        slots = std::max<uint32_t>(8, slots / 2 / 8 * 8);
     }
     return c->fail(RG_ERR_NOMEM, "trace buffers still overflow after retries");
 }

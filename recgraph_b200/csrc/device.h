@@ -62,8 +62,9 @@ struct PoaBatch {
 };
 
 // launchers (poa_kernels.cu)
+int poa_launch_config(int mode, int trace_bytes, uint32_t Lmax, int* ws_cols, int* blocks_per_sm);
 int launch_poa(int mode, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
-               int trace_bytes, int blocks, int threads, void* stream);
+               int trace_bytes, int blocks, int ws_cols, void* stream);
 int launch_int_peak(double* iadd, double* imnmx, double* viaddmnmx, void* stream);
 
 }  // namespace rg

@@ -18,7 +18,6 @@
 namespace rg {
 
 #define NEG_INF (-(1 << 30))
-constexpr int WS = 64;           // columns of a row kept in shared memory
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -88,12 +87,14 @@ struct RunEmitter {
 
 template <typename TC, int SB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-    k_poa_gap_global(DevGraph g, DevScoring sc, PoaWorkspace ws, PoaBatch b) {
-    __shared__ int32_t s_m[WARPS_PER_BLOCK][2][WS];
-    __shared__ int32_t s_y[WARPS_PER_BLOCK][2][WS];
+    k_poa_gap_global(DevGraph g, DevScoring sc, PoaWorkspace ws, PoaBatch b, int WS) {
+    // dynamic shared memory: per warp two (m, y) row buffers of WS columns each
+    extern __shared__ int32_t s_dyn[];
     __shared__ int32_t s_sc[48];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
+    int32_t* const s_mw = s_dyn + (size_t)wib * 4 * WS;  // [2][WS] m
+    int32_t* const s_yw = s_mw + 2 * WS;                 // [2][WS] y
     const uint32_t slot = blockIdx.x * WARPS_PER_BLOCK + wib;
     if (threadIdx.x < 48) s_sc[threadIdx.x] = (&sc.sc[0][0])[threadIdx.x];
     __syncthreads();
@@ -177,8 +178,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
             const int cur = i & 1;
             const bool to_smem = W <= (uint32_t)WS;
             const bool to_ring = (rf & RF_IS_PRED) || !to_smem;
-            int32_t* cur_m = to_smem ? s_m[wib][cur] : nullptr;
-            int32_t* cur_y = to_smem ? s_y[wib][cur] : nullptr;
+            int32_t* cur_m = s_mw + cur * WS;
+            int32_t* cur_y = s_yw + cur * WS;
             int32_t* rg_m = ring_m + (size_t)(i & RM) * ws.wstride;
             int32_t* rg_y = ring_y + (size_t)(i & RM) * ws.wstride;
             const bool prev_in_smem = (prev_right - prev_left) <= (uint32_t)WS;
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                                 lp = prev_left;
                                 rp = prev_right;
                                 if (prev_in_smem) {
-                                    mp = s_m[wib][cur ^ 1];
-                                    yp = s_y[wib][cur ^ 1];
+                                    mp = s_mw + (cur ^ 1) * WS;
+                                    yp = s_yw + (cur ^ 1) * WS;
                                 } else {
                                     mp = ring_m + (size_t)(p & RM) * ws.wstride;
                                     yp = ring_y + (size_t)(p & RM) * ws.wstride;
@@ -502,15 +503,36 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     }
 }
 
+static const void* poa_kernel(int mode, int trace_bytes) {
+    if (mode == RG_MODE_GAP_GLOBAL)
+        return trace_bytes == 1 ? (const void*)k_poa_gap_global<uint8_t, 2> : (const void*)k_poa_gap_global<uint16_t, 6>;
+    return nullptr;
+}
+
+// Shared-memory row width and resident blocks per SM for a batch whose longest read has Lmax columns.
+int poa_launch_config(int mode, int trace_bytes, uint32_t Lmax, int* ws_cols, int* blocks_per_sm) {
+    const void* k = poa_kernel(mode, trace_bytes);
+    if (!k) return -2;
+    int ws = 64;
+    while (ws < (int)Lmax && ws < 1536) ws += 64;  // 8 warps * 4 rows * 1536 cols * 4 B = 192 KB
+    size_t smem = (size_t)WARPS_PER_BLOCK * 4 * ws * sizeof(int32_t);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, WARPS_PER_BLOCK * 32, smem) != cudaSuccess) return -1;
+    *ws_cols = ws;
+    *blocks_per_sm = nb < 1 ? 1 : nb;
+    return 0;
+}
+
 int launch_poa(int mode, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
-               int trace_bytes, int blocks, int threads, void* stream) {
+               int trace_bytes, int blocks, int ws_cols, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    (void)threads;
+    size_t smem = (size_t)WARPS_PER_BLOCK * 4 * ws_cols * sizeof(int32_t);
     if (mode == RG_MODE_GAP_GLOBAL) {
         if (trace_bytes == 1)
-            k_poa_gap_global<uint8_t, 2><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+            k_poa_gap_global<uint8_t, 2><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b, ws_cols);
         else
-            k_poa_gap_global<uint16_t, 6><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+            k_poa_gap_global<uint16_t, 6><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b, ws_cols);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
     return -2;

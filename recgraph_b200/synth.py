@@ -111,27 +111,26 @@ def path_from_picks(structure, choices, pick):
 
 
 def mutate(rng, seq, err):
-    """Substitution / insertion / deletion at total rate err, 1:1:1."""
-    if err <= 0:
+    """Substitution / insertion / deletion at total rate err, 1:1:1 (vectorised)."""
+    if err <= 0 or not seq:
         return seq
-    out = bytearray()
-    r = rng.random(len(seq))
-    kinds = rng.integers(0, 3, size=len(seq))
-    subs = rng.integers(1, 4, size=len(seq))
-    ins = rng.integers(0, 4, size=len(seq))
-    idx = {65: 0, 67: 1, 71: 2, 84: 3}
-    for i, c in enumerate(seq):
-        if r[i] < err:
-            k = kinds[i]
-            if k == 0:
-                out.append(BASES[(idx[c] + subs[i]) % 4])
-            elif k == 1:
-                out.append(BASES[ins[i]])
-                out.append(c)
-            # k == 2: deletion
-        else:
-            out.append(c)
-    return bytes(out)
+    a = np.frombuffer(seq, dtype=np.uint8)
+    n = len(a)
+    mut = rng.random(n) < err
+    kinds = rng.integers(0, 3, size=n)
+    cnt = np.ones(n, dtype=np.int64)
+    is_sub, is_ins, is_del = mut & (kinds == 0), mut & (kinds == 1), mut & (kinds == 2)
+    cnt[is_ins] = 2
+    cnt[is_del] = 0
+    lut = np.zeros(256, dtype=np.uint8)
+    lut[[65, 67, 71, 84]] = [0, 1, 2, 3]
+    sub = BASES[(lut[a] + rng.integers(1, 4, size=n)) % 4]
+    ins = BASES[rng.integers(0, 4, size=n)]
+    first = np.where(is_sub, sub, np.where(is_ins, ins, a))
+    out = np.repeat(first, cnt)
+    pos = np.cumsum(cnt) - 1
+    out[pos[is_ins]] = a[is_ins]  # inserted base first, then the original one
+    return out.tobytes()
 
 
 def make_reads(g, n_reads, read_len, err=0.05, seed=3, mosaic_breaks=0, exact_len=True):
