@@ -1,0 +1,28 @@
+"""One short pass of the hot path for ncu (never a bench number)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from recgraph_b200 import Aligner, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--mode", type=int, default=2)
+ap.add_argument("--reads", type=int, default=1184)
+ap.add_argument("--read-len", type=int, default=1000)
+ap.add_argument("--graph-bp", type=int, default=100000)
+ap.add_argument("--paths", type=int, default=8)
+ap.add_argument("--passes", type=int, default=1)
+a = ap.parse_args()
+g = synth.make_graph(a.graph_bp, a.paths, seed=1)
+reads = synth.make_reads(g, a.reads, a.read_len, err=0.05, seed=3)
+al = Aligner(0)
+al.load_gfa_text(g.gfa())
+al.set_scoring()
+codes, off = al.pack_reads(reads)
+al.upload(codes, off)
+for _ in range(a.passes):
+    al.align_staged(a.mode)
+    print("kernel_ms, launches, cells:", al.kernel_stats())
+res = al.fetch()
+print("cells", sum(res.reads[i].cells for i in range(res.n_reads)))
