@@ -339,7 +339,7 @@ static int align_poa(rg_ctx* c, int mode) {
     // memory already held by this ctx's work-space is reusable
     free_b += (c->d_rowmeta.cap * sizeof(RowMeta)) + (c->d_ring_m.cap + c->d_ring_y.cap) * 4 + c->d_trace.cap +
               (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
-    const uint64_t full = std::min<uint64_t>((uint64_t)n * Lmax, 0x7fffff00ull);  // the band can open to the whole row
+    const uint64_t full = std::min<uint64_t>((uint64_t)n * Lmax, 0x7ffffe00ull);  // the band can open to the whole row
     const uint32_t run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)(n / 4 + 2 * Lmax)), 1u << 22);
     const size_t per_slot_fixed = (size_t)n * sizeof(RowMeta) + (size_t)c->dg.ring * wstride * 8 + (size_t)run_cap * sizeof(rg_run);
     const size_t budget_all = (size_t)(free_b * 0.85);
@@ -365,7 +365,7 @@ static int align_poa(rg_ctx* c, int mode) {
                 trace_cap = std::min<uint64_t>(full, (each - per_slot_fixed) / trace_bytes);
             }
         }
-        trace_cap &= ~255ull;
+        trace_cap = (trace_cap + 255) & ~255ull;  // round UP: `full` must always fit
         bool ok = c->d_rowmeta.ensure((size_t)slots * n) && c->d_ring_m.ensure((size_t)slots * c->dg.ring * wstride) &&
                   c->d_ring_y.ensure((size_t)slots * c->dg.ring * wstride) &&
                   c->d_trace.ensure((size_t)slots * trace_cap * trace_bytes) &&
@@ -413,7 +413,7 @@ static int align_poa(rg_ctx* c, int mode) {
         if (!overflow) return RG_OK;
         // rare: the whole batch is re-run with fewer reads in flight / larger run buffers
         if (c->h_counters.p[1] > out_runs_cap) out_runs_cap = std::min<size_t>(c->h_counters.p[1] * 2, (budget_all / 2) / sizeof(rg_run));
-        if (slots <= 8 && trace_cap >= (full & ~255ull)) return c->fail(RG_ERR_NOMEM, "trace buffers overflow at maximum size");
+        if (slots <= 8 && trace_cap >= full) return c->fail(RG_ERR_NOMEM, "trace buffers overflow at maximum size");
         slots = std::max<uint32_t>(8, slots / 2 / 8 * 8);
     }
     return c->fail(RG_ERR_NOMEM, "trace buffers still overflow after retries");
