@@ -113,6 +113,7 @@ struct rg_ctx {
     double kernel_ms = 0;
     uint64_t launches = 0, cells = 0;
     uint32_t slots_used = 0;
+    bool force_striped = getenv("RG_FORCE_STRIPED") != nullptr;  // testing: keep the generic striped kernel
     PinnedBuf<unsigned long long> h_counters;
 
     int fail(int code, const std::string& msg) {
@@ -329,9 +330,18 @@ static int align_poa(rg_ctx* c, int mode) {
     const uint32_t Lmax = c->max_len + 1;
     const int trace_bytes = f.max_indeg <= 4 ? 1 : 2;
     if (f.max_indeg > 64) return c->fail(RG_ERR_UNSUPPORTED, "in-degree above 64 is outside the trace-code domain");
-    const uint32_t wstride = (Lmax + 31) & ~31u;
+    uint32_t wstride = (Lmax + 31) & ~31u;
     int ws_cols = 64, blocks_per_sm = 1;
-    int lc = poa_launch_config(mode, trace_bytes, Lmax, &ws_cols, &blocks_per_sm);
+    // register-blocked kernel (lane-owned column blocks) whenever the longest read fits 32*C columns
+    const int blkC = (mode == RG_MODE_GAP_GLOBAL && !c->force_striped) ? gap_blk_cols(Lmax) : 0;
+    int lc;
+    if (blkC) {
+        wstride = 32u * blkC;
+        lc = gap_blk_blocks_per_sm(blkC, trace_bytes, &blocks_per_sm);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    } else {
+        lc = poa_launch_config(mode, trace_bytes, Lmax, &ws_cols, &blocks_per_sm);
+    }
     if (lc == -2) return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
     if (lc != 0) return c->cuda_fail("kernel configuration");
     size_t free_b = 0, total_b = 0;
@@ -339,7 +349,8 @@ static int align_poa(rg_ctx* c, int mode) {
     // memory already held by this ctx's work-space is reusable
     free_b += (c->d_rowmeta.cap * sizeof(RowMeta)) + (c->d_ring_m.cap + c->d_ring_y.cap) * 4 + c->d_trace.cap +
               (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
-    const uint64_t full = std::min<uint64_t>((uint64_t)n * Lmax, 0x7ffffe00ull);  // the band can open to the whole row
+    const uint64_t full = blkC ? (uint64_t)n * wstride  // fixed row stride, absolute columns
+                              : std::min<uint64_t>((uint64_t)n * Lmax, 0x7ffffe00ull);  // the band can open to the whole row
     const uint32_t run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)(n / 4 + 2 * Lmax)), 1u << 22);
     const size_t per_slot_fixed = (size_t)n * sizeof(RowMeta) + (size_t)c->dg.ring * wstride * 8 + (size_t)run_cap * sizeof(rg_run);
     const size_t budget_all = (size_t)(free_b * 0.85);
@@ -393,7 +404,9 @@ static int align_poa(rg_ctx* c, int mode) {
         b.counters = c->d_counters.p;
         cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
         cudaEventRecord(c->ev0, c->stream);
-        int rc = launch_poa(mode, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), ws_cols, c->stream);
+        if (blkC && trace_cap < full) return c->fail(RG_ERR_NOMEM, "not enough device memory for the blocked kernel's trace");
+        int rc = blkC ? launch_gap_global_blk(blkC, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), c->stream)
+                      : launch_poa(mode, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), ws_cols, c->stream);
         cudaEventRecord(c->ev1, c->stream);
         if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("alignment kernel");
         float ms = 0;

@@ -65,6 +65,11 @@ struct PoaBatch {
 int poa_launch_config(int mode, int trace_bytes, uint32_t Lmax, int* ws_cols, int* blocks_per_sm);
 int launch_poa(int mode, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
                int trace_bytes, int blocks, int ws_cols, void* stream);
+// register-blocked mode-2 kernel (poa_gap_blk.cu)
+int gap_blk_cols(uint32_t Lmax);
+int gap_blk_blocks_per_sm(int C, int trace_bytes, int* nb);
+int launch_gap_global_blk(int C, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
+                          int trace_bytes, int blocks, void* stream);
 int launch_int_peak(double* iadd, double* imnmx, double* viaddmnmx, void* stream);
 
 }  // namespace rg

@@ -1,0 +1,521 @@
+// Mode 2 (gap_global_abpoa.rs:11-250), register-blocked variant for reads of up to 32*C columns.
+//
+// One warp per read in flight. Lane t OWNS the C contiguous DP columns [t*C, (t+1)*C) for the whole read: the
+// previous row's m / y values of those columns stay in registers from row to row (no shared or global traffic on
+// rows inside a segment), every per-cell step is fully unrolled straight-line integer code, and the horizontal
+// affine dependency x[c] = max(x[c-1] + c1, h[c-1] + c2) is resolved by an in-lane chain plus ONE cross-lane
+// max-plus scan per row. Rows that are predecessors of later segment starts are written to an L2-resident ring
+// (absolute column index, NEG_INF outside the band) and gathered from there on segment-start rows.
+// Traceback codes are packed and written with one or two 128-bit stores per lane and row, at the fixed address
+// row * 32C + column, so the traceback needs no per-row offset lookup.
+#include <cuda_runtime.h>
+
+#include "device.h"
+#include "poa_common.cuh"
+
+namespace rg {
+
+#define NEGH (NEG_INF / 2)  // anything below is "no value"
+
+template <int C, typename TC>
+__device__ __forceinline__ void store_codes(TC* dst, const unsigned (&code)[C]) {
+    constexpr int PER = 4 / sizeof(TC);  // codes per 32-bit word
+    constexpr int NW = C / PER;
+    unsigned w[NW];
+#pragma unroll
+    for (int j = 0; j < NW; j++) {
+        unsigned v = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) v |= code[j * PER + q] << (q * 8 * sizeof(TC));
+        w[j] = v;
+    }
+    if constexpr (NW >= 4) {
+#pragma unroll
+        for (int j = 0; j < NW; j += 4) reinterpret_cast<uint4*>(dst)[j / 4] = make_uint4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+    } else if constexpr (NW == 2) {
+        reinterpret_cast<uint2*>(dst)[0] = make_uint2(w[0], w[1]);
+    } else {
+        reinterpret_cast<unsigned*>(dst)[0] = w[0];
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void store_row(int32_t* dst, const int (&v)[C]) {
+#pragma unroll
+    for (int j = 0; j < C; j += 4) reinterpret_cast<int4*>(dst)[j / 4] = make_int4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+
+template <int C, typename TC, int SB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+    k_gap_global_blk(DevGraph g, DevScoring sc, PoaWorkspace ws, PoaBatch b) {
+    static_assert(C % 4 == 0, "C must be a multiple of 4");
+    constexpr int STRIDE = 32 * C;
+    constexpr unsigned SMASK = (1u << SB) - 1;
+    __shared__ int32_t s_sc[48];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t slot = blockIdx.x * WARPS_PER_BLOCK + wib;
+    if (threadIdx.x < 48) s_sc[threadIdx.x] = (&sc.sc[0][0])[threadIdx.x];
+    __syncthreads();
+    if (slot >= ws.slots) return;
+
+    const uint32_t n = g.n;
+    const uint32_t RM = g.ring - 1;
+    RowMeta* rowmeta = ws.rowmeta + (size_t)slot * n;
+    int32_t* ring_m = ws.ring_m + (size_t)slot * g.ring * STRIDE;
+    int32_t* ring_y = ws.ring_y + (size_t)slot * g.ring * STRIDE;
+    TC* trace = reinterpret_cast<TC*>(ws.trace) + (size_t)slot * ws.trace_cap;
+    rg_run* runs = ws.runs + (size_t)slot * ws.run_cap;
+    const int o = sc.o, e = sc.e;
+    const int c1 = e + max(o, 0), c2 = o + e;
+    const int cbase = lane * C;
+
+    for (;;) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&b.counters[0], 1ull);
+        ticket = __shfl_sync(FULL, ticket, 0);
+        if (ticket >= (unsigned long long)b.n_reads) break;
+        const int ridx = b.order ? b.order[ticket] : (int)ticket;
+        const uint8_t* read = b.reads + b.read_off[ridx];
+        const int32_t L = (int32_t)(b.read_off[ridx + 1] - b.read_off[ridx]) + 1;  // includes '$'
+        int32_t bta;
+        if (sc.fixed_bta >= 0)
+            bta = sc.fixed_bta;
+        else {
+            float v = __fadd_rn(sc.b, __fmul_rn(sc.f, (float)L));  // (b + f * L as f32) as usize, main.rs:175
+            bta = !(v > 0.0f) ? 0 : (v >= 536870912.0f ? (1 << 29) : (int32_t)v);
+        }
+        bta = min(bta, 1 << 29);
+
+        rg_read_result res;
+        res.status = 0;
+        res.score = 0;
+        res.score_f32 = 0.f;
+        res.displacement = 0;
+        res.end_row = res.end_col = res.start_row = res.start_col = 0;
+        res.best_path = res.rev_best_path = 0;
+        res.fen = res.rsn = res.rec_col = res.rev_end_row = 0;
+        res.cells = 0;
+        res.run_off = 0;
+        res.n_runs = 0;
+        res.n_runs_rev = 0;
+        if (L > STRIDE || (uint64_t)n * STRIDE > ws.trace_cap) {  // host sizes the launch so that this never happens
+            res.status = RG_READ_TRACE_OVERFLOW;
+            if (lane == 0) b.results[ridx] = res;
+            continue;
+        }
+
+        // read codes of my columns (column c aligns read[c-1]); N (4) for padding
+        unsigned rcw[C / 4];
+#pragma unroll
+        for (int j = 0; j < C / 4; j++) {
+            unsigned w = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int c = cbase + j * 4 + q;
+                unsigned code = (c >= 1 && c < L) ? read[c - 1] : 4u;
+                w |= code << (8 * q);
+            }
+            rcw[j] = w;
+        }
+
+        int A[C], B[C];  // previous row: m and y of my columns (NEG_INF outside its band)
+        int status = 0;
+        uint64_t cells = 0;
+        uint32_t prev_bsp = 0;
+        int best_end_val = NEG_INF;
+        uint32_t best_end_row = 0;
+        int last_val = 0;
+        bool abort_read = false;
+
+        for (uint32_t i = 0; i + 1 < n; i++) {
+            const uint8_t rf = g.rowflags[i];
+            const bool nwp = rf & RF_NWP;
+            const uint32_t pb = g.pred_off[i], pe = nwp ? g.pred_off[i + 1] : pb;
+            uint32_t ms, me;
+            if (i == 0) {
+                ms = 0;
+                me = 0;
+            } else if (!nwp) {
+                ms = me = prev_bsp + 1;
+            } else {
+                uint32_t pl = 0xffffffffu, pr = 0;
+                for (uint32_t k = pb; k < pe; k++) {
+                    uint32_t p = g.pred_idx[k];
+                    uint32_t bs = (p == i - 1) ? prev_bsp : rowmeta[p].bsp;
+                    pl = min(pl, bs);
+                    pr = max(pr, bs);
+                }
+                ms = pl + 1;
+                me = pr + 1;
+            }
+            uint32_t left, right;
+            band_for_row(ms, me, g.r_values[i], L, bta, left, right);
+            if (right <= left) {  // reference: empty row -> index / subtract-overflow panic later on
+                status |= RG_READ_REF_PANIC;
+                abort_read = true;
+                break;
+            }
+            cells += right - left;
+            const int li = g.lnz[i];
+            const int best_p = (int)g.min_pred[i];
+            const unsigned mps = g.min_pred_slot[i];
+            unsigned code[C];
+            int bestv = NEG_INF;
+            int bcol = 0;
+
+            if (i == 0) {
+                // gap_global_abpoa.rs:68-77
+#pragma unroll
+                for (int k = 0; k < C; k++) {
+                    const int c = cbase + k;
+                    const bool act = c < (int)right;
+                    int v = (c == 0) ? 0 : o + e * c;
+                    A[k] = act ? v : NEG_INF;
+                    B[k] = A[k];
+                    code[k] = (c == 0) ? DIR_O : DIR_L;
+                    if (act && v >= bestv) {
+                        bestv = v;
+                        bcol = c;
+                    }
+                }
+            } else {
+                int D[C];         // best predecessor m at column c-1 (diagonal source)
+                unsigned S[C];    // slots: um | uy << 8 | d << 16 (segment-start rows only)
+                unsigned pred0_slot = 0xffffffffu;
+                if (!nwp) {
+                    int up = __shfl_up_sync(FULL, A[C - 1], 1);
+                    if (lane == 0) up = NEG_INF;
+#pragma unroll
+                    for (int k = C - 1; k >= 1; k--) D[k] = A[k - 1];
+                    D[0] = up;
+#pragma unroll
+                    for (int k = 0; k < C; k++) S[k] = 0;
+                } else {
+                    // gather over the predecessor rows (ring, absolute columns, NEG_INF outside their bands);
+                    // first predecessor in list order wins ties (strict >), gap_global_abpoa.rs:266-345
+#pragma unroll
+                    for (int k = 0; k < C; k++) {
+                        A[k] = NEG_INF;
+                        B[k] = NEG_INF;
+                        D[k] = NEG_INF;
+                        S[k] = 0;
+                    }
+                    for (uint32_t q = 0; q < pe - pb; q++) {
+                        const uint32_t p = g.pred_idx[pb + q];
+                        if (p == 0) pred0_slot = q;
+                        const int32_t* mp = ring_m + (size_t)(p & RM) * STRIDE + cbase;
+                        const int32_t* yp = ring_y + (size_t)(p & RM) * STRIDE + cbase;
+                        int carry = (lane == 0) ? NEG_INF : mp[-1];
+#pragma unroll
+                        for (int j = 0; j < C; j += 4) {
+                            int4 mv = reinterpret_cast<const int4*>(mp)[j / 4];
+                            int4 yv = reinterpret_cast<const int4*>(yp)[j / 4];
+                            const int mm[4] = {mv.x, mv.y, mv.z, mv.w};
+                            const int yy[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                            for (int t = 0; t < 4; t++) {
+                                const int k = j + t;
+                                if (mm[t] > A[k]) {
+                                    A[k] = mm[t];
+                                    S[k] = (S[k] & ~0xffu) | q;
+                                }
+                                if (yy[t] > B[k]) {
+                                    B[k] = yy[t];
+                                    S[k] = (S[k] & ~0xff00u) | (q << 8);
+                                }
+                                if (carry > D[k]) {
+                                    D[k] = carry;
+                                    S[k] = (S[k] & ~0xff0000u) | (q << 16);
+                                }
+                                carry = mm[t];
+                            }
+                        }
+                    }
+                }
+                // ---- pass A: vertical (y) and diagonal (d) per cell, independent across cells
+                const int fb0 = 2 * o + e * (best_p + 1);  // gap_global_abpoa.rs:117,139
+                const int32_t* srow = s_sc + li * 8;
+#pragma unroll
+                for (int k = 0; k < C; k++) {
+                    const int c = cbase + k;
+                    const int mu = A[k], uy = B[k];
+                    const bool uav = mu > NEGH;
+                    const int um = mu + o;
+                    const bool yf = uav && (uy > um);
+                    const int yv = uav ? max(um, uy) + e : fb0 + e * c;
+                    const unsigned us = uav ? (yf ? ((S[k] >> 8) & 0xffu) : (S[k] & 0xffu)) : mps;
+                    const int dv = D[k];
+                    const unsigned rc = (rcw[k / 4] >> (8 * (k % 4))) & 0xffu;
+                    const int dd = (dv > NEGH) ? dv + srow[rc] : NEG_INF;
+                    B[k] = yv;
+                    D[k] = dd;
+                    code[k] = (yf ? 8u : 0u) | (((S[k] >> 16) & SMASK) << 4) | ((us & SMASK) << (4 + SB));
+                }
+                // first column (gap_global_abpoa.rs:78-92): x = o + e*(best_p+1), m = x, y stays 0, dir U
+                const bool has_fc = (lane == 0) && left == 0;
+                // ---- pass B: in-lane chain of x over generators G_c = h[c-1] + c2 (seed at c == left)
+                const int seed = (left == 0) ? o + e * (best_p + 1) : fb0 + e * (int)left;
+                int hlast = max(D[C - 1], B[C - 1]);
+                if (cbase + C - 1 < (int)left || cbase + C - 1 >= (int)right) hlast = NEG_INF;
+                int hprev = __shfl_up_sync(FULL, hlast, 1);
+                if (lane == 0) hprev = NEG_INF;
+                int X[C];
+                {
+                    int xl = NEG_INF;
+#pragma unroll
+                    for (int k = 0; k < C; k++) {
+                        const int c = cbase + k;
+                        int hp;
+                        if (k == 0)
+                            hp = hprev;
+                        else {
+                            hp = max(D[k - 1], B[k - 1]);
+                            if (k == 1 && has_fc) hp = NEG_INF;  // the first-column cell has m = x (no d / y candidate)
+                        }
+                        int gen = (c > (int)left && c < (int)right && hp > NEGH) ? hp + c2 : NEG_INF;
+                        if (c == (int)left) gen = seed;
+                        xl = max(xl + c1, gen);
+                        X[k] = xl;
+                    }
+                }
+                // ---- cross-lane max-plus scan: x entering lane t = max over earlier lanes
+                int z = X[C - 1] - (cbase + C - 1) * c1;
+                if (X[C - 1] <= NEGH) z = NEG_INF;
+                int winc = warp_incl_max(z, lane);
+                int wexc = __shfl_up_sync(FULL, winc, 1);
+                if (lane == 0) wexc = NEG_INF;
+                const int xin0 = (wexc > NEGH) ? wexc + cbase * c1 : NEG_INF;
+                // ---- pass C: x, m, direction, flags
+                unsigned xn_bits = 0;
+#pragma unroll
+                for (int k = 0; k < C; k++) {
+                    const int c = cbase + k;
+                    const bool act = c >= (int)left && c < (int)right;
+                    int x = X[k];
+                    if (xin0 > NEGH) x = max(x, xin0 + k * c1);
+                    const bool fc = (k == 0) && has_fc;
+                    const int dd = D[k];
+                    int yv = B[k];
+                    const int ye = fc ? NEG_INF : yv;
+                    const int m = max(max(dd, x), ye);
+                    unsigned dir;
+                    if (dd < x)
+                        dir = (x < ye) ? DIR_U : DIR_L;
+                    else
+                        dir = (dd < ye) ? DIR_U : DIR_D;
+                    if (fc) {
+                        dir = DIR_U;
+                        yv = 0;
+                        code[k] = (mps & SMASK) << (4 + SB);
+                    }
+                    // gap_global_abpoa.rs:153-154: set_path_cell(u_pred, 'u') panics when u_pred == 0
+                    if (nwp && act && !fc && dd > NEGH && dd < x && x < ye && ((code[k] >> (4 + SB)) & SMASK) == pred0_slot) status |= RG_READ_REF_PANIC;
+                    code[k] |= dir;
+                    if (x > m + o) xn_bits |= 1u << k;
+                    A[k] = act ? m : NEG_INF;
+                    B[k] = act ? yv : NEG_INF;
+                    if (act && m >= bestv) {
+                        bestv = m;
+                        bcol = c;
+                    }
+                }
+                // path_x flag of column c: x[c-1] > m[c-1] + o (gap_global_abpoa.rs:358-364), only for c > left
+                unsigned prev_last = __shfl_up_sync(FULL, xn_bits >> (C - 1), 1) & 1u;
+                if (lane == 0) prev_last = 0;
+                unsigned xf = (xn_bits << 1) | prev_last;
+#pragma unroll
+                for (int k = 0; k < C; k++) {
+                    const int c = cbase + k;
+                    if (c > (int)left && c < (int)right && ((xf >> k) & 1u)) code[k] |= 4u;
+                }
+            }
+            // ---- row arg-max, right-most (>=)  (gap_global_abpoa.rs:198-203)
+            const int tmax = __reduce_max_sync(FULL, bestv);
+            const unsigned eq = __ballot_sync(FULL, bestv == tmax && bestv > NEGH);
+            const uint32_t row_bsp = (uint32_t)__shfl_sync(FULL, bcol, 31 - __clz(eq));
+            // ---- stores: packed trace codes, ring copy for predecessor rows, row meta
+            store_codes<C, TC>(trace + (size_t)i * STRIDE + cbase, code);
+            if (rf & RF_IS_PRED) {
+                store_row<C>(ring_m + (size_t)(i & RM) * STRIDE + cbase, A);
+                store_row<C>(ring_y + (size_t)(i & RM) * STRIDE + cbase, B);
+            }
+            if (lane == 0) {
+                RowMeta rm;
+                rm.base = 0;
+                rm.left = left;
+                rm.right = right;
+                rm.bsp = row_bsp;
+                rowmeta[i] = rm;
+            }
+            __syncwarp();
+            prev_bsp = row_bsp;
+            if ((rf & RF_F_PRED) || i == n - 2) {
+                int lv = NEG_INF;
+#pragma unroll
+                for (int k = 0; k < C; k++)
+                    if (cbase + k == (int)right - 1) lv = A[k];
+                const int lastcell = __reduce_max_sync(FULL, lv);
+                if ((rf & RF_F_PRED) && lastcell > best_end_val) {
+                    best_end_val = lastcell;
+                    best_end_row = i;
+                }
+                if (i == n - 2) last_val = lastcell;
+            }
+        }
+
+        status = __reduce_or_sync(FULL, (unsigned)status);
+        res.status = status;
+        res.cells = cells;
+        if (!abort_read && !(status & RG_READ_REF_PANIC)) {
+            // end cell (gap_global_abpoa.rs:206-214): row n-2 unless an F predecessor is strictly better
+            uint32_t last_row = n - 2;
+            int best_value = last_val;
+            if (best_end_val > last_val) {
+                last_row = best_end_row;
+                best_value = best_end_val;
+            }
+            RowMeta meta = rowmeta[last_row];
+            uint32_t row = last_row, col = meta.right - 1;
+            res.score = best_value;
+            res.end_row = row;
+            res.end_col = col;
+            // ---- traceback (gaf_output.rs:96-253) fused with band_ampl_enough (gap_global_abpoa.rs:371-455)
+            RunEmitter em;
+            em.init(runs, ws.run_cap);
+            int bandchk = -1;
+            bool panic = false;
+            for (;;) {
+                uint32_t cd = trace[(size_t)row * STRIDE + col];
+                const uint32_t dir = cd & 3u;
+                if (dir == DIR_O) break;
+                if (bandchk < 0) {
+                    if (row == 0 || col == 0)
+                        bandchk = 1;
+                    else if ((col == meta.left && meta.left != 0) || (col == meta.right - 1 && meta.right != (uint32_t)L))
+                        bandchk = 0;
+                }
+                const bool rnwp = g.rowflags[row] & RF_NWP;
+                if (dir == DIR_D) {
+                    uint32_t p = rnwp ? g.pred_idx[g.pred_off[row] + ((cd >> 4) & SMASK)] : row - 1;
+                    em.step(g.lnz[row] == read[col - 1] ? RG_OP_D : RG_OP_d, row, lane);
+                    row = p;
+                    col -= 1;
+                    meta = rowmeta[row];
+                } else if (dir == DIR_L) {
+                    if (cd & 4u) {
+                        while (cd & 4u) {
+                            em.step(RG_OP_L, row, lane);
+                            if (col <= meta.left) {
+                                panic = true;
+                                break;
+                            }
+                            col -= 1;
+                            cd = trace[(size_t)row * STRIDE + col];
+                        }
+                    } else {
+                        em.step(RG_OP_L, row, lane);
+                        if (col <= meta.left)
+                            panic = true;
+                        else
+                            col -= 1;
+                    }
+                } else {  // DIR_U
+                    if (cd & 8u) {
+                        bool first = true;
+                        while (cd & 8u) {
+                            const bool cn = g.rowflags[row] & RF_NWP;
+                            uint32_t p = cn ? g.pred_idx[g.pred_off[row] + ((cd >> (4 + SB)) & SMASK)] : row - 1;
+                            em.step(first ? RG_OP_U : RG_OP_Y, row, lane);
+                            first = false;
+                            row = p;
+                            meta = rowmeta[row];
+                            if (col < meta.left || col >= meta.right) {
+                                panic = true;
+                                break;
+                            }
+                            cd = trace[(size_t)row * STRIDE + col];
+                        }
+                    } else {
+                        uint32_t p = rnwp ? g.pred_idx[g.pred_off[row] + ((cd >> (4 + SB)) & SMASK)] : row - 1;
+                        em.step(RG_OP_U, row, lane);
+                        row = p;
+                        meta = rowmeta[row];
+                    }
+                }
+                if (panic || col < meta.left || col >= meta.right) {
+                    panic = true;
+                    break;
+                }
+            }
+            em.flush(lane);
+            if (panic) res.status |= RG_READ_REF_PANIC;
+            if (bandchk == 0) res.status |= RG_READ_BAND_WARNING;
+            if (em.overflow) res.status |= RG_READ_TRACE_OVERFLOW;
+            res.start_row = row;
+            res.start_col = col;
+            uint32_t nr = em.overflow ? 0 : em.n;
+            unsigned long long ro = 0;
+            if (lane == 0) ro = atomicAdd(&b.counters[1], (unsigned long long)nr);
+            ro = __shfl_sync(FULL, ro, 0);
+            if (ro + nr > b.out_run_cap) {
+                res.status |= RG_READ_TRACE_OVERFLOW;
+                nr = 0;
+            }
+            __syncwarp();
+            for (uint32_t k = lane; k < nr; k += 32) b.out_runs[ro + k] = runs[k];
+            res.run_off = ro;
+            res.n_runs = nr;
+        }
+        if (lane == 0) b.results[ridx] = res;
+        __syncwarp();
+    }
+}
+
+// Columns per lane for a batch whose longest read has Lmax columns (incl. '$'); 0 = use the striped kernel.
+int gap_blk_cols(uint32_t Lmax) {
+    if (Lmax <= 128) return 4;
+    if (Lmax <= 256) return 8;
+    if (Lmax <= 512) return 16;
+    if (Lmax <= 1024) return 32;
+    return 0;
+}
+
+template <int C>
+static int launch_c(const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b, int trace_bytes,
+                    int blocks, cudaStream_t st) {
+    if (trace_bytes == 1)
+        k_gap_global_blk<C, uint8_t, 2><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+    else
+        k_gap_global_blk<C, uint16_t, 6><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_gap_global_blk(int C, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
+                          int trace_bytes, int blocks, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {
+        case 4: return launch_c<4>(g, s, ws, b, trace_bytes, blocks, st);
+        case 8: return launch_c<8>(g, s, ws, b, trace_bytes, blocks, st);
+        case 16: return launch_c<16>(g, s, ws, b, trace_bytes, blocks, st);
+        case 32: return launch_c<32>(g, s, ws, b, trace_bytes, blocks, st);
+        default: return -2;
+    }
+}
+
+template <int C>
+static int occ_c(int trace_bytes, int* nb) {
+    const void* k = trace_bytes == 1 ? (const void*)k_gap_global_blk<C, uint8_t, 2> : (const void*)k_gap_global_blk<C, uint16_t, 6>;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, WARPS_PER_BLOCK * 32, 0) == cudaSuccess ? 0 : -1;
+}
+int gap_blk_blocks_per_sm(int C, int trace_bytes, int* nb) {
+    switch (C) {
+        case 4: return occ_c<4>(trace_bytes, nb);
+        case 8: return occ_c<8>(trace_bytes, nb);
+        case 16: return occ_c<16>(trace_bytes, nb);
+        case 32: return occ_c<32>(trace_bytes, nb);
+        default: return -2;
+    }
+}
+
+}  // namespace rg
