@@ -119,10 +119,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             rcw[j] = w;
         }
 
+        const long long t_start = clock64();
         int A[C], B[C];  // previous row: m and y of my columns (NEG_INF outside its band)
         int status = 0;
         uint64_t cells = 0;
-        uint32_t prev_bsp = 0;
+        uint32_t prev_bsp = 0, prev_left = 0, prev_right = 0;
         int best_end_val = NEG_INF;
         uint32_t best_end_row = 0;
         int last_val = 0;
@@ -164,7 +165,92 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             int bestv = NEG_INF;
             int bcol = 0;
 
-            if (i == 0) {
+            // Fast path (the steady state of a row inside a segment): band starts at column 0 and lies inside the
+            // previous row's band, so every active cell has its vertical and diagonal source and none of the
+            // availability / fallback logic of gap_global_abpoa.rs:110-141 can trigger.
+            const bool fast = (i > 0) && !nwp && left == 0 && prev_left == 0 && right <= prev_right;
+            if (fast) {
+                const int32_t* srow = s_sc + li * 8;
+                int up = __shfl_up_sync(FULL, A[C - 1], 1);
+                unsigned ybits = 0;
+                int D[C];
+                // pass A (descending so that A[k-1] is still the previous row when cell k reads its diagonal)
+#pragma unroll
+                for (int k = C - 1; k >= 0; k--) {
+                    const int um = A[k] + o;
+                    const int uy = B[k];
+                    const int yv = max(um, uy) + e;
+                    if (uy > um) ybits |= 1u << k;
+                    const unsigned rc = (rcw[k / 4] >> (8 * (k % 4))) & 0xffu;
+                    int dd = ((k == 0) ? up : A[k - 1]) + srow[rc];
+                    int h = max(dd, yv);
+                    if (k == 0 && lane == 0) {  // first-column cell: m = x only
+                        dd = NEG_INF;
+                        h = NEG_INF;
+                    }
+                    B[k] = yv;
+                    D[k] = dd;
+                    A[k] = h;
+                }
+                // pass B: in-lane x chain; generator of column c is h[c-1] + c2, the seed sits at column 0
+                int hprev = __shfl_up_sync(FULL, A[C - 1], 1);
+                int X[C];
+                {
+                    int xl = NEG_INF;
+#pragma unroll
+                    for (int k = 0; k < C; k++) {
+                        int gen = ((k == 0) ? hprev : A[k - 1]) + c2;
+                        if (k == 0 && lane == 0) gen = o + e * (best_p + 1);  // gap_global_abpoa.rs:88
+                        xl = max(xl + c1, gen);
+                        X[k] = xl;
+                    }
+                }
+                const int z = X[C - 1] - (cbase + C - 1) * c1;
+                const int winc = warp_incl_max(z, lane);
+                int wexc = __shfl_up_sync(FULL, winc, 1);
+                if (lane == 0) wexc = NEG_INF;
+                int xin = wexc + cbase * c1;
+                // pass C
+                unsigned xn_prev = 0;  // "x[c-1] > m[c-1] + o" of the previous cell
+                unsigned xn_last = 0;
+#pragma unroll
+                for (int k = 0; k < C; k++) {
+                    const int c = cbase + k;
+                    const int x = max(X[k], xin);
+                    xin += c1;
+                    const int dd = D[k];
+                    int yv = B[k];
+                    int ye = yv;
+                    if (k == 0 && lane == 0) {
+                        ye = NEG_INF;
+                        yv = 0;
+                    }
+                    const int t = max(dd, x);
+                    const int m = max(t, ye);
+                    unsigned cd = (t < ye) ? (unsigned)DIR_U : ((dd < x) ? (unsigned)DIR_L : (unsigned)DIR_D);
+                    if ((ybits >> k) & 1u) cd |= 8u;
+                    if (k == 0 && lane == 0) cd = DIR_U | ((mps & SMASK) << (4 + SB));
+                    if (k > 0 && xn_prev) cd |= 4u;
+                    xn_prev = (x > m + o) ? 1u : 0u;
+                    if (k == C - 1) xn_last = xn_prev;
+                    code[k] = cd;
+                    const bool act = c < (int)right;
+                    A[k] = act ? m : NEG_INF;
+                    B[k] = act ? yv : NEG_INF;
+                    bestv = max(bestv, A[k]);
+                }
+                unsigned pl = __shfl_up_sync(FULL, xn_last, 1);
+                if (lane != 0 && pl) code[0] |= 4u;
+                // right-most maximum inside the lane (only lanes holding the row maximum matter)
+                {
+                    const int lanemax = bestv;
+                    unsigned eqb = 0;
+#pragma unroll
+                    for (int k = 0; k < C; k++)
+                        if (A[k] == lanemax) eqb |= 1u << k;
+                    bcol = cbase + (31 - __clz(eqb | 1u));
+                }
+            } else if (i == 0) {
                 // gap_global_abpoa.rs:68-77
 #pragma unroll
                 for (int k = 0; k < C; k++) {
@@ -350,6 +436,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             }
             __syncwarp();
             prev_bsp = row_bsp;
+            prev_left = left;
+            prev_right = right;
             if ((rf & RF_F_PRED) || i == n - 2) {
                 int lv = NEG_INF;
 #pragma unroll
@@ -364,6 +452,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             }
         }
 
+        const long long t_dp = clock64();
         status = __reduce_or_sync(FULL, (unsigned)status);
         res.status = status;
         res.cells = cells;
@@ -466,6 +555,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             for (uint32_t k = lane; k < nr; k += 32) b.out_runs[ro + k] = runs[k];
             res.run_off = ro;
             res.n_runs = nr;
+        }
+        {   // diagnostic: SM cycles spent in the forward pass / in traceback+publish (kilo-cycles)
+            const long long t_end = clock64();
+            res.fen = (uint32_t)((t_dp - t_start) >> 10);
+            res.rsn = (uint32_t)((t_end - t_dp) >> 10);
         }
         if (lane == 0) b.results[ridx] = res;
         __syncwarp();

@@ -26,3 +26,7 @@ for _ in range(a.passes):
     print("kernel_ms, launches, cells:", al.kernel_stats())
 res = al.fetch()
 print("cells", sum(res.reads[i].cells for i in range(res.n_reads)))
+import numpy as np
+dp = np.array([res.reads[i].fen for i in range(res.n_reads)], dtype=np.float64)
+tb = np.array([res.reads[i].rsn for i in range(res.n_reads)], dtype=np.float64)
+print("kcycles per read: forward mean %.0f, traceback mean %.0f (%.1f%% of total); runs/read %.0f" % (dp.mean(), tb.mean(), 100 * tb.sum() / (dp.sum() + tb.sum()), res.n_runs_total / max(1, res.n_reads)))
