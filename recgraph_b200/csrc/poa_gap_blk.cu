@@ -266,26 +266,31 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     }
                 }
             } else {
-                int D[C];         // best predecessor m at column c-1 (diagonal source)
-                unsigned S[C];    // slots: um | uy << 8 | d << 16 (segment-start rows only)
+                // General path (segment starts, growing / shifted bands). Deliberately NOT unrolled: the per-lane
+                // arrays live in (L1-resident) local memory and the loops are rolled, so that this rarely taken
+                // path stays small in the instruction cache next to the unrolled fast path.
+                int GA[C], GB[C], GD[C], GX[C];  // best pred m at c, best pred y at c, best pred m at c-1, in-lane x
+                unsigned GS[C];                  // slots: um | uy << 8 | d << 16, later the cell's trace code
                 unsigned pred0_slot = 0xffffffffu;
                 if (!nwp) {
                     int up = __shfl_up_sync(FULL, A[C - 1], 1);
                     if (lane == 0) up = NEG_INF;
 #pragma unroll
-                    for (int k = C - 1; k >= 1; k--) D[k] = A[k - 1];
-                    D[0] = up;
-#pragma unroll
-                    for (int k = 0; k < C; k++) S[k] = 0;
+                    for (int k = 0; k < C; k++) {
+                        GA[k] = A[k];
+                        GB[k] = B[k];
+                        GD[k] = (k == 0) ? up : A[k - 1];
+                        GS[k] = 0;
+                    }
                 } else {
                     // gather over the predecessor rows (ring, absolute columns, NEG_INF outside their bands);
                     // first predecessor in list order wins ties (strict >), gap_global_abpoa.rs:266-345
-#pragma unroll
+#pragma unroll 1
                     for (int k = 0; k < C; k++) {
-                        A[k] = NEG_INF;
-                        B[k] = NEG_INF;
-                        D[k] = NEG_INF;
-                        S[k] = 0;
+                        GA[k] = NEG_INF;
+                        GB[k] = NEG_INF;
+                        GD[k] = NEG_INF;
+                        GS[k] = 0;
                     }
                     for (uint32_t q = 0; q < pe - pb; q++) {
                         const uint32_t p = g.pred_idx[pb + q];
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                         const int32_t* mp = ring_m + (size_t)(p & RM) * STRIDE + cbase;
                         const int32_t* yp = ring_y + (size_t)(p & RM) * STRIDE + cbase;
                         int carry = (lane == 0) ? NEG_INF : mp[-1];
-#pragma unroll
+#pragma unroll 1
                         for (int j = 0; j < C; j += 4) {
                             int4 mv = reinterpret_cast<const int4*>(mp)[j / 4];
                             int4 yv = reinterpret_cast<const int4*>(yp)[j / 4];
@@ -302,89 +307,91 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 #pragma unroll
                             for (int t = 0; t < 4; t++) {
                                 const int k = j + t;
-                                if (mm[t] > A[k]) {
-                                    A[k] = mm[t];
-                                    S[k] = (S[k] & ~0xffu) | q;
+                                unsigned sl = GS[k];
+                                if (mm[t] > GA[k]) {
+                                    GA[k] = mm[t];
+                                    sl = (sl & ~0xffu) | q;
                                 }
-                                if (yy[t] > B[k]) {
-                                    B[k] = yy[t];
-                                    S[k] = (S[k] & ~0xff00u) | (q << 8);
+                                if (yy[t] > GB[k]) {
+                                    GB[k] = yy[t];
+                                    sl = (sl & ~0xff00u) | (q << 8);
                                 }
-                                if (carry > D[k]) {
-                                    D[k] = carry;
-                                    S[k] = (S[k] & ~0xff0000u) | (q << 16);
+                                if (carry > GD[k]) {
+                                    GD[k] = carry;
+                                    sl = (sl & ~0xff0000u) | (q << 16);
                                 }
+                                GS[k] = sl;
                                 carry = mm[t];
                             }
                         }
                     }
                 }
-                // ---- pass A: vertical (y) and diagonal (d) per cell, independent across cells
                 const int fb0 = 2 * o + e * (best_p + 1);  // gap_global_abpoa.rs:117,139
                 const int32_t* srow = s_sc + li * 8;
-#pragma unroll
-                for (int k = 0; k < C; k++) {
-                    const int c = cbase + k;
-                    const int mu = A[k], uy = B[k];
-                    const bool uav = mu > NEGH;
-                    const int um = mu + o;
-                    const bool yf = uav && (uy > um);
-                    const int yv = uav ? max(um, uy) + e : fb0 + e * c;
-                    const unsigned us = uav ? (yf ? ((S[k] >> 8) & 0xffu) : (S[k] & 0xffu)) : mps;
-                    const int dv = D[k];
-                    const unsigned rc = (rcw[k / 4] >> (8 * (k % 4))) & 0xffu;
-                    const int dd = (dv > NEGH) ? dv + srow[rc] : NEG_INF;
-                    B[k] = yv;
-                    D[k] = dd;
-                    code[k] = (yf ? 8u : 0u) | (((S[k] >> 16) & SMASK) << 4) | ((us & SMASK) << (4 + SB));
-                }
-                // first column (gap_global_abpoa.rs:78-92): x = o + e*(best_p+1), m = x, y stays 0, dir U
-                const bool has_fc = (lane == 0) && left == 0;
-                // ---- pass B: in-lane chain of x over generators G_c = h[c-1] + c2 (seed at c == left)
+                const bool has_fc = (lane == 0) && left == 0;  // first column (gap_global_abpoa.rs:78-92)
                 const int seed = (left == 0) ? o + e * (best_p + 1) : fb0 + e * (int)left;
-                int hlast = max(D[C - 1], B[C - 1]);
-                if (cbase + C - 1 < (int)left || cbase + C - 1 >= (int)right) hlast = NEG_INF;
-                int hprev = __shfl_up_sync(FULL, hlast, 1);
-                if (lane == 0) hprev = NEG_INF;
-                int X[C];
+                // ---- pass A (y, d) and pass B (in-lane x chain; generator of column c is h[c-1] + c2)
+                int hprev;
                 {
-                    int xl = NEG_INF;
-#pragma unroll
+                    int hl = NEG_INF, xl = NEG_INF, hp = NEG_INF;
+                    // the previous lane's last h is needed first: compute it for every lane up front
+                    {
+                        const int k = C - 1, c = cbase + k;
+                        const int mu = GA[k], uy = GB[k];
+                        const bool uav = mu > NEGH;
+                        const int yv = uav ? max(mu + o, uy) + e : fb0 + e * c;
+                        const unsigned rc = (c >= 1 && c < L) ? read[c - 1] : 4u;
+                        const int dd = (GD[k] > NEGH) ? GD[k] + srow[rc] : NEG_INF;
+                        hl = max(dd, yv);
+                        if (c < (int)left || c >= (int)right || (k == 0 && has_fc)) hl = NEG_INF;
+                    }
+                    hprev = __shfl_up_sync(FULL, hl, 1);
+                    if (lane == 0) hprev = NEG_INF;
+                    hp = hprev;
+#pragma unroll 1
                     for (int k = 0; k < C; k++) {
                         const int c = cbase + k;
-                        int hp;
-                        if (k == 0)
-                            hp = hprev;
-                        else {
-                            hp = max(D[k - 1], B[k - 1]);
-                            if (k == 1 && has_fc) hp = NEG_INF;  // the first-column cell has m = x (no d / y candidate)
-                        }
+                        const int mu = GA[k], uy = GB[k];
+                        const bool uav = mu > NEGH;
+                        const int um = mu + o;
+                        const bool yf = uav && (uy > um);
+                        const int yv = uav ? max(um, uy) + e : fb0 + e * c;
+                        const unsigned sl = GS[k];
+                        const unsigned us = uav ? (yf ? ((sl >> 8) & 0xffu) : (sl & 0xffu)) : mps;
+                        const unsigned rc = (c >= 1 && c < L) ? read[c - 1] : 4u;
+                        const int dv = GD[k];
+                        const int dd = (dv > NEGH) ? dv + srow[rc] : NEG_INF;
+                        GB[k] = yv;
+                        GD[k] = dd;
+                        GS[k] = (yf ? 8u : 0u) | (((sl >> 16) & SMASK) << 4) | ((us & SMASK) << (4 + SB));
                         int gen = (c > (int)left && c < (int)right && hp > NEGH) ? hp + c2 : NEG_INF;
                         if (c == (int)left) gen = seed;
                         xl = max(xl + c1, gen);
-                        X[k] = xl;
+                        GX[k] = xl;
+                        hp = (k == 0 && has_fc) ? NEG_INF : max(dd, yv);  // the first-column cell has m = x only
                     }
                 }
                 // ---- cross-lane max-plus scan: x entering lane t = max over earlier lanes
-                int z = X[C - 1] - (cbase + C - 1) * c1;
-                if (X[C - 1] <= NEGH) z = NEG_INF;
+                int z = GX[C - 1] - (cbase + C - 1) * c1;
+                if (GX[C - 1] <= NEGH) z = NEG_INF;
                 int winc = warp_incl_max(z, lane);
                 int wexc = __shfl_up_sync(FULL, winc, 1);
                 if (lane == 0) wexc = NEG_INF;
                 const int xin0 = (wexc > NEGH) ? wexc + cbase * c1 : NEG_INF;
                 // ---- pass C: x, m, direction, flags
                 unsigned xn_bits = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < C; k++) {
                     const int c = cbase + k;
                     const bool act = c >= (int)left && c < (int)right;
-                    int x = X[k];
+                    int x = GX[k];
                     if (xin0 > NEGH) x = max(x, xin0 + k * c1);
                     const bool fc = (k == 0) && has_fc;
-                    const int dd = D[k];
-                    int yv = B[k];
+                    const int dd = GD[k];
+                    int yv = GB[k];
                     const int ye = fc ? NEG_INF : yv;
                     const int m = max(max(dd, x), ye);
+                    unsigned cd = GS[k];
                     unsigned dir;
                     if (dd < x)
                         dir = (x < ye) ? DIR_U : DIR_L;
@@ -393,14 +400,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     if (fc) {
                         dir = DIR_U;
                         yv = 0;
-                        code[k] = (mps & SMASK) << (4 + SB);
+                        cd = (mps & SMASK) << (4 + SB);
                     }
                     // gap_global_abpoa.rs:153-154: set_path_cell(u_pred, 'u') panics when u_pred == 0
-                    if (nwp && act && !fc && dd > NEGH && dd < x && x < ye && ((code[k] >> (4 + SB)) & SMASK) == pred0_slot) status |= RG_READ_REF_PANIC;
-                    code[k] |= dir;
+                    if (nwp && act && !fc && dd > NEGH && dd < x && x < ye && ((cd >> (4 + SB)) & SMASK) == pred0_slot) status |= RG_READ_REF_PANIC;
+                    GS[k] = cd | dir;
                     if (x > m + o) xn_bits |= 1u << k;
-                    A[k] = act ? m : NEG_INF;
-                    B[k] = act ? yv : NEG_INF;
+                    GA[k] = act ? m : NEG_INF;
+                    GB[k] = act ? yv : NEG_INF;
                     if (act && m >= bestv) {
                         bestv = m;
                         bcol = c;
@@ -409,11 +416,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                 // path_x flag of column c: x[c-1] > m[c-1] + o (gap_global_abpoa.rs:358-364), only for c > left
                 unsigned prev_last = __shfl_up_sync(FULL, xn_bits >> (C - 1), 1) & 1u;
                 if (lane == 0) prev_last = 0;
-                unsigned xf = (xn_bits << 1) | prev_last;
+                const unsigned xf = (xn_bits << 1) | prev_last;
 #pragma unroll
                 for (int k = 0; k < C; k++) {
                     const int c = cbase + k;
-                    if (c > (int)left && c < (int)right && ((xf >> k) & 1u)) code[k] |= 4u;
+                    A[k] = GA[k];
+                    B[k] = GB[k];
+                    code[k] = GS[k] | ((c > (int)left && c < (int)right && ((xf >> k) & 1u)) ? 4u : 0u);
                 }
             }
             // ---- row arg-max, right-most (>=)  (gap_global_abpoa.rs:198-203)
