@@ -84,6 +84,7 @@ struct rg_ctx {
     DevBuf<uint8_t> d_lnz, d_rowflags, d_min_pred_slot, d_prev_slot;
     DevBuf<uint32_t> d_pred_off, d_pred_idx, d_min_pred;
     DevBuf<int32_t> d_r_values;
+    DevBuf<RowInfo> d_rowinfo;
     DevGraph dg{};
     // scoring
     bool has_scoring = false;
@@ -131,9 +132,34 @@ static int upload_graph(rg_ctx* c) {
     FlatGraph& f = c->fg;
     cudaStream_t st = c->stream;
     std::vector<uint8_t> rowflags(f.n, 0);
-    for (uint32_t i = 0; i < f.n; i++) rowflags[i] = (f.nwp[i] ? RF_NWP : 0) | (f.is_pred_row[i] ? RF_IS_PRED : 0);
+    // RF_SINGLE_PREV: segment start whose only predecessor is the row right above it (and not the '$' row): the
+    // kernels treat it like a row inside a segment, so its predecessor need not be kept in the ring either.
+    for (uint32_t i = 0; i < f.n; i++) rowflags[i] = (f.nwp[i] ? RF_NWP : 0);
+    for (uint32_t i = 2; i + 1 < f.n; i++) {
+        if (!f.nwp[i]) continue;
+        uint32_t b = f.pred_off[i], e = f.pred_off[i + 1];
+        if (e - b == 1 && f.pred_idx[b] == i - 1)
+            rowflags[i] |= RF_SINGLE_PREV;
+        else
+            for (uint32_t k = b; k < e; k++) rowflags[f.pred_idx[k]] |= RF_IS_PRED;
+    }
+    if (f.n > 2 && f.nwp[1])
+        for (uint32_t k = f.pred_off[1]; k < f.pred_off[2]; k++) rowflags[f.pred_idx[k]] |= RF_IS_PRED;
     for (uint32_t k = f.pred_off[f.n - 1]; k < f.pred_off[f.n]; k++) rowflags[f.pred_idx[k]] |= RF_F_PRED;
-    bool ok = c->d_lnz.upload(f.lnz, st) && c->d_rowflags.upload(rowflags, st) &&
+    std::vector<RowInfo> rowinfo(f.n);
+    for (uint32_t i = 0; i < f.n; i++) {
+        uint32_t np = f.nwp[i] ? f.pred_off[i + 1] - f.pred_off[i] : 0;
+        RowInfo ri;
+        ri.r_value = f.r_values[i];
+        ri.min_pred = f.min_pred[i];
+        ri.pred_off = f.pred_off[i];
+        ri.lnz = f.lnz[i];
+        ri.flags = rowflags[i];
+        ri.min_pred_slot = f.min_pred_slot[i];
+        ri.npred = (uint8_t)std::min<uint32_t>(np, 255);
+        rowinfo[i] = ri;
+    }
+    bool ok = c->d_rowinfo.upload(rowinfo, st) && c->d_lnz.upload(f.lnz, st) && c->d_rowflags.upload(rowflags, st) &&
               c->d_pred_off.upload(f.pred_off, st) && c->d_pred_idx.upload(f.pred_idx, st) &&
               c->d_min_pred.upload(f.min_pred, st) && c->d_min_pred_slot.upload(f.min_pred_slot, st) &&
               c->d_prev_slot.upload(f.prev_slot, st) && c->d_r_values.upload(f.r_values, st);
@@ -149,6 +175,7 @@ static int upload_graph(rg_ctx* c) {
     c->dg.min_pred_slot = c->d_min_pred_slot.p;
     c->dg.prev_slot = c->d_prev_slot.p;
     c->dg.r_values = c->d_r_values.p;
+    c->dg.rowinfo = c->d_rowinfo.p;
     c->dg.ring = ring;
     c->has_graph = true;
     c->results_ready = false;

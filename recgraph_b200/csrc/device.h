@@ -7,7 +7,15 @@
 namespace rg {
 
 // rowflags bits
-enum : uint8_t { RF_NWP = 1, RF_IS_PRED = 2, RF_F_PRED = 4 };
+enum : uint8_t { RF_NWP = 1, RF_IS_PRED = 2, RF_F_PRED = 4, RF_SINGLE_PREV = 8 /* nwp row whose only predecessor is i-1 */ };
+
+// Everything the forward pass needs to know about a row, packed for one 128-bit load.
+struct RowInfo {
+    int32_t r_value;
+    uint32_t min_pred;
+    uint32_t pred_off;
+    uint8_t lnz, flags, min_pred_slot, npred;
+};
 
 // Graph arrays resident in HBM (one copy per device; read-only during alignment).
 struct DevGraph {
@@ -20,6 +28,7 @@ struct DevGraph {
     const uint8_t* min_pred_slot;   // n
     const uint8_t* prev_slot;       // n
     const int32_t* r_values;        // n
+    const RowInfo* rowinfo;         // n
     uint32_t ring;                  // power of two > max look-back: depth of the predecessor-row ring
 };
 

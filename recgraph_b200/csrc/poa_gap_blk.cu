@@ -129,10 +129,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
         int last_val = 0;
         bool abort_read = false;
 
+        int4 ri_next = reinterpret_cast<const int4*>(g.rowinfo)[0];
         for (uint32_t i = 0; i + 1 < n; i++) {
-            const uint8_t rf = g.rowflags[i];
-            const bool nwp = rf & RF_NWP;
-            const uint32_t pb = g.pred_off[i], pe = nwp ? g.pred_off[i + 1] : pb;
+            // packed row info, fetched one row ahead (hides the L1/L2 latency behind the previous row's work)
+            const int4 riv = ri_next;
+            ri_next = reinterpret_cast<const int4*>(g.rowinfo)[i + 1];
+            const uint32_t rbits = (uint32_t)riv.w;
+            const uint8_t rf = (rbits >> 8) & 0xffu;
+            // a segment start whose only predecessor is row i-1 behaves exactly like a row inside a segment
+            const bool nwp = (rf & RF_NWP) && !(rf & RF_SINGLE_PREV);
+            const uint32_t pb = (uint32_t)riv.z, pe = pb + (nwp ? (rbits >> 24) : 0u);
             uint32_t ms, me;
             if (i == 0) {
                 ms = 0;
@@ -151,16 +157,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                 me = pr + 1;
             }
             uint32_t left, right;
-            band_for_row(ms, me, g.r_values[i], L, bta, left, right);
+            band_for_row(ms, me, riv.x, L, bta, left, right);
             if (right <= left) {  // reference: empty row -> index / subtract-overflow panic later on
                 status |= RG_READ_REF_PANIC;
                 abort_read = true;
                 break;
             }
             cells += right - left;
-            const int li = g.lnz[i];
-            const int best_p = (int)g.min_pred[i];
-            const unsigned mps = g.min_pred_slot[i];
+            const int li = rbits & 0xffu;
+            const int best_p = riv.y;
+            const unsigned mps = (rbits >> 16) & 0xffu;
             unsigned code[C];
             int bestv = NEG_INF;
             int bcol = 0;
