@@ -9,6 +9,9 @@ namespace rg {
 // rowflags bits
 enum : uint8_t { RF_NWP = 1, RF_IS_PRED = 2, RF_F_PRED = 4, RF_SINGLE_PREV = 8 /* nwp row whose only predecessor is i-1 */ };
 
+// prev_slot values: slot of the predecessor list that holds row i-1
+enum : unsigned { PREV_ALWAYS_SLOT = 0xFE /* row inside a segment */, PREV_NONE_SLOT = 0xFF };
+
 // Everything the forward pass needs to know about a row, packed for one 128-bit load.
 struct RowInfo {
     int32_t r_value;

@@ -61,6 +61,19 @@ struct RunEmitter {
             count = 0;
         }
     }
+    // `cnt` consecutive steps of the same op starting at row r (rows descending for graph-consuming ops)
+    __device__ __forceinline__ void bulk(uint32_t o, uint32_t r, uint32_t cnt, int lane) {
+        if (cnt == 0) return;
+        bool cont = count && o == op && count + cnt < 0x0fffffffu && (o == RG_OP_L || o == RG_OP_LPAD ? r == row : r + count == row);
+        if (cont)
+            count += cnt;
+        else {
+            flush(lane);
+            op = o;
+            row = r;
+            count = cnt;
+        }
+    }
     __device__ __forceinline__ void step(uint32_t o, uint32_t r, int lane) {
         bool cont = count && o == op && count < 0x0fffffffu && (o == RG_OP_L || o == RG_OP_LPAD ? r == row : r + count == row);
         if (cont)

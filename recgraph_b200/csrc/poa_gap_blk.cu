@@ -12,6 +12,7 @@
 
 #include "device.h"
 #include "poa_common.cuh"
+#include "poa_walk.cuh"
 
 namespace rg {
 
@@ -487,71 +488,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             // ---- traceback (gaf_output.rs:96-253) fused with band_ampl_enough (gap_global_abpoa.rs:371-455)
             RunEmitter em;
             em.init(runs, ws.run_cap);
-            int bandchk = -1;
-            bool panic = false;
-            for (;;) {
-                uint32_t cd = trace[(size_t)row * STRIDE + col];
-                const uint32_t dir = cd & 3u;
-                if (dir == DIR_O) break;
-                if (bandchk < 0) {
-                    if (row == 0 || col == 0)
-                        bandchk = 1;
-                    else if ((col == meta.left && meta.left != 0) || (col == meta.right - 1 && meta.right != (uint32_t)L))
-                        bandchk = 0;
-                }
-                const bool rnwp = g.rowflags[row] & RF_NWP;
-                if (dir == DIR_D) {
-                    uint32_t p = rnwp ? g.pred_idx[g.pred_off[row] + ((cd >> 4) & SMASK)] : row - 1;
-                    em.step(g.lnz[row] == read[col - 1] ? RG_OP_D : RG_OP_d, row, lane);
-                    row = p;
-                    col -= 1;
-                    meta = rowmeta[row];
-                } else if (dir == DIR_L) {
-                    if (cd & 4u) {
-                        while (cd & 4u) {
-                            em.step(RG_OP_L, row, lane);
-                            if (col <= meta.left) {
-                                panic = true;
-                                break;
-                            }
-                            col -= 1;
-                            cd = trace[(size_t)row * STRIDE + col];
-                        }
-                    } else {
-                        em.step(RG_OP_L, row, lane);
-                        if (col <= meta.left)
-                            panic = true;
-                        else
-                            col -= 1;
-                    }
-                } else {  // DIR_U
-                    if (cd & 8u) {
-                        bool first = true;
-                        while (cd & 8u) {
-                            const bool cn = g.rowflags[row] & RF_NWP;
-                            uint32_t p = cn ? g.pred_idx[g.pred_off[row] + ((cd >> (4 + SB)) & SMASK)] : row - 1;
-                            em.step(first ? RG_OP_U : RG_OP_Y, row, lane);
-                            first = false;
-                            row = p;
-                            meta = rowmeta[row];
-                            if (col < meta.left || col >= meta.right) {
-                                panic = true;
-                                break;
-                            }
-                            cd = trace[(size_t)row * STRIDE + col];
-                        }
-                    } else {
-                        uint32_t p = rnwp ? g.pred_idx[g.pred_off[row] + ((cd >> (4 + SB)) & SMASK)] : row - 1;
-                        em.step(RG_OP_U, row, lane);
-                        row = p;
-                        meta = rowmeta[row];
-                    }
-                }
-                if (panic || col < meta.left || col >= meta.right) {
-                    panic = true;
-                    break;
-                }
-            }
+            const WalkOut wo = walk_affine<TC, SB, STRIDE>(trace, rowmeta, g, read, L, row, col, em, lane);
+            row = wo.row;
+            col = wo.col;
+            const int bandchk = wo.bandchk;
+            const bool panic = wo.panic;
             em.flush(lane);
             if (panic) res.status |= RG_READ_REF_PANIC;
             if (bandchk == 0) res.status |= RG_READ_BAND_WARNING;
