@@ -2,6 +2,7 @@
 // global_abpoa.rs, local_poa.rs, gap_global_abpoa.rs, gap_local_poa.rs, bitfield_path.rs, gaf_output.rs.
 #include <algorithm>
 #include <charconv>
+#include <cstdlib>
 
 #include "oracle.hpp"
 
@@ -75,7 +76,13 @@ std::string build_cigar(const std::vector<char>& cigar) {
 
 // ------------------------------------------------------------------------------- bitfield_path.rs
 // 32-bit cell: bits 31..16 predecessor (u16, TRUNCATING — F3), bits 15..0 direction code.
-typedef uint32_t PathCell;
+typedef uint64_t PathCell;
+// RGO_PRED32=1 (tests on graphs above 65 535 rows, outside the reference's valid domain): keep the full
+// predecessor instead of truncating it to u16. The cell then needs 64 bits.
+static bool pred32_mode() {
+    static const bool on = std::getenv("RGO_PRED32") != nullptr;
+    return on;
+}
 static inline PathCell set_path_cell(size_t pred, char dir) {
     uint32_t d;
     switch (dir) {
@@ -89,9 +96,9 @@ static inline PathCell set_path_cell(size_t pred, char dir) {
         case 'M': d = 7; break;
         default: throw RefPanic("impossible direction char");  // bitfield_path.rs:13
     }
-    return ((uint32_t)(uint16_t)pred << 16) | d;
+    return ((uint64_t)(pred32_mode() ? (uint32_t)pred : (uint32_t)(uint16_t)pred) << 16) | d;
 }
-static inline size_t pred_from_bitvec(PathCell c) { return c >> 16; }
+static inline size_t pred_from_bitvec(PathCell c) { return (size_t)(c >> 16); }
 static inline char dir_from_bitvec(PathCell c) {
     static const char t[8] = {'O', 'D', 'd', 'L', 'U', 'X', 'Y', 'M'};
     uint32_t d = c & 0xffff;
