@@ -355,16 +355,27 @@ static int align_poa(rg_ctx* c, int mode) {
     const FlatGraph& f = c->fg;
     const uint32_t n = f.n;
     const uint32_t Lmax = c->max_len + 1;
-    const int trace_bytes = f.max_indeg <= 4 ? 1 : 2;
-    if (f.max_indeg > 64) return c->fail(RG_ERR_UNSUPPORTED, "in-degree above 64 is outside the trace-code domain");
+    const bool lin = mode == RG_MODE_GLOBAL || mode == RG_MODE_LOCAL || mode == RG_MODE_GAP_LOCAL;
+    const int trace_bytes = lin ? poa_lin_trace_bytes(f.max_indeg) : (f.max_indeg <= 4 ? 1 : 2);
+    if (f.max_indeg > (lin ? 31u : 64u)) return c->fail(RG_ERR_UNSUPPORTED, "in-degree above the trace-code domain (31 for modes 0/1/3, 64 for mode 2)");
+    if (mode == RG_MODE_GLOBAL || mode == RG_MODE_LOCAL)
+        for (int k = 1; k < 5; k++)
+            if (c->scoring.score[k][5] != c->scoring.score[0][5])
+                return c->fail(RG_ERR_UNSUPPORTED, "modes 0/1 need one gap score for all characters (true for every matrix the reference builds)");
     uint32_t wstride = (Lmax + 31) & ~31u;
     int ws_cols = 64, blocks_per_sm = 1;
     // register-blocked kernel (lane-owned column blocks) whenever the longest read fits 32*C columns
-    const int blkC = (mode == RG_MODE_GAP_GLOBAL && !c->force_striped) ? gap_blk_cols(Lmax) : 0;
+    const int blkC = lin ? gap_blk_cols(Lmax) : ((mode == RG_MODE_GAP_GLOBAL && !c->force_striped) ? gap_blk_cols(Lmax) : 0);
+    if (lin && !blkC) return c->fail(RG_ERR_UNSUPPORTED, "modes 0/1/3: reads longer than 1023 bases are not supported on the device yet");
     int lc;
     if (blkC) {
         wstride = 32u * blkC;
-        lc = gap_blk_blocks_per_sm(blkC, trace_bytes, &blocks_per_sm);
+        if (lin) {
+            lc = 0;
+            blocks_per_sm = 2;
+        } else {
+            lc = gap_blk_blocks_per_sm(blkC, trace_bytes, &blocks_per_sm);
+        }
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     } else {
         lc = poa_launch_config(mode, trace_bytes, Lmax, &ws_cols, &blocks_per_sm);
@@ -432,7 +443,8 @@ static int align_poa(rg_ctx* c, int mode) {
         cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
         cudaEventRecord(c->ev0, c->stream);
         if (blkC && trace_cap < full) return c->fail(RG_ERR_NOMEM, "not enough device memory for the blocked kernel's trace");
-        int rc = blkC ? launch_gap_global_blk(blkC, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), c->stream)
+        int rc = lin ? launch_poa_lin(mode, blkC, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), c->stream)
+                 : blkC ? launch_gap_global_blk(blkC, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), c->stream)
                       : launch_poa(mode, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), ws_cols, c->stream);
         cudaEventRecord(c->ev1, c->stream);
         if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("alignment kernel");
@@ -475,6 +487,9 @@ int rg_align_staged(rg_ctx* c, int mode) {
     }
     int rc;
     switch (mode) {
+        case RG_MODE_GLOBAL:
+        case RG_MODE_LOCAL:
+        case RG_MODE_GAP_LOCAL:
         case RG_MODE_GAP_GLOBAL: rc = align_poa(c, mode); break;
         default: return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
     }

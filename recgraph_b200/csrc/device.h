@@ -82,6 +82,10 @@ int gap_blk_cols(uint32_t Lmax);
 int gap_blk_blocks_per_sm(int C, int trace_bytes, int* nb);
 int launch_gap_global_blk(int C, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
                           int trace_bytes, int blocks, void* stream);
+// modes 0 / 1 / 3 (poa_lin.cu)
+int poa_lin_trace_bytes(uint32_t max_indeg);
+int launch_poa_lin(int mode, int C, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
+                   int trace_bytes, int blocks, void* stream);
 int launch_int_peak(double* iadd, double* imnmx, double* viaddmnmx, void* stream);
 
 }  // namespace rg

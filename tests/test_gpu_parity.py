@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXAMPLE = os.path.join(ROOT, "tests", "golden", "example")
 
-IMPLEMENTED = {2}
+IMPLEMENTED = {0, 1, 2, 3}
 
 
 def _both(args):
@@ -96,3 +96,53 @@ def test_empty_batch_and_errors():
     assert res.n_reads == 0
     with pytest.raises(RecGraphError):
         al.align(2, ["ACGTXX"])
+
+
+EX = [os.path.join(EXAMPLE, "reads.fa"), os.path.join(EXAMPLE, "graph.gfa")]
+
+
+@pytest.mark.parametrize("extra", [[], ["-b", "50"], ["-b", "1000"], ["-b", "20", "-f", "0.3"], ["-M", "1", "-X", "1"],
+                                   ["-b", "200", "-t", "HOXD70"], ["-b", "300", "-t", "HOXD55"], ["-b", "7"]])
+def test_mode0_example(extra):
+    """BASELINE config 1: `-m 0` on example/ (AVX2 semantics). Default flags give the degenerate
+    "band not enough" records; larger -b gives real alignments."""
+    _assert_same(["-m", "0"] + extra + EX)
+
+
+@pytest.mark.parametrize("extra", [[], ["-M", "3", "-X", "2"], ["-t", "HOXD70"], ["-t", "HOXD55"], ["-M", "1", "-X", "5"]])
+def test_mode1_example(extra):
+    _assert_same(["-m", "1"] + extra + EX)
+
+
+@pytest.mark.parametrize("extra", [[], ["-O", "10", "-E", "1"], ["-O", "0", "-E", "2"], ["-M", "1", "-X", "1", "-O", "1", "-E", "1"],
+                                   ["-t", "HOXD70", "-O", "400", "-E", "30"]])
+def test_mode3_example(extra):
+    _assert_same(["-m", "3"] + extra + EX)
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "3"])
+@pytest.mark.parametrize("name", ["small", "mid", "short_reads"])
+@pytest.mark.parametrize("extra", [[], ["-b", "40", "-f", "0.1"]])
+def test_modes013_synthetic(synth_files, mode, name, extra):
+    if mode != "0" and extra:
+        pytest.skip("band flags only matter for mode 0")
+    fa, gfa = synth_files[name]
+    _assert_same(["-m", mode] + extra + [fa, gfa])
+
+
+def test_mode3_reference_unit_vectors():
+    """gap_local_poa.rs:198-277 through rg_set_lnz_graph on the GPU."""
+    from recgraph_b200 import Aligner
+    from tests.test_oracle_golden import POA_CASES
+    al = Aligner()
+    for variant, (lnz, nwp, preds), read, scores, o, e, bta, expected, cite in POA_CASES:
+        if variant != 3:
+            continue
+        table = [[0] * 6 for _ in range(6)]
+        idx = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 4, "-": 5}
+        for (a, b), v in scores.items():
+            table[idx[a]][idx[b]] = v
+        al.set_lnz_graph(lnz, nwp, preds)
+        al.set_scoring(table=table, gap_open=-o, gap_ext=-e)
+        recs, _ = al.align(3, [read[1:]])
+        assert recs[0].score == expected, cite
