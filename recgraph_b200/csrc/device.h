@@ -73,6 +73,41 @@ struct PoaBatch {
     unsigned long long* counters;  // [0] next read, [1] runs used
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pathwise family (modes 4/5/8/9). Rows are partitioned into GROUPS, one per incoming edge:
+// members = paths(row) & paths(edge), leader = alphas[pred] if a member, else alphas[row] if a member, else the
+// lowest member (pathwise_alignment_semiglobal.rs:91-152). Built once per graph on the host.
+struct PwGroup {
+    uint32_t pred;    // predecessor row (forward graph) / successor row (reverse graph)
+    uint32_t leader;  // path id
+    uint32_t lead_is_alpha_of_pred;  // leader == alphas[pred]: its row is available in compact form
+    uint32_t pad;
+};
+struct DevPathGraph {
+    uint32_t n, P, PW;
+    const uint8_t* lnz;
+    const uint32_t* alphas;      // n
+    const uint32_t* node_bits;   // n * PW
+    const uint32_t* grp_off;     // n + 1
+    const PwGroup* grp;          // groups of all rows
+    const uint32_t* grp_mask;    // PW words per group: members
+    const uint8_t* nwp;          // PathGraph nwp of this direction
+    const uint32_t* fpred_off;   // mode 4/8: groups of the 'F' row = (pred, edge paths): index range in grp (row n-1)
+    uint32_t ring;               // rows kept (pow2 > look-back)
+    uint32_t max_groups;         // max groups per row
+};
+struct PwWorkspace {
+    int32_t* S;         // slots * ring * Lp * Pp     (absolute scores, [row][col][path])
+    int32_t* lead;      // slots * ring * Lp          (score of the row's alpha path, compact)
+    uint32_t* trace;    // slots * n * Lp * PW * 2    (2-bit own-argmax code per path-cell, as two bit planes)
+    rg_run* runs;       // slots * run_cap
+    uint32_t Lp, Pp;    // padded columns / paths
+    uint32_t run_cap;
+    uint32_t slots;
+};
+int launch_pathwise(int mode, const DevPathGraph& g, const DevScoring& s, const PwWorkspace& ws, const PoaBatch& b,
+                    int blocks, void* stream);
+
 // launchers (poa_kernels.cu)
 int poa_launch_config(int mode, int trace_bytes, uint32_t Lmax, int* ws_cols, int* blocks_per_sm);
 int launch_poa(int mode, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
