@@ -86,6 +86,15 @@ struct rg_ctx {
     DevBuf<int32_t> d_r_values;
     DevBuf<RowInfo> d_rowinfo;
     DevGraph dg{};
+    // pathwise graph (forward)
+    DevBuf<uint32_t> d_alphas, d_node_bits, d_grp_off, d_grp_mask;
+    DevBuf<PwGroup> d_grp;
+    DevBuf<uint8_t> d_pw_nwp;
+    DevPathGraph dpg{};
+    bool has_path_graph = false;
+    std::string path_graph_error;
+    DevBuf<int32_t> d_pwS, d_pwLead;
+    DevBuf<uint32_t> d_pwTrace;
     // scoring
     bool has_scoring = false;
     rg_scoring scoring{};
@@ -127,6 +136,99 @@ struct rg_ctx {
         return RG_ERR_CUDA;
     }
 };
+
+// Groups of the pathwise DP for one direction, as CSR over rows.
+static void build_groups(const FlatGraph& f, const std::vector<uint8_t>& nwp, const std::vector<uint32_t>& poff,
+                         const std::vector<uint32_t>& pidx, const std::vector<uint32_t>& ebits, bool reverse,
+                         std::vector<uint32_t>& grp_off, std::vector<PwGroup>& grp, std::vector<uint32_t>& grp_mask,
+                         uint32_t& max_groups) {
+    const uint32_t n = f.n, PW = f.PW;
+    grp_off.assign(n + 1, 0);
+    grp.clear();
+    grp_mask.clear();
+    max_groups = 1;
+    auto bit = [&](const uint32_t* m, uint32_t p) { return (m[p / 32] >> (p % 32)) & 1u; };
+    const uint32_t base_row = reverse ? n - 1 : 0;   // the row the DP starts from has no groups
+    for (uint32_t i = 0; i < n; i++) {
+        grp_off[i] = (uint32_t)grp.size();
+        if (i == base_row) continue;
+        const uint32_t* nb = &f.node_bits[(size_t)i * PW];
+        auto add = [&](uint32_t pred, const uint32_t* emask, bool is_end_row) {
+            std::vector<uint32_t> m(PW);
+            bool any = false;
+            for (uint32_t w = 0; w < PW; w++) {
+                m[w] = emask ? (nb[w] & emask[w]) : (nb[w] & f.node_bits[(size_t)pred * PW + w]);
+                any |= m[w] != 0;
+            }
+            if (!any) return;
+            PwGroup gpr{};
+            gpr.pred = pred;
+            uint32_t ap = f.alphas[pred], ai = f.alphas[i];
+            uint32_t leader;
+            if (ap < f.P && bit(m.data(), ap))
+                leader = ap;
+            else if (ai < f.P && bit(m.data(), ai))
+                leader = ai;
+            else {
+                leader = 0;
+                while (!bit(m.data(), leader)) leader++;
+            }
+            gpr.leader = leader;
+            gpr.lead_is_alpha_of_pred = (!is_end_row && leader == ap) ? 1u : 0u;
+            grp.push_back(gpr);
+            grp_mask.insert(grp_mask.end(), m.begin(), m.end());
+        };
+        const bool end_row = reverse ? (i == 0) : (i == n - 1);
+        if (!nwp[i] && !end_row) {
+            add(reverse ? i + 1 : i - 1, nullptr, false);
+        } else {
+            for (uint32_t k = poff[i]; k < poff[i + 1]; k++) add(pidx[k], &ebits[(size_t)k * PW], end_row);
+        }
+        if (!end_row) max_groups = std::max<uint32_t>(max_groups, (uint32_t)grp.size() - grp_off[i]);
+    }
+    grp_off[n] = (uint32_t)grp.size();
+}
+
+static int upload_path_graph(rg_ctx* c) {
+    FlatGraph& f = c->fg;
+    c->has_path_graph = false;
+    c->path_graph_error.clear();
+    if (!f.has_paths) {
+        c->path_graph_error = "the graph has no paths (P lines): pathwise modes need them";
+        return RG_OK;
+    }
+    for (uint32_t i = 1; i + 1 < f.n; i++)
+        if (f.alphas[i] >= f.P) {
+            // pathwise_graph.rs:182 + pathwise_alignment_semiglobal.rs:62-70: index alphas[i] = P+1 panics
+            c->path_graph_error = "a segment is covered by no path: the reference panics (alphas = P+1)";
+            return RG_OK;
+        }
+    std::vector<uint32_t> grp_off, grp_mask;
+    std::vector<PwGroup> grp;
+    uint32_t max_groups = 1;
+    build_groups(f, f.pw_nwp, f.pw_pred_off, f.pw_pred_idx, f.pw_edge_bits, false, grp_off, grp, grp_mask, max_groups);
+    cudaStream_t st = c->stream;
+    bool ok = c->d_alphas.upload(f.alphas, st) && c->d_node_bits.upload(f.node_bits, st) && c->d_grp_off.upload(grp_off, st) &&
+              c->d_grp_mask.upload(grp_mask, st) && c->d_grp.upload(grp, st) && c->d_pw_nwp.upload(f.pw_nwp, st);
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) return c->cuda_fail("path graph upload");
+    uint32_t ring = 2;
+    while (ring <= f.pw_max_lookback) ring <<= 1;
+    c->dpg.n = f.n;
+    c->dpg.P = f.P;
+    c->dpg.PW = f.PW;
+    c->dpg.lnz = c->d_lnz.p;
+    c->dpg.alphas = c->d_alphas.p;
+    c->dpg.node_bits = c->d_node_bits.p;
+    c->dpg.grp_off = c->d_grp_off.p;
+    c->dpg.grp = c->d_grp.p;
+    c->dpg.grp_mask = c->d_grp_mask.p;
+    c->dpg.nwp = c->d_pw_nwp.p;
+    c->dpg.fpred_off = nullptr;
+    c->dpg.ring = ring;
+    c->dpg.max_groups = max_groups;
+    c->has_path_graph = true;
+    return RG_OK;
+}
 
 static int upload_graph(rg_ctx* c) {
     FlatGraph& f = c->fg;
@@ -252,7 +354,9 @@ int rg_load_gfa_text(rg_ctx* c, const char* text, size_t len) {
     if (!parse_gfa(text, len, g, err)) return c->fail(err.find("outside the supported") != std::string::npos ? RG_ERR_UNSUPPORTED : RG_ERR_IO, err);
     int rc = flatten_graph(g, c->fg, err);
     if (rc != RG_OK) return c->fail(rc, err);
-    return upload_graph(c);
+    rc = upload_graph(c);
+    if (rc != RG_OK) return rc;
+    return upload_path_graph(c);
 }
 
 int rg_load_gfa_file(rg_ctx* c, const char* path) {
@@ -471,6 +575,70 @@ static int align_poa(rg_ctx* c, int mode) {
     return c->fail(RG_ERR_NOMEM, "trace buffers still overflow after retries");
 }
 
+static int align_pathwise(rg_ctx* c, int mode) {
+    if (!c->has_path_graph)
+        return c->fail(c->path_graph_error.find("panics") != std::string::npos ? RG_ERR_REF_PANIC : RG_ERR_INVALID,
+                       c->path_graph_error.empty() ? "no path graph" : c->path_graph_error);
+    const FlatGraph& f = c->fg;
+    for (int k = 1; k < 5; k++)
+        if (c->scoring.score[k][5] != c->scoring.score[0][5] || c->scoring.score[5][k] != c->scoring.score[0][5])
+            return c->fail(RG_ERR_UNSUPPORTED, "pathwise modes need one gap score for all characters (true for every matrix the reference builds)");
+    const uint32_t n = f.n, PW = f.PW;
+    PwWorkspace ws{};
+    ws.Lp = (c->max_len + 1 + 31) & ~31u;
+    ws.Pp = PW * 32;
+    ws.run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * ws.Lp), 1u << 22);
+    int bps = 1;
+    int lc = pathwise_blocks_per_sm(c->dpg, ws, &bps);
+    if (lc == -3) return c->fail(RG_ERR_UNSUPPORTED, "read too long for the pathwise kernel's shared-memory move table");
+    if (lc != 0) return c->cuda_fail("kernel configuration");
+    if (bps < 1) bps = 1;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    free_b += (c->d_pwS.cap + c->d_pwLead.cap + c->d_pwTrace.cap) * 4 + (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
+    const size_t per_slot = (size_t)c->dpg.ring * ws.Lp * ws.Pp * 4 + (size_t)c->dpg.ring * ws.Lp * 4 +
+                            (size_t)n * ws.Lp * PW * 8 + (size_t)ws.run_cap * sizeof(rg_run);
+    const size_t budget_all = (size_t)(free_b * 0.85);
+    size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(ws.run_cap, 16384), (budget_all / 8) / sizeof(rg_run));
+    out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
+    const size_t budget = budget_all - out_runs_cap * sizeof(rg_run);
+    uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * bps, (uint32_t)c->n_reads);
+    slots = (uint32_t)std::min<size_t>(slots, budget / per_slot);
+    if (slots < 1) return c->fail(RG_ERR_NOMEM, "not enough device memory for one pathwise read in flight");
+    ws.slots = slots;
+    bool ok = c->d_pwS.ensure((size_t)slots * c->dpg.ring * ws.Lp * ws.Pp) && c->d_pwLead.ensure((size_t)slots * c->dpg.ring * ws.Lp) &&
+              c->d_pwTrace.ensure((size_t)slots * n * ws.Lp * PW * 2) && c->d_slot_runs.ensure((size_t)slots * ws.run_cap) &&
+              c->d_out_runs.ensure(out_runs_cap) && c->d_results.ensure(c->n_reads + 1) && c->d_counters.ensure(4);
+    if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
+    ws.S = c->d_pwS.p;
+    ws.lead = c->d_pwLead.p;
+    ws.trace = c->d_pwTrace.p;
+    ws.runs = c->d_slot_runs.p;
+    PoaBatch b{};
+    b.reads = c->d_reads.p;
+    b.read_off = c->d_read_off.p;
+    b.n_reads = c->n_reads;
+    b.order = c->d_order.p;
+    b.results = c->d_results.p;
+    b.out_runs = c->d_out_runs.p;
+    b.out_run_cap = out_runs_cap;
+    b.counters = c->d_counters.p;
+    cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
+    cudaEventRecord(c->ev0, c->stream);
+    int rc = launch_pathwise(mode, c->dpg, c->ds, ws, b, (int)slots, c->stream);
+    cudaEventRecord(c->ev1, c->stream);
+    if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("pathwise kernel");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->kernel_ms += ms;
+    c->launches += 1;
+    c->slots_used = slots;
+    cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("result copy");
+    c->n_runs_total = std::min<uint64_t>(c->h_counters.p[1], out_runs_cap);
+    return RG_OK;
+}
+
 int rg_align_staged(rg_ctx* c, int mode) {
     if (!c) return RG_ERR_INVALID;
     if (!c->has_graph) return c->fail(RG_ERR_INVALID, "no graph loaded");
@@ -491,6 +659,8 @@ int rg_align_staged(rg_ctx* c, int mode) {
         case RG_MODE_LOCAL:
         case RG_MODE_GAP_LOCAL:
         case RG_MODE_GAP_GLOBAL: rc = align_poa(c, mode); break;
+        case RG_MODE_PATHWISE_GLOBAL:
+        case RG_MODE_PATHWISE_SEMIGLOBAL: rc = align_pathwise(c, mode); break;
         default: return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
     }
     if (rc != RG_OK) return rc;

@@ -105,6 +105,7 @@ struct PwWorkspace {
     uint32_t run_cap;
     uint32_t slots;
 };
+int pathwise_blocks_per_sm(const DevPathGraph& g, const PwWorkspace& ws, int* nb);
 int launch_pathwise(int mode, const DevPathGraph& g, const DevScoring& s, const PwWorkspace& ws, const PoaBatch& b,
                     int blocks, void* stream);
 

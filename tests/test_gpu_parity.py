@@ -146,3 +146,16 @@ def test_mode3_reference_unit_vectors():
         al.set_scoring(table=table, gap_open=-o, gap_ext=-e)
         recs, _ = al.align(3, [read[1:]])
         assert recs[0].score == expected, cite
+
+
+@pytest.mark.parametrize("mode", ["4", "5"])
+@pytest.mark.parametrize("extra", [[], ["-M", "1", "-X", "3"], ["-t", "HOXD70"]])
+def test_pathwise_example(mode, extra):
+    _assert_same(["-m", mode] + extra + EX)
+
+
+@pytest.mark.parametrize("mode", ["4", "5"])
+@pytest.mark.parametrize("name", ["small", "mid", "short_reads", "long_read"])
+def test_pathwise_synthetic(synth_files, mode, name):
+    fa, gfa = synth_files[name]
+    _assert_same(["-m", mode, fa, gfa])
