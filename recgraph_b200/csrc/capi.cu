@@ -90,7 +90,15 @@ struct rg_ctx {
     DevBuf<uint32_t> d_alphas, d_node_bits, d_grp_off, d_grp_mask;
     DevBuf<PwGroup> d_grp;
     DevBuf<uint8_t> d_pw_nwp;
-    DevPathGraph dpg{};
+    DevPathGraph dpg{}, dpg_rev{};
+    DevBuf<uint32_t> d_rgrp_off, d_rgrp_mask;
+    DevBuf<PwGroup> d_rgrp;
+    DevBuf<uint8_t> d_rv_nwp;
+    DevBuf<uint64_t> d_seg;
+    DevBuf<int32_t> d_dfs, d_dfe;
+    DevBuf<int32_t> d_rS, d_rLead, d_lastcol;
+    DevBuf<uint32_t> d_rTrace;
+    DevBuf<int2> d_fm, d_rwbest;
     bool has_path_graph = false;
     std::string path_graph_error;
     DevBuf<int32_t> d_pwS, d_pwLead;
@@ -207,9 +215,16 @@ static int upload_path_graph(rg_ctx* c) {
     std::vector<PwGroup> grp;
     uint32_t max_groups = 1;
     build_groups(f, f.pw_nwp, f.pw_pred_off, f.pw_pred_idx, f.pw_edge_bits, false, grp_off, grp, grp_mask, max_groups);
+    std::vector<uint32_t> rgrp_off, rgrp_mask;
+    std::vector<PwGroup> rgrp;
+    uint32_t rmax_groups = 1;
+    build_groups(f, f.rv_nwp, f.rv_pred_off, f.rv_pred_idx, f.rv_edge_bits, true, rgrp_off, rgrp, rgrp_mask, rmax_groups);
     cudaStream_t st = c->stream;
     bool ok = c->d_alphas.upload(f.alphas, st) && c->d_node_bits.upload(f.node_bits, st) && c->d_grp_off.upload(grp_off, st) &&
-              c->d_grp_mask.upload(grp_mask, st) && c->d_grp.upload(grp, st) && c->d_pw_nwp.upload(f.pw_nwp, st);
+              c->d_grp_mask.upload(grp_mask, st) && c->d_grp.upload(grp, st) && c->d_pw_nwp.upload(f.pw_nwp, st) &&
+              c->d_rgrp_off.upload(rgrp_off, st) && c->d_rgrp_mask.upload(rgrp_mask, st) && c->d_rgrp.upload(rgrp, st) &&
+              c->d_rv_nwp.upload(f.rv_nwp, st) && c->d_seg.upload(f.row_seg_id, st) && c->d_dfs.upload(f.dfs, st) &&
+              c->d_dfe.upload(f.dfe, st);
     if (!ok || cudaStreamSynchronize(st) != cudaSuccess) return c->cuda_fail("path graph upload");
     uint32_t ring = 2;
     while (ring <= f.pw_max_lookback) ring <<= 1;
@@ -223,9 +238,20 @@ static int upload_path_graph(rg_ctx* c) {
     c->dpg.grp = c->d_grp.p;
     c->dpg.grp_mask = c->d_grp_mask.p;
     c->dpg.nwp = c->d_pw_nwp.p;
-    c->dpg.fpred_off = nullptr;
+    c->dpg.seg = c->d_seg.p;
+    c->dpg.dfs = c->d_dfs.p;
+    c->dpg.dfe = c->d_dfe.p;
     c->dpg.ring = ring;
     c->dpg.max_groups = max_groups;
+    c->dpg_rev = c->dpg;
+    c->dpg_rev.grp_off = c->d_rgrp_off.p;
+    c->dpg_rev.grp = c->d_rgrp.p;
+    c->dpg_rev.grp_mask = c->d_rgrp_mask.p;
+    c->dpg_rev.nwp = c->d_rv_nwp.p;
+    uint32_t rring = 2;
+    while (rring <= f.rv_max_lookback) rring <<= 1;
+    c->dpg_rev.ring = rring;
+    c->dpg_rev.max_groups = rmax_groups;
     c->has_path_graph = true;
     return RG_OK;
 }
@@ -415,6 +441,9 @@ int rg_set_scoring(rg_ctx* c, const rg_scoring* s) {
     c->ds.b = s->extra_b;
     c->ds.f = s->extra_f;
     c->ds.fixed_bta = s->fixed_bta;
+    c->ds.R = s->base_rec_cost;
+    c->ds.r = s->multi_rec_cost;
+    c->ds.rbw = s->rec_band_width;
     c->has_scoring = true;
     return RG_OK;
 }
@@ -584,20 +613,28 @@ static int align_pathwise(rg_ctx* c, int mode) {
         if (c->scoring.score[k][5] != c->scoring.score[0][5] || c->scoring.score[5][k] != c->scoring.score[0][5])
             return c->fail(RG_ERR_UNSUPPORTED, "pathwise modes need one gap score for all characters (true for every matrix the reference builds)");
     const uint32_t n = f.n, PW = f.PW;
+    const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
+    if (f.P > 128) return c->fail(RG_ERR_UNSUPPORTED, "more than 128 paths are not supported on the device yet");
+    if (n >= (1u << 21)) return c->fail(RG_ERR_UNSUPPORTED, "graph too large for the pathwise kernels");
     PwWorkspace ws{};
+    PwRecWorkspace rw{};
     ws.Lp = (c->max_len + 1 + 31) & ~31u;
     ws.Pp = PW * 32;
     ws.run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * ws.Lp), 1u << 22);
     int bps = 1;
-    int lc = pathwise_blocks_per_sm(c->dpg, ws, &bps);
+    int lc = pathwise_blocks_per_sm(c->dpg, c->dpg_rev, ws, rec, &bps);
     if (lc == -3) return c->fail(RG_ERR_UNSUPPORTED, "read too long for the pathwise kernel's shared-memory move table");
     if (lc != 0) return c->cuda_fail("kernel configuration");
     if (bps < 1) bps = 1;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    free_b += (c->d_pwS.cap + c->d_pwLead.cap + c->d_pwTrace.cap) * 4 + (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
-    const size_t per_slot = (size_t)c->dpg.ring * ws.Lp * ws.Pp * 4 + (size_t)c->dpg.ring * ws.Lp * 4 +
-                            (size_t)n * ws.Lp * PW * 8 + (size_t)ws.run_cap * sizeof(rg_run);
+    free_b += (c->d_pwS.cap + c->d_pwLead.cap + c->d_pwTrace.cap + c->d_rS.cap + c->d_rLead.cap + c->d_rTrace.cap + c->d_lastcol.cap) * 4 +
+              (c->d_fm.cap + c->d_rwbest.cap) * 8 + (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
+    size_t per_slot = (size_t)c->dpg.ring * ws.Lp * ws.Pp * 4 + (size_t)c->dpg.ring * ws.Lp * 4 +
+                      (size_t)n * ws.Lp * PW * 8 + (size_t)ws.run_cap * sizeof(rg_run);
+    if (rec)
+        per_slot += (size_t)c->dpg_rev.ring * ws.Lp * ws.Pp * 4 + (size_t)c->dpg_rev.ring * ws.Lp * 4 + (size_t)n * ws.Lp * PW * 8 +
+                    (size_t)n * ws.Lp * 16 + (size_t)n * ws.Pp * 4;
     const size_t budget_all = (size_t)(free_b * 0.85);
     size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(ws.run_cap, 16384), (budget_all / 8) / sizeof(rg_run));
     out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
@@ -609,7 +646,17 @@ static int align_pathwise(rg_ctx* c, int mode) {
     bool ok = c->d_pwS.ensure((size_t)slots * c->dpg.ring * ws.Lp * ws.Pp) && c->d_pwLead.ensure((size_t)slots * c->dpg.ring * ws.Lp) &&
               c->d_pwTrace.ensure((size_t)slots * n * ws.Lp * PW * 2) && c->d_slot_runs.ensure((size_t)slots * ws.run_cap) &&
               c->d_out_runs.ensure(out_runs_cap) && c->d_results.ensure(c->n_reads + 1) && c->d_counters.ensure(4);
+    if (ok && rec)
+        ok = c->d_rS.ensure((size_t)slots * c->dpg_rev.ring * ws.Lp * ws.Pp) && c->d_rLead.ensure((size_t)slots * c->dpg_rev.ring * ws.Lp) &&
+             c->d_rTrace.ensure((size_t)slots * n * ws.Lp * PW * 2) && c->d_fm.ensure((size_t)slots * n * ws.Lp) &&
+             c->d_rwbest.ensure((size_t)slots * n * ws.Lp) && c->d_lastcol.ensure((size_t)slots * n * ws.Pp);
     if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
+    rw.S = c->d_rS.p;
+    rw.lead = c->d_rLead.p;
+    rw.trace = c->d_rTrace.p;
+    rw.fm = c->d_fm.p;
+    rw.rw = c->d_rwbest.p;
+    rw.lastcol = c->d_lastcol.p;
     ws.S = c->d_pwS.p;
     ws.lead = c->d_pwLead.p;
     ws.trace = c->d_pwTrace.p;
@@ -625,7 +672,7 @@ static int align_pathwise(rg_ctx* c, int mode) {
     b.counters = c->d_counters.p;
     cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
     cudaEventRecord(c->ev0, c->stream);
-    int rc = launch_pathwise(mode, c->dpg, c->ds, ws, b, (int)slots, c->stream);
+    int rc = launch_pathwise(mode, c->dpg, c->dpg_rev, c->ds, ws, rw, b, (int)slots, c->stream);
     cudaEventRecord(c->ev1, c->stream);
     if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("pathwise kernel");
     float ms = 0;
@@ -660,7 +707,9 @@ int rg_align_staged(rg_ctx* c, int mode) {
         case RG_MODE_GAP_LOCAL:
         case RG_MODE_GAP_GLOBAL: rc = align_poa(c, mode); break;
         case RG_MODE_PATHWISE_GLOBAL:
-        case RG_MODE_PATHWISE_SEMIGLOBAL: rc = align_pathwise(c, mode); break;
+        case RG_MODE_PATHWISE_SEMIGLOBAL:
+        case RG_MODE_REC_GLOBAL:
+        case RG_MODE_REC_SEMIGLOBAL: rc = align_pathwise(c, mode); break;
         default: return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
     }
     if (rc != RG_OK) return rc;

@@ -40,6 +40,9 @@ struct DevScoring {
     int32_t o, e;
     float b, f;
     int32_t fixed_bta;
+    int32_t R;    // base recombination cost
+    float r;      // displacement multiplier
+    float rbw;    // recombination band width
 };
 
 // Per-row record kept for every row of the read in flight: trace base (offset of column 0 of the row inside the
@@ -92,7 +95,9 @@ struct DevPathGraph {
     const PwGroup* grp;          // groups of all rows
     const uint32_t* grp_mask;    // PW words per group: members
     const uint8_t* nwp;          // PathGraph nwp of this direction
-    const uint32_t* fpred_off;   // mode 4/8: groups of the 'F' row = (pred, edge paths): index range in grp (row n-1)
+    const uint64_t* seg;         // nodes_id_pos: segment id of each row (0 for rows 0 and n-1)
+    const int32_t* dfs;          // distance from start / from end (pathwise_graph.rs:306-354)
+    const int32_t* dfe;
     uint32_t ring;               // rows kept (pow2 > look-back)
     uint32_t max_groups;         // max groups per row
 };
@@ -105,9 +110,19 @@ struct PwWorkspace {
     uint32_t run_cap;
     uint32_t slots;
 };
-int pathwise_blocks_per_sm(const DevPathGraph& g, const PwWorkspace& ws, int* nb);
-int launch_pathwise(int mode, const DevPathGraph& g, const DevScoring& s, const PwWorkspace& ws, const PoaBatch& b,
-                    int blocks, void* stream);
+// extra buffers of modes 8/9: the reverse pass and the per-(row, column) arg-max tables of best_alignment
+struct PwRecWorkspace {
+    int32_t* S;        // slots * ring_rev * Lp * Pp
+    int32_t* lead;     // slots * ring_rev * Lp
+    uint32_t* trace;   // slots * n * Lp * PW * 2
+    int2* fm;          // slots * n * Lp : forward  {max over all path slots, path | member << 31}
+    int2* rw;          // slots * n * Lp : reverse, column index L-1-j
+    int32_t* lastcol;  // slots * n * Pp : forward scores of the last column
+};
+constexpr int REC_SURV = 2048;  // forward nodes of one column staged for the pair expansion
+int pathwise_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const PwWorkspace& ws, bool rec, int* nb);
+int launch_pathwise(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwWorkspace& ws,
+                    const PwRecWorkspace& rw, const PoaBatch& b, int blocks, void* stream);
 
 // launchers (poa_kernels.cu)
 int poa_launch_config(int mode, int trace_bytes, uint32_t Lmax, int* ws_cols, int* blocks_per_sm);

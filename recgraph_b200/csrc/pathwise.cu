@@ -1,16 +1,25 @@
-// Pathwise alignment, modes 4 / 5 (pathwise_alignment.rs:5-340, pathwise_alignment_semiglobal.rs:6-277) and their
-// traceback (pathwise_alignment_output.rs:7-184), in the exact ABSOLUTE-score form of SURVEY §3.4:
-// per row and per incoming edge ("group") the LEADER path does a linear-gap DP over the read, every other member
-// path copies the leader's move (D / U / L) applied to its own scores. This is what the reference's delta-encoded
-// tensor computes (verified against the literal restatement in oracle/pathwise.cpp).
+// Pathwise alignment (modes 4 / 5: pathwise_alignment.rs:5-340, pathwise_alignment_semiglobal.rs:6-277, traceback
+// pathwise_alignment_output.rs:7-184) and recombination alignment (modes 8 / 9:
+// pathwise_alignment_recombination.rs:23-897, tracebacks recombination_output.rs:12-782) on sm_100a.
+//
+// The DP is the exact ABSOLUTE-score form of SURVEY §3.4: per row and per incoming edge ("group") the LEADER path
+// does a linear-gap DP over the read, every other member path copies the leader's move (D / U / L) applied to its own
+// scores. This is what the reference's delta-encoded tensor computes (checked against the literal restatement in
+// oracle/pathwise.cpp). The reverse pass of modes 8/9 (`rev_align`) is the same routine on the reverse graph, rows
+// descending, with the read reversed (column jj = L-1-j).
 //
 // One CTA per read. Scores live in an L2-resident ring of rows, layout [row][column][path] so that a warp whose
 // lanes are paths reads and writes 128-byte lines. Per row:
 //   phase 1 (per group, all threads over column blocks): leader candidates, CTA-wide max-plus scan for the
 //           horizontal dependency, one move byte per column in shared memory;
 //   phase 2 (warps over column chunks, lanes = paths): members apply the move; each path also records its OWN
-//           arg-max (2 bits per path-cell, stored as two ballot bit-planes) — that is what build_alignment
-//           re-derives from the stored scores when it walks the best path back.
+//           arg-max (2 bits per path-cell, stored as two ballot bit-planes) — what build_alignment re-derives from
+//           the stored scores when it walks a path back. Modes 8/9 also keep, per (row, column), the arg-max over
+//           ALL path slots (non-member slots hold 0 as in the reference) for best_alignment.
+// best_alignment (pathwise_alignment_recombination.rs:759-873) is an exact pruned reduction: a (column, node) pair
+// is expanded over the second node only if its upper bound m + max_w - R can still reach the running maximum;
+// the f32 arithmetic uses separately rounded mul / add / sub exactly as the reference, and the sequential
+// acceptance rule is restated as (max score; first index with it; first index with it that is on a segment edge).
 #include <cuda_runtime.h>
 
 #include "device.h"
@@ -18,11 +27,11 @@
 
 namespace rg {
 
-constexpr int PT = 256;  // threads per CTA
+constexpr int PT = 256;    // threads per CTA
+constexpr int MAXPW = 4;   // up to 128 paths
 enum { MV_D = 1, MV_U = 2, MV_L = 3 };
 
 __device__ __forceinline__ int block_excl_max(int z, int tid, int* s_w) {
-    // exclusive prefix max over the CTA's threads (identity NEG_INF)
     const int lane = tid & 31, w = tid >> 5;
     int inc = warp_incl_max(z, lane);
     if (lane == 31) s_w[w] = inc;
@@ -35,27 +44,324 @@ __device__ __forceinline__ int block_excl_max(int z, int tid, int* s_w) {
     return max(base, exc);
 }
 
-__global__ void __launch_bounds__(PT) k_pathwise(DevPathGraph g, DevScoring sc, PwWorkspace ws, PoaBatch b, int mode) {
+struct PwSmem {
+    unsigned char* mv;  // [max_groups][Lp]
+    int32_t* du;        // [Lp]
+    int32_t* res;       // [Pp]
+    uint32_t* end;      // [Pp]
+    int* w;             // [PT/32]
+};
+
+struct PwDir {  // buffers of one DP direction for the read in flight
+    int32_t* S;
+    int32_t* lead;
+    uint32_t* trace;
+    int2* colbest;     // modes 8/9: per (row, column): {max over all slots, path | member << 31}
+    int32_t* lastcol;  // forward: [row][Pp] scores of the last column
+};
+
+// One DP pass over all rows. Returns nothing; mode-5 best end and mode-4 results are left in shared memory.
+__device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, const int32_t* s_sc,
+                      const uint8_t* read, int L, uint32_t Lp, uint32_t Pp, bool rev, bool free_border, bool track_best,
+                      bool track_results, int g_gr, int g_rd, int* s_best_val, int* s_best_set, uint32_t* s_best_row,
+                      uint32_t* s_best_path) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = g.n, P = g.P, PW = g.PW, RM = g.ring - 1;
+    const uint32_t base_row = rev ? n - 1 : 0;
+    auto rcode = [&](int jj) -> unsigned { return rev ? read[L - 1 - jj] : read[jj - 1]; };
+    // ---- base row: every path carries the accumulated read gaps (pathwise_alignment_semiglobal.rs:26-32,
+    //      pathwise_alignment_recombination.rs:148-155)
+    {
+        int32_t* Sb = d.S + (size_t)(base_row & RM) * Lp * Pp;
+        for (uint32_t idx = tid; idx < (uint32_t)L * Pp; idx += PT) {
+            const uint32_t j = idx / Pp, q = idx % Pp;
+            Sb[(size_t)j * Pp + q] = (q < P) ? (int)j * g_rd : 0;
+        }
+        int32_t* lb = d.lead + (size_t)(base_row & RM) * Lp;
+        for (int j = tid; j < L; j += PT) lb[j] = j * g_rd;
+        if (d.lastcol && !rev)
+            for (uint32_t q = tid; q < Pp; q += PT) d.lastcol[q] = (q < P) ? (L - 1) * g_rd : 0;
+    }
+    __syncthreads();
+    const int Cc = (L - 1 + PT - 1) / PT;
+    const int chunk = (L + PT / 32 - 1) / (PT / 32);
+
+    for (uint32_t t = 1; t + 1 < n; t++) {
+        const uint32_t i = rev ? n - 1 - t : t;
+        const uint32_t g0 = g.grp_off[i], g1 = g.grp_off[i + 1];
+        const int li = g.lnz[i];
+        const int32_t* srow = s_sc + li * 8;
+        const uint32_t alpha_i = g.alphas[i];
+        int32_t* Si = d.S + (size_t)(i & RM) * Lp * Pp;
+        int32_t* lead_i = d.lead + (size_t)(i & RM) * Lp;
+        // ================= phase 1: the leader's DP of every group =================
+        for (uint32_t gi = g0; gi < g1; gi++) {
+            const PwGroup gr = g.grp[gi];
+            unsigned char* mv = sm.mv + (size_t)(gi - g0) * Lp;
+            const int32_t* lp = gr.lead_is_alpha_of_pred ? d.lead + (size_t)(gr.pred & RM) * Lp : nullptr;
+            const int32_t* Sp = d.S + (size_t)(gr.pred & RM) * Lp * Pp + gr.leader;
+            const int m0 = free_border ? 0 : (lp ? lp[0] : Sp[0]) + g_gr;
+            const int jb = 1 + tid * Cc, je = min(L, jb + Cc);
+            int v = NEG_INF;
+            int pl = (jb < L) ? (lp ? lp[jb - 1] : Sp[(size_t)(jb - 1) * Pp]) : 0;
+            for (int j = jb; j < je; j++) {
+                const int pc = lp ? lp[j] : Sp[(size_t)j * Pp];
+                const int dd = pl + srow[rcode(j)];
+                const int u = pc + g_gr;
+                const int du = max(dd, u);
+                sm.du[j] = du;
+                mv[j] = (dd >= u) ? MV_D : MV_U;  // equality tests in the order d, u (…_semiglobal.rs:46-57)
+                int gen = du;
+                if (j == 1) gen = max(du, m0 + g_rd);
+                v = max(v + g_rd, gen);
+                pl = pc;
+            }
+            const int z = (jb < je && v > NEG_INF / 2) ? v - (je - 1) * g_rd : NEG_INF;
+            const int wexc = block_excl_max(z, tid, sm.w);
+            int lcand = (wexc > NEG_INF / 2) ? wexc + jb * g_rd : NEG_INF;  // m[jb-1] + g_rd
+            const bool own_alpha = gr.leader == alpha_i;
+            for (int j = jb; j < je; j++) {
+                if (j == 1) lcand = m0 + g_rd;
+                const int du = sm.du[j];
+                int m = du;
+                if (lcand > du) {
+                    m = lcand;
+                    mv[j] = MV_L;
+                }
+                if (own_alpha) lead_i[j] = m;
+                lcand = m + g_rd;
+            }
+            if (own_alpha && tid == 0) lead_i[0] = m0;
+        }
+        __syncthreads();
+        // ================= phase 2: members apply their leader's move =================
+        {
+            const int jb = warp * chunk, je = min(L, jb + chunk);
+            // per pass (32 paths) state
+            int gq[MAXPW];
+            const int32_t* Spq[MAXPW];
+            bool quirk[MAXPW];
+            int col0[MAXPW], prev_new[MAXPW], sp_prev[MAXPW];
+#pragma unroll
+            for (int ps = 0; ps < MAXPW; ps++) {
+                gq[ps] = -1;
+                Spq[ps] = d.S;
+                quirk[ps] = false;
+                col0[ps] = prev_new[ps] = sp_prev[ps] = 0;
+                if ((uint32_t)ps >= PW) continue;
+                const uint32_t q = ps * 32 + lane;
+                uint32_t pq = 0;
+                if (q < P)
+                    for (uint32_t gi = g0; gi < g1; gi++)
+                        if ((g.grp_mask[(size_t)gi * PW + ps] >> lane) & 1u) {
+                            gq[ps] = (int)(gi - g0);
+                            pq = g.grp[gi].pred;
+                        }
+                if (gq[ps] < 0) continue;
+                Spq[ps] = d.S + (size_t)(pq & RM) * Lp * Pp + q;
+                // reverse pass: the 'F' row is never made absolute by the reference (absolute_scores stops before it,
+                // pathwise_alignment_recombination.rs:748), so its traceback sees 0 for every path but path 0
+                quirk[ps] = rev && pq == n - 1 && q != 0;
+                col0[ps] = free_border ? 0 : Spq[ps][0] + g_gr;
+                if (jb > 0 && jb < je) {
+                    const unsigned char* mv = sm.mv + (size_t)gq[ps] * Lp;
+                    int j0 = jb - 1;
+                    while (j0 >= 1 && mv[j0] == MV_L) j0--;
+                    int base;
+                    if (j0 == 0)
+                        base = col0[ps];
+                    else if (mv[j0] == MV_D)
+                        base = Spq[ps][(size_t)(j0 - 1) * Pp] + srow[rcode(j0)];
+                    else
+                        base = Spq[ps][(size_t)j0 * Pp] + g_gr;
+                    prev_new[ps] = base + (jb - 1 - j0) * g_rd;
+                    sp_prev[ps] = Spq[ps][(size_t)(jb - 1) * Pp];
+                }
+            }
+            int row_best = NEG_INF;
+            uint32_t row_path = 0;
+            for (int j = jb; j < je; j++) {
+                const int sj = (j >= 1) ? srow[rcode(j)] : 0;
+                int cb_val = NEG_INF;
+                uint32_t cb_path = 0;
+#pragma unroll
+                for (int ps = 0; ps < MAXPW; ps++) {
+                    if ((uint32_t)ps >= PW) continue;
+                    const uint32_t q = ps * 32 + lane;
+                    const bool member = gq[ps] >= 0;
+                    int nv = 0;
+                    unsigned code = 0;
+                    if (member) {
+                        const int sp = Spq[ps][(size_t)j * Pp];
+                        if (j == 0) {
+                            nv = col0[ps];
+                        } else {
+                            const unsigned m = sm.mv[(size_t)gq[ps] * Lp + j];
+                            const int lq = prev_new[ps] + g_rd;
+                            nv = (m == MV_D) ? sp_prev[ps] + sj : ((m == MV_U) ? sp + g_gr : lq);
+                            // own arg-max in build_alignment's order: d, then u, else l
+                            const int dq = (quirk[ps] ? 0 : sp_prev[ps]) + sj, uq = (quirk[ps] ? 0 : sp) + g_gr;
+                            const int bq = max(dq, max(uq, lq));
+                            code = (bq == dq) ? MV_D : ((bq == uq) ? MV_U : MV_L);
+                        }
+                        sp_prev[ps] = sp;
+                        prev_new[ps] = nv;
+                    }
+                    Si[(size_t)j * Pp + q] = nv;
+                    const unsigned p0 = __ballot_sync(FULL, code & 1u), p1 = __ballot_sync(FULL, code & 2u);
+                    if (lane == 0) reinterpret_cast<uint2*>(d.trace)[((size_t)i * Lp + j) * PW + ps] = make_uint2(p0, p1);
+                    if (d.colbest) {
+                        // max of (score, path) over ALL slots; the highest path id wins ties (…_recombination.rs:809-830)
+                        const int val = (q < P) ? nv : NEG_INF;
+                        const int mx = __reduce_max_sync(FULL, val);
+                        if (mx >= cb_val) {
+                            const unsigned eq = __ballot_sync(FULL, val == mx);
+                            cb_val = mx;
+                            cb_path = ps * 32 + (31 - __clz(eq));
+                        }
+                    }
+                    if (j == L - 1 && !rev) {
+                        if (d.lastcol) d.lastcol[(size_t)i * Pp + q] = nv;
+                        const int cand = member ? nv : NEG_INF;
+                        const int mx = __reduce_max_sync(FULL, cand);
+                        const unsigned eq = __ballot_sync(FULL, member && cand == mx);
+                        if (eq && mx > row_best) {  // first strict maximum in path order
+                            row_best = mx;
+                            row_path = ps * 32 + (__ffs(eq) - 1);
+                        }
+                        if (track_results && member)
+                            for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
+                                if (g.grp[fg].pred == i && ((g.grp_mask[(size_t)fg * PW + ps] >> lane) & 1u)) {
+                                    sm.res[q] = nv;   // pathwise_alignment.rs:305-319
+                                    sm.end[q] = i;
+                                }
+                    }
+                }
+                if (d.colbest && lane == 0) {
+                    const bool memb = (g.node_bits[(size_t)i * PW + cb_path / 32] >> (cb_path % 32)) & 1u;
+                    d.colbest[(size_t)i * Lp + j] = make_int2(cb_val, (int)(cb_path | (memb ? 0x80000000u : 0u)));
+                }
+            }
+            if (track_best && je == L && jb < je && lane == 0 && row_best > NEG_INF / 2) {
+                // …_semiglobal.rs:269-273: a row replaces the incumbent only if strictly better
+                if (!*s_best_set || row_best > *s_best_val) {
+                    *s_best_set = 1;
+                    *s_best_val = row_best;
+                    *s_best_row = i;
+                    *s_best_path = row_path;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// own-argmax code of path q at (row, col) in one direction's trace
+__device__ __forceinline__ unsigned pw_code(const uint32_t* trace, uint32_t Lp, uint32_t PW, uint32_t row, int col, uint32_t q) {
+    const uint2 pl = reinterpret_cast<const uint2*>(trace)[((size_t)row * Lp + col) * PW + q / 32];
+    return ((pl.x >> (q % 32)) & 1u) | (((pl.y >> (q % 32)) & 1u) << 1);
+}
+__device__ __forceinline__ uint32_t pw_pred(const DevPathGraph& g, uint32_t row, uint32_t q, uint32_t dflt) {
+    uint32_t pred = dflt;
+    for (uint32_t gi = g.grp_off[row]; gi < g.grp_off[row + 1]; gi++)
+        if ((g.grp_mask[(size_t)gi * g.PW + q / 32] >> (q % 32)) & 1u) pred = g.grp[gi].pred;
+    return pred;
+}
+
+// Forward-direction walk shared by build_alignment (pathwise_alignment_output.rs:7-184), the no_rec builders
+// (recombination_output.rs:239-361,633-782) and the forward half of the rec builders (:100-163,472-557).
+__device__ void pw_walk_fwd(const DevPathGraph& g, const uint32_t* trace, uint32_t Lp, const uint8_t* read, uint32_t path,
+                            uint32_t& ii, int& j, bool pad_global, RunEmitter& em) {
+    while (ii > 0 && j > 0) {
+        const unsigned code = pw_code(trace, Lp, g.PW, ii, j, path);
+        if (code == MV_D) {
+            em.step(g.lnz[ii] != read[j - 1] ? RG_OP_d : RG_OP_D, ii, 0);
+            ii = pw_pred(g, ii, path, ii - 1);
+            j--;
+        } else if (code == MV_U) {
+            em.step(RG_OP_U, ii, 0);
+            ii = pw_pred(g, ii, path, ii - 1);
+        } else {
+            em.step(RG_OP_L, ii, 0);
+            j--;
+        }
+    }
+    while (j > 0) {
+        em.step(RG_OP_L, ii, 0);
+        j--;
+    }
+    if (pad_global)
+        while (ii > 0) {
+            em.step(RG_OP_U, ii, 0);
+            ii = pw_pred(g, ii, path, g.nwp[ii] ? 0u : ii - 1);
+        }
+}
+
+struct RecBest {   // state of best_alignment's reduction
+    float v;            // maximum candidate score
+    unsigned long long k1;  // first (j,i,ri) with score v
+    unsigned long long k2;  // first (j,i,ri) with score v on a segment edge
+};
+__device__ __forceinline__ void rec_merge(RecBest& a, float v, unsigned long long key, bool edge) {
+    if (v > a.v) {
+        a.v = v;
+        a.k1 = key;
+        a.k2 = edge ? key : ~0ull;
+    } else if (v == a.v) {
+        a.k1 = min(a.k1, key);
+        if (edge) a.k2 = min(a.k2, key);
+    }
+}
+__device__ __forceinline__ void rec_merge2(RecBest& a, const RecBest& o) {
+    if (o.v > a.v)
+        a = o;
+    else if (o.v == a.v) {
+        a.k1 = min(a.k1, o.k1);
+        a.k2 = min(a.k2, o.k2);
+    }
+}
+
+__global__ void __launch_bounds__(PT) k_pathwise(DevPathGraph g, DevPathGraph rg_, DevScoring sc, PwWorkspace ws,
+                                                  PwRecWorkspace rw, PoaBatch b, int mode) {
     extern __shared__ unsigned char s_dyn[];
     __shared__ int32_t s_sc[48];
     __shared__ int s_w[PT / 32];
     __shared__ unsigned long long s_ticket;
     __shared__ int s_best_val, s_best_set;
     __shared__ uint32_t s_best_row, s_best_path;
+    __shared__ float s_redv[PT / 32];
+    __shared__ unsigned long long s_redk1[PT / 32], s_redk2[PT / 32];
+    __shared__ int s_red_i[PT / 32];
+    __shared__ RecBest s_rb;
+    __shared__ int s_nsurv;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t slot = blockIdx.x;
     if (tid < 48) s_sc[tid] = (&sc.sc[0][0])[tid];
-    const uint32_t n = g.n, P = g.P, PW = g.PW, Lp = ws.Lp, Pp = ws.Pp, RM = g.ring - 1;
-    // dynamic smem: moves [max_groups][Lp] bytes | du [Lp] ints | results [Pp] ints | ending [Pp] uints
-    unsigned char* s_mv = s_dyn;
-    int32_t* s_du = reinterpret_cast<int32_t*>(s_dyn + (((size_t)g.max_groups * Lp + 15) & ~(size_t)15));
-    int32_t* s_res = s_du + Lp;
-    uint32_t* s_end = reinterpret_cast<uint32_t*>(s_res + Pp);
-    int32_t* S = ws.S + (size_t)slot * g.ring * Lp * Pp;
-    int32_t* lead = ws.lead + (size_t)slot * g.ring * Lp;
-    uint32_t* trace = ws.trace + (size_t)slot * n * Lp * PW * 2;
+    const uint32_t n = g.n, P = g.P, PW = g.PW, Lp = ws.Lp, Pp = ws.Pp;
+    const uint32_t mg = max(g.max_groups, rg_.max_groups);
+    PwSmem sm;
+    sm.mv = s_dyn;
+    sm.du = reinterpret_cast<int32_t*>(s_dyn + (((size_t)mg * Lp + 15) & ~(size_t)15));
+    sm.res = sm.du + Lp;
+    sm.end = reinterpret_cast<uint32_t*>(sm.res + Pp);
+    sm.w = s_w;
+    uint32_t* s_surv = sm.end + Pp;  // [REC_SURV] survivors of one column (modes 8/9)
+    const bool rec_mode = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
+    const bool global_mode = mode == RG_MODE_PATHWISE_GLOBAL || mode == RG_MODE_REC_GLOBAL;
+    PwDir fwd, rvd;
+    fwd.S = ws.S + (size_t)slot * g.ring * Lp * Pp;
+    fwd.lead = ws.lead + (size_t)slot * g.ring * Lp;
+    fwd.trace = ws.trace + (size_t)slot * n * Lp * PW * 2;
+    fwd.colbest = rec_mode ? rw.fm + (size_t)slot * n * Lp : nullptr;
+    fwd.lastcol = rec_mode ? rw.lastcol + (size_t)slot * n * Pp : nullptr;
+    if (rec_mode) {
+        rvd.S = rw.S + (size_t)slot * rg_.ring * Lp * Pp;
+        rvd.lead = rw.lead + (size_t)slot * rg_.ring * Lp;
+        rvd.trace = rw.trace + (size_t)slot * n * Lp * PW * 2;
+        rvd.colbest = rw.rw + (size_t)slot * n * Lp;
+        rvd.lastcol = nullptr;
+    }
     rg_run* runs = ws.runs + (size_t)slot * ws.run_cap;
-    const bool global_mode = (mode == RG_MODE_PATHWISE_GLOBAL);
     const int g_gr = sc.sc[0][5], g_rd = sc.sc[0][5];  // uniform gap score (checked on the host)
     __syncthreads();
 
@@ -76,7 +382,7 @@ __global__ void __launch_bounds__(PT) k_pathwise(DevPathGraph g, DevScoring sc, 
         res.end_row = res.end_col = res.start_row = res.start_col = 0;
         res.best_path = res.rev_best_path = 0;
         res.fen = res.rsn = res.rec_col = res.rev_end_row = 0;
-        res.cells = (uint64_t)(n - 2) * (uint64_t)(L - 1);
+        res.cells = (uint64_t)(n - 2) * (uint64_t)(L - 1) * (rec_mode ? 2 : 1);
         res.run_off = 0;
         res.n_runs = 0;
         res.n_runs_rev = 0;
@@ -92,221 +398,334 @@ __global__ void __launch_bounds__(PT) k_pathwise(DevPathGraph g, DevScoring sc, 
             s_best_path = 0;
         }
         for (uint32_t q = tid; q < Pp; q += PT) {
-            s_res[q] = 0;
-            s_end[q] = 0;
+            sm.res[q] = 0;
+            sm.end[q] = 0;
         }
-        // ---- row 0: every path carries the accumulated read gaps (pathwise_alignment_semiglobal.rs:26-32)
-        for (uint32_t idx = tid; idx < (uint32_t)L * Pp; idx += PT) {
-            const uint32_t j = idx / Pp, q = idx % Pp;
-            S[(size_t)j * Pp + q] = (q < P) ? (int)j * g_rd : 0;
-        }
-        for (int j = tid; j < L; j += PT) lead[j] = j * g_rd;
         __syncthreads();
+        pw_dp(g, fwd, sm, s_sc, read, L, Lp, Pp, false, !global_mode, mode == RG_MODE_PATHWISE_SEMIGLOBAL,
+              mode == RG_MODE_PATHWISE_GLOBAL, g_gr, g_rd, &s_best_val, &s_best_set, &s_best_row, &s_best_path);
+        if (rec_mode)
+            pw_dp(rg_, rvd, sm, s_sc, read, L, Lp, Pp, true, !global_mode, false, false, g_gr, g_rd, &s_best_val,
+                  &s_best_set, &s_best_row, &s_best_path);
 
-        const int Cc = (L - 1 + PT - 1) / PT;        // phase 1: columns per thread
-        const int chunk = (L + PT / 32 - 1) / (PT / 32);  // phase 2: columns per warp
-
-        for (uint32_t i = 1; i + 1 < n; i++) {
-            const uint32_t g0 = g.grp_off[i], g1 = g.grp_off[i + 1];
-            const int li = g.lnz[i];
-            const int32_t* srow = s_sc + li * 8;
-            const uint32_t alpha_i = g.alphas[i];
-            int32_t* Si = S + (size_t)(i & RM) * Lp * Pp;
-            int32_t* lead_i = lead + (size_t)(i & RM) * Lp;
-            // ================= phase 1: the leader's DP of every group =================
-            for (uint32_t gi = g0; gi < g1; gi++) {
-                const PwGroup gr = g.grp[gi];
-                unsigned char* mv = s_mv + (size_t)(gi - g0) * Lp;
-                const int32_t* lp = gr.lead_is_alpha_of_pred ? lead + (size_t)(gr.pred & RM) * Lp : nullptr;
-                const int32_t* Sp = S + (size_t)(gr.pred & RM) * Lp * Pp + gr.leader;
-                const int m0 = global_mode ? (lp ? lp[0] : Sp[0]) + g_gr : 0;  // column 0 of this row for the leader
-                const int jb = 1 + tid * Cc, je = min(L, jb + Cc);
-                int v = NEG_INF;
-                int pl = (jb < L) ? (lp ? lp[jb - 1] : Sp[(size_t)(jb - 1) * Pp]) : 0;
-                for (int j = jb; j < je; j++) {
-                    const int pc = lp ? lp[j] : Sp[(size_t)j * Pp];
-                    const int d = pl + srow[read[j - 1]];
-                    const int u = pc + g_gr;
-                    const int du = max(d, u);
-                    s_du[j] = du;
-                    mv[j] = (d >= u) ? MV_D : MV_U;  // equality tests in the order d, u (pathwise_alignment_semiglobal.rs:46-57)
-                    int gen = du;
-                    if (j == 1) gen = max(du, m0 + g_rd);
-                    v = max(v + g_rd, gen);
-                    pl = pc;
+        if (!rec_mode) {
+            // ================= modes 4 / 5: end cell, traceback (thread 0), publish =================
+            if (tid == 0) {
+                uint32_t best_path, ending;
+                int score;
+                if (global_mode) {
+                    // max of (score, path): highest path id wins ties (pathwise_alignment.rs:320-325)
+                    best_path = 0;
+                    for (uint32_t q = 1; q < P; q++)
+                        if (sm.res[q] >= sm.res[best_path]) best_path = q;
+                    ending = sm.end[best_path];
+                    score = sm.res[best_path];
+                } else {
+                    best_path = s_best_path;
+                    ending = s_best_row;
+                    score = s_best_val;
                 }
-                int z = (jb < je && v > NEG_INF / 2) ? v - (je - 1) * g_rd : NEG_INF;
-                const int wexc = block_excl_max(z, tid, s_w);
-                int lcand = (wexc > NEG_INF / 2) ? wexc + jb * g_rd : NEG_INF;  // m[jb-1] + g_rd
-                const bool own_alpha = gr.leader == alpha_i;
-                for (int j = jb; j < je; j++) {
-                    if (j == 1) lcand = m0 + g_rd;
-                    const int du = s_du[j];
-                    int m = du;
-                    if (lcand > du) {
-                        m = lcand;
-                        mv[j] = MV_L;
-                    }
-                    if (own_alpha) lead_i[j] = m;
-                    lcand = m + g_rd;
+                res.score = score;
+                res.best_path = best_path;
+                res.end_row = ending;
+                res.end_col = (uint32_t)(L - 1);
+                RunEmitter em;
+                em.init(runs, ws.run_cap);
+                uint32_t ii = ending;
+                int j = L - 1;
+                pw_walk_fwd(g, fwd.trace, Lp, read, best_path, ii, j, global_mode, em);
+                em.flush(0);
+                res.start_row = ii;
+                if (em.overflow) res.status |= RG_READ_TRACE_OVERFLOW;
+                uint32_t nr = em.overflow ? 0 : em.n;
+                unsigned long long ro = atomicAdd(&b.counters[1], (unsigned long long)nr);
+                if (ro + nr > b.out_run_cap) {
+                    res.status |= RG_READ_TRACE_OVERFLOW;
+                    nr = 0;
                 }
-                if (own_alpha && tid == 0) lead_i[0] = m0;
+                for (uint32_t k = 0; k < nr; k++) b.out_runs[ro + k] = runs[k];
+                res.run_off = ro;
+                res.n_runs = nr;
+                b.results[ridx] = res;
             }
             __syncthreads();
-            // ================= phase 2: members apply their leader's move =================
-            {
-                const int jb = warp * chunk, je = min(L, jb + chunk);
-                int row_best = NEG_INF;
-                uint32_t row_path = 0;
-                for (uint32_t pass = 0; pass < PW; pass++) {
-                    const uint32_t q = pass * 32 + lane;
-                    // my group
-                    int gq = -1;
-                    uint32_t pq = 0;
-                    if (q < P)
-                        for (uint32_t gi = g0; gi < g1; gi++)
-                            if ((g.grp_mask[(size_t)gi * PW + pass] >> lane) & 1u) {
-                                gq = (int)(gi - g0);
-                                pq = g.grp[gi].pred;
-                            }
-                    const bool member = gq >= 0;
-                    const int32_t* Sp = S + (size_t)(pq & RM) * Lp * Pp + q;
-                    const unsigned char* mv = s_mv + (size_t)(member ? gq : 0) * Lp;
-                    const int col0 = (member && global_mode) ? Sp[0] + g_gr : 0;
-                    int prev_new = 0, sp_prev = 0;
-                    if (member && jb > 0 && jb < je) {
-                        // value of column jb-1 of this row: walk the L-run back to its anchor (another warp owns it)
-                        int j0 = jb - 1;
-                        while (j0 >= 1 && mv[j0] == MV_L) j0--;
-                        int base;
-                        if (j0 == 0)
-                            base = col0;
-                        else if (mv[j0] == MV_D)
-                            base = Sp[(size_t)(j0 - 1) * Pp] + srow[read[j0 - 1]];
-                        else
-                            base = Sp[(size_t)j0 * Pp] + g_gr;
-                        prev_new = base + (jb - 1 - j0) * g_rd;
-                        sp_prev = Sp[(size_t)(jb - 1) * Pp];
-                    }
-                    for (int j = jb; j < je; j++) {
-                        int nv = 0;
-                        unsigned code = 0;
-                        if (member) {
-                            const int sp = Sp[(size_t)j * Pp];
-                            if (j == 0) {
-                                nv = col0;
-                            } else {
-                                const int sj = srow[read[j - 1]];
-                                const int dq = sp_prev + sj, uq = sp + g_gr, lq = prev_new + g_rd;
-                                const unsigned m = mv[j];
-                                nv = (m == MV_D) ? dq : ((m == MV_U) ? uq : lq);
-                                // own arg-max in build_alignment's order: d, then u, else l
-                                const int bq = max(dq, max(uq, lq));
-                                code = (bq == dq) ? MV_D : ((bq == uq) ? MV_U : MV_L);
-                            }
-                            sp_prev = sp;
-                            prev_new = nv;
-                        }
-                        Si[(size_t)j * Pp + q] = nv;
-                        const unsigned p0 = __ballot_sync(FULL, code & 1u), p1 = __ballot_sync(FULL, code & 2u);
-                        if (lane == 0)
-                            reinterpret_cast<uint2*>(trace)[((size_t)i * Lp + j) * PW + pass] = make_uint2(p0, p1);
-                        if (j == L - 1) {
-                            // candidates of the last column (best_ending_node / results of mode 4)
-                            const int cand = member ? nv : NEG_INF;
-                            const int mx = __reduce_max_sync(FULL, cand);
-                            const unsigned eq = __ballot_sync(FULL, member && cand == mx);
-                            if (eq && mx > row_best) {  // first strict maximum in path order
-                                row_best = mx;
-                                row_path = pass * 32 + (__ffs(eq) - 1);
-                            }
-                            if (global_mode && member) {
-                                // pathwise_alignment.rs:305-319: paths whose last node this row is
-                                for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
-                                    if (g.grp[fg].pred == i && ((g.grp_mask[(size_t)fg * PW + pass] >> lane) & 1u)) {
-                                        s_res[q] = nv;
-                                        s_end[q] = i;
-                                    }
+            continue;
+        }
+
+        // ================= modes 8 / 9: best_alignment (…_recombination.rs:759-873) =================
+        // 1. baseline (no recombination)
+        if (tid == 0) {
+            bool has = false;
+            int mx = 0;
+            uint32_t bp = 0;
+            if (mode == RG_MODE_REC_GLOBAL) {
+                for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++) {
+                    const uint32_t pred = g.grp[fg].pred;
+                    for (uint32_t q = 0; q < P; q++)
+                        if ((g.grp_mask[(size_t)fg * PW + q / 32] >> (q % 32)) & 1u) {
+                            const int v = fwd.lastcol[(size_t)pred * Pp + q];
+                            if (!has || mx < v) {
+                                has = true;
+                                mx = v;
+                                bp = q;
                             }
                         }
+                }
+            } else {
+                for (uint32_t i = 0; i + 1 < n; i++)
+                    for (uint32_t q = 0; q < P; q++)
+                        if ((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u) {
+                            const int v = fwd.lastcol[(size_t)i * Pp + q];
+                            if (!has || mx < v) {
+                                has = true;
+                                mx = v;
+                                bp = q;
+                            }
+                        }
+            }
+            s_best_val = mx;
+            s_best_path = bp;
+            s_rb.v = (float)mx;
+            s_rb.k1 = ~0ull;
+            s_rb.k2 = ~0ull;
+        }
+        __syncthreads();
+        const int base_score = s_best_val;
+        const uint32_t base_path = s_best_path;
+        // 2. candidates. out_of_band = max((L * (1 - B) / 2) as i32, 1)
+        int oob;
+        {
+            const float t1 = __fmul_rn((float)L, __fsub_rn(1.0f, sc.rbw));
+            const float t2 = __fdiv_rn(t1, 2.0f);
+            int oi = (t2 != t2) ? 0 : (t2 >= 2147483648.0f ? 2147483647 : (t2 <= -2147483648.0f ? (-2147483647 - 1) : (int)t2));
+            oob = max(oi, 1);
+        }
+        const float Rf = (float)sc.R;
+        const bool prune = sc.r >= 0.0f;
+        RecBest mine;
+        mine.v = (float)base_score;
+        mine.k1 = ~0ull;
+        mine.k2 = ~0ull;
+        for (int j = oob; j < L - oob; j++) {
+            const int jj = L - 1 - j;  // column of w in the reverse pass's coordinates
+            // upper bounds of this column
+            int wmax = NEG_INF;
+            for (uint32_t ri = 1 + tid; ri + 1 < n; ri += PT) {
+                const int2 e = rvd.colbest[(size_t)ri * Lp + jj];
+                if (e.y < 0) wmax = max(wmax, e.x);
+            }
+            wmax = __reduce_max_sync(FULL, wmax);
+            if (lane == 0) s_red_i[warp] = wmax;
+            if (tid == 0) s_nsurv = 0;
+            __syncthreads();
+            wmax = s_red_i[0];
+            for (int k = 1; k < PT / 32; k++) wmax = max(wmax, s_red_i[k]);
+            const float cur = s_rb.v;
+            __syncthreads();
+            if (wmax <= NEG_INF / 2) continue;
+            // survivors: forward nodes whose best case can still reach the running maximum
+            for (uint32_t i = 1 + tid; i + 1 < n; i += PT) {
+                const int2 e = fwd.colbest[(size_t)i * Lp + j];
+                if (e.y >= 0) continue;  // arg-max slot is not a member path (…_recombination.rs:833)
+                const float ub = __fsub_rn((float)(e.x + wmax), Rf);
+                if (!prune || ub >= cur) {
+                    const int pos = atomicAdd(&s_nsurv, 1);
+                    if (pos < REC_SURV) s_surv[pos] = i;
+                }
+            }
+            __syncthreads();
+            const int nsurv = s_nsurv;
+            if (nsurv > REC_SURV) {
+                // too many to stage: every thread walks all forward nodes itself (exact, just slower)
+                for (uint32_t i = 1; i + 1 < n; i++) {
+                    const int2 fe = fwd.colbest[(size_t)i * Lp + j];
+                    if (fe.y >= 0) continue;
+                    const uint32_t fp = (uint32_t)fe.y & 0x7fffffffu;
+                    const uint32_t seg_i = g.seg[i];
+                    const bool iedge = seg_i != g.seg[i + 1];
+                    for (uint32_t ri = 1 + tid; ri + 1 < n; ri += PT) {
+                        const int2 we = rvd.colbest[(size_t)ri * Lp + jj];
+                        if (we.y >= 0) continue;
+                        const uint32_t rp = (uint32_t)we.y & 0x7fffffffu;
+                        if (g.seg[ri] == seg_i || fp == rp) continue;
+                        const int dd = abs(g.dfs[i] - g.dfs[ri]) + abs(g.dfe[i] - g.dfe[ri]);
+                        const float pen = __fadd_rn(Rf, __fmul_rn(sc.r, (float)dd));
+                        const float nv = __fsub_rn((float)(fe.x + we.x), pen);
+                        const bool edge = iedge && g.seg[ri] != g.seg[ri - 1];
+                        rec_merge(mine, nv, ((unsigned long long)j << 42) | ((unsigned long long)i << 21) | ri, edge);
                     }
                 }
-                if (!global_mode && je == L && jb < je && lane == 0 && row_best > NEG_INF / 2) {
-                    // pathwise_alignment_semiglobal.rs:269-273: a row replaces the incumbent only if strictly better
-                    if (!s_best_set || row_best > s_best_val) {
-                        s_best_set = 1;
-                        s_best_val = row_best;
-                        s_best_row = i;
-                        s_best_path = row_path;
+            } else {
+                for (int s = 0; s < nsurv; s++) {
+                    const uint32_t i = s_surv[s];
+                    const int2 fe = fwd.colbest[(size_t)i * Lp + j];
+                    const uint32_t fp = (uint32_t)fe.y & 0x7fffffffu;
+                    const uint32_t seg_i = g.seg[i];
+                    const bool iedge = seg_i != g.seg[i + 1];
+                    const int dfs_i = g.dfs[i], dfe_i = g.dfe[i];
+                    for (uint32_t ri = 1 + tid; ri + 1 < n; ri += PT) {
+                        const int2 we = rvd.colbest[(size_t)ri * Lp + jj];
+                        if (we.y >= 0) continue;
+                        const uint32_t rp = (uint32_t)we.y & 0x7fffffffu;
+                        if (g.seg[ri] == seg_i || fp == rp) continue;
+                        const int dd = abs(dfs_i - g.dfs[ri]) + abs(dfe_i - g.dfe[ri]);
+                        const float pen = __fadd_rn(Rf, __fmul_rn(sc.r, (float)dd));
+                        const float nv = __fsub_rn((float)(fe.x + we.x), pen);
+                        const bool edge = iedge && g.seg[ri] != g.seg[ri - 1];
+                        rec_merge(mine, nv, ((unsigned long long)j << 42) | ((unsigned long long)i << 21) | ri, edge);
                     }
                 }
+            }
+            // publish the running maximum so that later columns prune against it
+            float wv = mine.v;
+#pragma unroll
+            for (int dlt = 16; dlt >= 1; dlt >>= 1) wv = fmaxf(wv, __shfl_xor_sync(FULL, wv, dlt));
+            if (lane == 0) s_redv[warp] = wv;
+            __syncthreads();
+            if (tid == 0) {
+                float m = s_rb.v;
+                for (int k = 0; k < PT / 32; k++) m = fmaxf(m, s_redv[k]);
+                s_rb.v = m;
             }
             __syncthreads();
         }
-
-        // ================= end cell, traceback (thread 0), publish =================
-        if (tid == 0) {
-            uint32_t best_path, ending;
-            int score;
-            if (global_mode) {
-                // max of (score, path): highest path id wins ties (pathwise_alignment.rs:320-325)
-                best_path = 0;
-                for (uint32_t q = 1; q < P; q++)
-                    if (s_res[q] >= s_res[best_path]) best_path = q;
-                ending = s_end[best_path];
-                score = s_res[best_path];
-            } else {
-                best_path = s_best_path;
-                ending = s_best_row;
-                score = s_best_val;
+        // 3. reduce (max score; first key with it; first edge key with it)
+        {
+            RecBest r = mine;
+#pragma unroll
+            for (int dlt = 16; dlt >= 1; dlt >>= 1) {
+                RecBest o;
+                o.v = __shfl_xor_sync(FULL, r.v, dlt);
+                o.k1 = __shfl_xor_sync(FULL, r.k1, dlt);
+                o.k2 = __shfl_xor_sync(FULL, r.k2, dlt);
+                rec_merge2(r, o);
             }
-            res.score = score;
-            res.best_path = best_path;
-            res.end_row = ending;
-            res.end_col = (uint32_t)(L - 1);
+            if (lane == 0) {
+                s_redv[warp] = r.v;
+                s_redk1[warp] = r.k1;
+                s_redk2[warp] = r.k2;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                RecBest t;
+                t.v = s_redv[0];
+                t.k1 = s_redk1[0];
+                t.k2 = s_redk2[0];
+                for (int k = 1; k < PT / 32; k++) {
+                    RecBest o;
+                    o.v = s_redv[k];
+                    o.k1 = s_redk1[k];
+                    o.k2 = s_redk2[k];
+                    rec_merge2(t, o);
+                }
+                s_rb = t;
+            }
+            __syncthreads();
+        }
+        // 4. outcome + traceback (thread 0)
+        if (tid == 0) {
+            const RecBest t = s_rb;
+            const float basef = (float)base_score;
+            // sequential acceptance rule restated: a candidate is taken if it beats the incumbent, or ties it while
+            // the incumbent is not on a segment edge and the candidate is (…_recombination.rs:844-851)
+            // If the maximum beats the baseline: the first candidate with it wins unless it is off-edge and an on-edge
+            // tie follows (k2, the first on-edge tie, equals k1 when k1 itself is on an edge). If the maximum only
+            // ties the baseline: the first on-edge candidate with it, if any.
+            unsigned long long key = ~0ull;
+            if (t.k1 != ~0ull) {
+                if (t.v > basef)
+                    key = (t.k2 != ~0ull) ? t.k2 : t.k1;
+                else if (t.v == basef)
+                    key = t.k2;
+            }
             RunEmitter em;
             em.init(runs, ws.run_cap);
-            uint32_t ii = ending;
-            int j = L - 1;
-            const uint32_t bw = best_path / 32, bb = best_path % 32;
-            while (ii > 0 && j > 0) {
-                const uint2 pl = reinterpret_cast<const uint2*>(trace)[((size_t)ii * Lp + j) * PW + bw];
-                const unsigned code = ((pl.x >> bb) & 1u) | (((pl.y >> bb) & 1u) << 1);
-                uint32_t pred = ii - 1;
-                if (code != MV_L)
-                    for (uint32_t gi = g.grp_off[ii]; gi < g.grp_off[ii + 1]; gi++)
-                        if ((g.grp_mask[(size_t)gi * PW + bw] >> bb) & 1u) pred = g.grp[gi].pred;
-                if (code == MV_D) {
-                    em.step(g.lnz[ii] != read[j - 1] ? RG_OP_d : RG_OP_D, ii, 0);
-                    ii = pred;
-                    j--;
-                } else if (code == MV_U) {
-                    em.step(RG_OP_U, ii, 0);
-                    ii = pred;
+            res.score = base_score;
+            if (key == ~0ull) {
+                // no recombination: gaf_output_{global,semiglobal}_no_rec
+                uint32_t ending = 0;
+                if (mode == RG_MODE_REC_GLOBAL) {
+                    for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
+                        if ((g.grp_mask[(size_t)fg * PW + base_path / 32] >> (base_path % 32)) & 1u) ending = g.grp[fg].pred;
                 } else {
-                    em.step(RG_OP_L, ii, 0);
-                    j--;
+                    // ending_node (…_recombination.rs:885-897): first strict maximum over the rows of the path
+                    bool has = false;
+                    int bs = 0;
+                    for (uint32_t i = 1; i + 1 < n; i++)
+                        if ((g.node_bits[(size_t)i * PW + base_path / 32] >> (base_path % 32)) & 1u) {
+                            const int v = fwd.lastcol[(size_t)i * Pp + base_path];
+                            if (!has || v > bs) {
+                                has = true;
+                                bs = v;
+                                ending = i;
+                            }
+                        }
                 }
-            }
-            while (j > 0) {  // pathwise_alignment_output.rs:111-114
-                em.step(RG_OP_L, ii, 0);
-                j--;
-            }
-            if (global_mode) {
-                while (ii > 0) {  // :116-138
-                    uint32_t pred = 0;
-                    if (!g.nwp[ii])
-                        pred = ii - 1;
-                    else
-                        for (uint32_t gi = g.grp_off[ii]; gi < g.grp_off[ii + 1]; gi++)
-                            if ((g.grp_mask[(size_t)gi * PW + bw] >> bb) & 1u) pred = g.grp[gi].pred;
-                    em.step(RG_OP_U, ii, 0);
-                    ii = pred;
+                res.best_path = res.rev_best_path = base_path;
+                res.end_row = ending;
+                res.end_col = (uint32_t)(L - 1);
+                res.score = fwd.lastcol[(size_t)ending * Pp + base_path];
+                res.score_f32 = (float)base_score;
+                uint32_t ii = ending;
+                int j = L - 1;
+                pw_walk_fwd(g, fwd.trace, Lp, read, base_path, ii, j, mode == RG_MODE_REC_GLOBAL, em);
+                em.flush(0);
+                res.start_row = ii;
+                res.n_runs = em.n;
+            } else {
+                const uint32_t rcol = (uint32_t)(key >> 42), fen = (uint32_t)((key >> 21) & 0x1fffffu), rsn = (uint32_t)(key & 0x1fffffu);
+                const uint32_t fp = (uint32_t)fwd.colbest[(size_t)fen * Lp + rcol].y & 0x7fffffffu;
+                const uint32_t rp = (uint32_t)rvd.colbest[(size_t)rsn * Lp + (L - 1 - rcol)].y & 0x7fffffffu;
+                res.status |= RG_READ_RECOMBINATION;
+                res.best_path = fp;
+                res.rev_best_path = rp;
+                res.fen = fen;
+                res.rsn = rsn;
+                res.rec_col = rcol;
+                res.score_f32 = t.v;
+                res.displacement = abs(g.dfs[fen] - g.dfs[rsn]) + abs(g.dfe[fen] - g.dfe[rsn]);
+                // forward half, traceback order (recombination_output.rs:100-163 / 472-557)
+                uint32_t ii = fen;
+                int j = (int)rcol;
+                pw_walk_fwd(g, fwd.trace, Lp, read, fp, ii, j, mode == RG_MODE_REC_GLOBAL, em);
+                em.flush(0);
+                res.start_row = ii;
+                res.n_runs = em.n;
+                // reverse half, forward order (:38-98 / 389-470): rows ascend
+                em.ascending = true;
+                uint32_t ri = rsn;
+                int cj = (int)rcol;
+                uint32_t rev_end = ri;
+                while (ri > 0 && ri < n - 1 && cj < L - 1) {
+                    const unsigned code = pw_code(rvd.trace, Lp, PW, ri, L - 1 - cj, rp);
+                    rev_end = ri;
+                    if (code == MV_D) {
+                        em.step(g.lnz[ri] != read[cj] ? RG_OP_d : RG_OP_D, ri, 0);  // r_seq[j] = seq[j+1]
+                        ri = pw_pred(rg_, ri, rp, ri + 1);
+                        cj++;
+                    } else if (code == MV_U) {
+                        em.step(RG_OP_U, ri, 0);
+                        ri = pw_pred(rg_, ri, rp, ri + 1);
+                    } else {
+                        em.step(RG_OP_L, ri, 0);
+                        cj++;
+                    }
                 }
+                while (cj < L - 1) {
+                    em.step(RG_OP_L, ri, 0);
+                    cj++;
+                }
+                if (mode == RG_MODE_REC_GLOBAL)
+                    while (ri < n - 1) {
+                        em.step(RG_OP_U, ri, 0);
+                        ri = rg_.nwp[ri] ? pw_pred(rg_, ri, rp, ri + 1) : ri + 1;
+                    }
+                em.flush(0);
+                res.rev_end_row = rev_end;
+                res.n_runs_rev = em.n - res.n_runs;
+                res.end_row = fen;
+                res.end_col = rcol;
             }
-            em.flush(0);
-            res.start_row = ii;
-            res.start_col = 0;
             if (em.overflow) res.status |= RG_READ_TRACE_OVERFLOW;
             uint32_t nr = em.overflow ? 0 : em.n;
             unsigned long long ro = atomicAdd(&b.counters[1], (unsigned long long)nr);
@@ -316,29 +735,31 @@ __global__ void __launch_bounds__(PT) k_pathwise(DevPathGraph g, DevScoring sc, 
             }
             for (uint32_t k = 0; k < nr; k++) b.out_runs[ro + k] = runs[k];
             res.run_off = ro;
-            res.n_runs = nr;
+            if (nr == 0) res.n_runs = res.n_runs_rev = 0;
             b.results[ridx] = res;
         }
         __syncthreads();
     }
 }
 
-size_t pathwise_smem_bytes(const DevPathGraph& g, const PwWorkspace& ws) {
-    return (((size_t)g.max_groups * ws.Lp + 15) & ~(size_t)15) + (size_t)ws.Lp * 4 + (size_t)ws.Pp * 8;
+size_t pathwise_smem_bytes(const DevPathGraph& g, const DevPathGraph& rg_, const PwWorkspace& ws, bool rec) {
+    const uint32_t mg = rec ? (g.max_groups > rg_.max_groups ? g.max_groups : rg_.max_groups) : g.max_groups;
+    return (((size_t)mg * ws.Lp + 15) & ~(size_t)15) + (size_t)ws.Lp * 4 + (size_t)ws.Pp * 8 + (rec ? REC_SURV * 4 : 0);
 }
 
-int launch_pathwise(int mode, const DevPathGraph& g, const DevScoring& s, const PwWorkspace& ws, const PoaBatch& b,
-                    int blocks, void* stream) {
+int launch_pathwise(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwWorkspace& ws,
+                    const PwRecWorkspace& rw, const PoaBatch& b, int blocks, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = pathwise_smem_bytes(g, ws);
+    const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
+    const size_t smem = pathwise_smem_bytes(g, rg_, ws, rec);
     if (smem > 200 * 1024) return -3;
     if (cudaFuncSetAttribute(k_pathwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    k_pathwise<<<blocks, PT, smem, st>>>(g, s, ws, b, mode);
+    k_pathwise<<<blocks, PT, smem, st>>>(g, rg_, s, ws, rw, b, mode);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int pathwise_blocks_per_sm(const DevPathGraph& g, const PwWorkspace& ws, int* nb) {
-    const size_t smem = pathwise_smem_bytes(g, ws);
+int pathwise_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const PwWorkspace& ws, bool rec, int* nb) {
+    const size_t smem = pathwise_smem_bytes(g, rg_, ws, rec);
     if (smem > 200 * 1024) return -3;
     if (cudaFuncSetAttribute(k_pathwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k_pathwise, PT, smem) == cudaSuccess ? 0 : -1;

@@ -39,7 +39,9 @@ struct RunEmitter {
     uint32_t cap, n;
     uint32_t op, row, count;
     bool overflow;
+    bool ascending;  // rows of graph-consuming ops increase (reverse half of modes 8/9)
     __device__ __forceinline__ void init(rg_run* b, uint32_t c) {
+        ascending = false;
         buf = b;
         cap = c;
         n = 0;
@@ -64,7 +66,8 @@ struct RunEmitter {
     // `cnt` consecutive steps of the same op starting at row r (rows descending for graph-consuming ops)
     __device__ __forceinline__ void bulk(uint32_t o, uint32_t r, uint32_t cnt, int lane) {
         if (cnt == 0) return;
-        bool cont = count && o == op && count + cnt < 0x0fffffffu && (o == RG_OP_L || o == RG_OP_LPAD ? r == row : r + count == row);
+        bool cont = count && o == op && count + cnt < 0x0fffffffu &&
+                    (o == RG_OP_L || o == RG_OP_LPAD ? r == row : (ascending ? r == row + count : r + count == row));
         if (cont)
             count += cnt;
         else {
@@ -75,7 +78,8 @@ struct RunEmitter {
         }
     }
     __device__ __forceinline__ void step(uint32_t o, uint32_t r, int lane) {
-        bool cont = count && o == op && count < 0x0fffffffu && (o == RG_OP_L || o == RG_OP_LPAD ? r == row : r + count == row);
+        bool cont = count && o == op && count < 0x0fffffffu &&
+                    (o == RG_OP_L || o == RG_OP_LPAD ? r == row : (ascending ? r == row + count : r + count == row));
         if (cont)
             count++;
         else {

@@ -159,3 +159,35 @@ def test_pathwise_example(mode, extra):
 def test_pathwise_synthetic(synth_files, mode, name):
     fa, gfa = synth_files[name]
     _assert_same(["-m", mode, fa, gfa])
+
+
+@pytest.mark.parametrize("mode", ["8", "9"])
+@pytest.mark.parametrize("extra", [[], ["-R", "1", "-r", "0.05"], ["-B", "0.6"], ["-R", "0", "-r", "0"], ["-M", "1", "-X", "3", "-R", "2"]])
+def test_recombination_example(mode, extra):
+    _assert_same(["-m", mode] + extra + EX)
+
+
+@pytest.fixture(scope="module")
+def mosaic_files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mosaic")
+    out = {}
+    for name, (bp, paths, nreads, rlen, err, seed, breaks) in {
+        "m1": (900, 6, 16, 200, 0.02, 31, 2),
+        "m2": (1500, 10, 12, 350, 0.03, 32, 1),
+        "m3": (600, 4, 10, 80, 0.0, 33, 3),
+    }.items():
+        g = synth.make_graph(bp, paths, seed=seed)
+        reads = synth.make_reads(g, nreads, rlen, err=err, seed=seed + 100, mosaic_breaks=breaks)
+        gfa, fa = d / f"{name}.gfa", d / f"{name}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        out[name] = (str(fa), str(gfa))
+    return out
+
+
+@pytest.mark.parametrize("mode", ["8", "9"])
+@pytest.mark.parametrize("name", ["m1", "m2", "m3"])
+@pytest.mark.parametrize("extra", [[], ["-R", "2", "-r", "0.01"]])
+def test_recombination_mosaics(mosaic_files, mode, name, extra):
+    fa, gfa = mosaic_files[name]
+    _assert_same(["-m", mode] + extra + [fa, gfa])
