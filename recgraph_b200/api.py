@@ -182,3 +182,81 @@ class Aligner:
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         self._check(self.lib.rg_int_peak(self.ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"iadd3_gops": a.value, "vimnmx_gops": b.value, "viaddmnmx_gops": c.value}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# api.rs:11-164 — library entry points (only the POA modes are exposed there). Same names, argument meaning and
+# defaults as the reference: `bases_to_add` is a FRACTION of the read length (default 0.1, api.rs:21,55), the
+# default f32 matrix has gap-vs-char = X (score_matrix.rs:52-66, not 2X), default o = -10, e = -6 (api.rs:65-66).
+# `graph` is an Aligner with a graph loaded (the HashGraph argument of the reference); scores are passed as the
+# 6x6 table over A,C,G,T,N,'-' (see create_score_matrix_i32 / _f32 below).
+class GAFStruct:
+    def __init__(self, line):
+        f = line.rstrip("\n").split("\t")
+        self.line = line.rstrip("\n")
+        self.query_name, self.query_length, self.query_start, self.query_end = f[0], int(f[1]), int(f[2]), int(f[3])
+        self.strand = f[4]
+        self.path = [int(x) for x in f[5].split(">") if x]
+        self.path_length, self.path_start, self.path_end = int(f[6]), int(f[7]), int(f[8])
+        self.residue_matches_number = int(f[9])
+        self.alignment_block_length, self.mapping_quality = f[10], f[11]
+        self.comments = "\t".join(f[12:])
+
+    def to_string(self):
+        return self.line
+
+
+def create_score_matrix_i32(match_score=None, mismatch_score=None, matrix_type=None):
+    """api.rs:131-149. mismatch_score is the (negative) score itself, as in the reference."""
+    s = _lib.Scoring()
+    lib = _lib.load()
+    kind = {None: 0, "HOXD55.mtx": 2, "HOXD55": 2, "HOXD70.mtx": 3, "HOXD70": 3}[matrix_type]
+    lib.rg_make_score_matrix(kind, match_score or 0, mismatch_score or 0, ctypes.byref(s))
+    return [[s.score[i][j] for j in range(6)] for i in range(6)]
+
+
+def create_score_matrix_f32(match_score=None, mismatch_score=None, matrix_type=None):
+    """api.rs:153-164: same values as the i32 builder, as f32."""
+    return create_score_matrix_i32(match_score, mismatch_score, matrix_type)
+
+
+def _default_f32_table():
+    s = _lib.Scoring()
+    _lib.load().rg_make_score_matrix(1, 2, -4, ctypes.byref(s))  # create_score_matrix_match_mis_f32(2, -4)
+    return [[s.score[i][j] for j in range(6)] for i in range(6)]
+
+
+def _api_align(graph, mode, read, sequence_name, table, bta, o=-10, e=-6):
+    name = sequence_name[0] if sequence_name else "no_name"
+    graph.set_scoring(table=table, gap_open=-o, gap_ext=-e, fixed_bta=bta if bta is not None else -1)
+    _recs, text = graph.align(mode, [read.upper().replace("-", "N")], names=[name])
+    lines = text.splitlines()
+    return GAFStruct(lines[-1]) if lines else None
+
+
+def _bases_to_add(read, frac):
+    import numpy as _np
+    return int(_np.float32(len(read)) * _np.float32(0.1 if frac is None else frac))  # api.rs:21: f32 product, truncated
+
+
+def align_global_no_gap(read, graph, sequence_name=None, score_matrix=None, bases_to_add=None):
+    """api.rs:11-40 -> global_abpoa::exec_simd."""
+    return _api_align(graph, 0, read, sequence_name, score_matrix or _default_f32_table(), _bases_to_add(read, bases_to_add))
+
+
+def align_global_gap(read, graph, sequence_name=None, score_matrix=None, bases_to_add=None, o=None, e=None):
+    """api.rs:43-72 -> gap_global_abpoa::exec."""
+    table = score_matrix or create_score_matrix_i32(2, -4)
+    return _api_align(graph, 2, read, sequence_name, table, _bases_to_add(read, bases_to_add),
+                      -10 if o is None else o, -6 if e is None else e)
+
+
+def align_local_no_gap(read, graph, sequence_name=None, score_matrix=None):
+    """api.rs:76-99 -> local_poa::exec_simd."""
+    return _api_align(graph, 1, read, sequence_name, score_matrix or _default_f32_table(), None)
+
+
+def align_local_gap(read, graph, sequence_name=None, score_matrix=None, o=None, e=None):
+    """api.rs:102-128 -> gap_local_poa::exec."""
+    table = score_matrix or create_score_matrix_i32(2, -4)
+    return _api_align(graph, 3, read, sequence_name, table, None, -10 if o is None else o, -6 if e is None else e)

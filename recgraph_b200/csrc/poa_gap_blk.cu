@@ -46,7 +46,7 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int (&v)[C]) {
     for (int j = 0; j < C; j += 4) reinterpret_cast<int4*>(dst)[j / 4] = make_int4(v[j], v[j + 1], v[j + 2], v[j + 3]);
 }
 
-template <int C, typename TC, int SB>
+template <int C, typename TC, int SB, bool SIMPLE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
     k_gap_global_blk(DevGraph g, DevScoring sc, PoaWorkspace ws, PoaBatch b) {
     static_assert(C % 4 == 0, "C must be a multiple of 4");
@@ -120,6 +120,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             rcw[j] = w;
         }
 
+        // match/mismatch scoring (SIMPLE): per base one bit mask over my columns, so that the substitution score of
+        // a cell is a bit test instead of a shared-memory table lookup
+        unsigned eqm0 = 0, eqm1 = 0, eqm2 = 0, eqm3 = 0;
+        if (SIMPLE) {
+#pragma unroll
+            for (int k = 0; k < C; k++) {
+                const unsigned rc = (rcw[k / 4] >> (8 * (k % 4))) & 0xffu;
+                eqm0 |= (rc == 0u ? 1u : 0u) << k;
+                eqm1 |= (rc == 1u ? 1u : 0u) << k;
+                eqm2 |= (rc == 2u ? 1u : 0u) << k;
+                eqm3 |= (rc == 3u ? 1u : 0u) << k;
+            }
+        }
+        const int s_match = sc.sc[0][0], s_mis = sc.sc[0][1];
         const long long t_start = clock64();
         int A[C], B[C];  // previous row: m and y of my columns (NEG_INF outside its band)
         int status = 0;
@@ -178,6 +192,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             const bool fast = (i > 0) && !nwp && left == 0 && prev_left == 0 && right <= prev_right;
             if (fast) {
                 const int32_t* srow = s_sc + li * 8;
+                const unsigned em = li == 0 ? eqm0 : (li == 1 ? eqm1 : (li == 2 ? eqm2 : (li == 3 ? eqm3 : 0u)));
                 int up = __shfl_up_sync(FULL, A[C - 1], 1);
                 unsigned ybits = 0;
                 int D[C];
@@ -188,8 +203,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     const int uy = B[k];
                     const int yv = max(um, uy) + e;
                     if (uy > um) ybits |= 1u << k;
-                    const unsigned rc = (rcw[k / 4] >> (8 * (k % 4))) & 0xffu;
-                    int dd = ((k == 0) ? up : A[k - 1]) + srow[rc];
+                    int sub;
+                    if (SIMPLE) {
+                        sub = ((em >> k) & 1u) ? s_match : s_mis;
+                    } else {
+                        const unsigned rc = (rcw[k / 4] >> (8 * (k % 4))) & 0xffu;
+                        sub = srow[rc];
+                    }
+                    int dd = ((k == 0) ? up : A[k - 1]) + sub;
                     int h = max(dd, yv);
                     if (k == 0 && lane == 0) {  // first-column cell: m = x only
                         dd = NEG_INF;
@@ -531,13 +552,29 @@ int gap_blk_cols(uint32_t Lmax) {
     return 0;
 }
 
+// match/mismatch table of score_matrix.rs:35-66: M on the A,C,G,T diagonal, X elsewhere among A,C,G,T,N
+static bool simple_scoring(const DevScoring& s) {
+    for (int a = 0; a < 5; a++)
+        for (int b = 0; b < 5; b++)
+            if (s.sc[a][b] != ((a == b && a < 4) ? s.sc[0][0] : s.sc[0][1])) return false;
+    return true;
+}
+
 template <int C>
 static int launch_c(const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b, int trace_bytes,
                     int blocks, cudaStream_t st) {
-    if (trace_bytes == 1)
-        k_gap_global_blk<C, uint8_t, 2><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
-    else
-        k_gap_global_blk<C, uint16_t, 6><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+    const bool simple = simple_scoring(s);
+    if (trace_bytes == 1) {
+        if (simple)
+            k_gap_global_blk<C, uint8_t, 2, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+        else
+            k_gap_global_blk<C, uint8_t, 2, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+    } else {
+        if (simple)
+            k_gap_global_blk<C, uint16_t, 6, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+        else
+            k_gap_global_blk<C, uint16_t, 6, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -555,7 +592,7 @@ int launch_gap_global_blk(int C, const DevGraph& g, const DevScoring& s, const P
 
 template <int C>
 static int occ_c(int trace_bytes, int* nb) {
-    const void* k = trace_bytes == 1 ? (const void*)k_gap_global_blk<C, uint8_t, 2> : (const void*)k_gap_global_blk<C, uint16_t, 6>;
+    const void* k = trace_bytes == 1 ? (const void*)k_gap_global_blk<C, uint8_t, 2, true> : (const void*)k_gap_global_blk<C, uint16_t, 6, true>;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, WARPS_PER_BLOCK * 32, 0) == cudaSuccess ? 0 : -1;
 }
 int gap_blk_blocks_per_sm(int C, int trace_bytes, int* nb) {

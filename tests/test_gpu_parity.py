@@ -191,3 +191,29 @@ def mosaic_files(tmp_path_factory):
 def test_recombination_mosaics(mosaic_files, mode, name, extra):
     fa, gfa = mosaic_files[name]
     _assert_same(["-m", mode] + extra + [fa, gfa])
+
+
+def test_api_rs_entry_points_match_cli():
+    """api.rs:43-72,102-128: library defaults (bases_to_add = 0.1 * len, o = -10, e = -6) == CLI with those flags."""
+    import recgraph_b200 as rb
+    from tests import oracle_lib
+    fa, gfa = EX
+    names, seqs = [], []
+    for ln in open(fa):
+        if ln.startswith(">"):
+            names.append(ln[1:].strip())
+        else:
+            seqs.append(ln.strip())
+    al = rb.Aligner()
+    al.load_gfa(gfa)
+    bta = int(len(seqs[0]) * 0.1)
+    rc, out, _ = oracle_lib.run_cli(["-m", "2", "-O", "10", "-E", "6", "-b", str(bta), "-f", "0", fa, gfa])
+    exp = [l for l in out.splitlines() if "\t" in l]
+    rc, out3, _ = oracle_lib.run_cli(["-m", "3", "-O", "10", "-E", "6", fa, gfa])
+    exp3 = [l for l in out3.splitlines() if "\t" in l]
+    for k in range(4):
+        g = rb.align_global_gap(seqs[k], al, (names[k], k + 1))
+        assert g.to_string() == exp[k]
+        g3 = rb.align_local_gap(seqs[k], al, (names[k], k + 1))
+        assert g3.to_string() == exp3[k]
+        assert g3.path == [int(x) for x in exp3[k].split("\t")[5].split(">") if x]
