@@ -241,7 +241,7 @@ def main():
         cells_s = cells_per_step * args.steps / (kernel_ms * 1e-3)  # per GPU, device time of the dominant kernel
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_poa_gap_global")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_gap_global_blk")
         except Exception:
             pass
         line = {
@@ -257,7 +257,7 @@ def main():
             "clocks": summarize_clocks(samples),
             "roofline": {"bound": "hbm", "achieved": cells_s * 1.0 / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": cells_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_poa_gap_global",
+                         "kernel": "k_gap_global_blk<32,u8,2> (csrc/poa_gap_blk.cu)",
                          "note": "algorithmic bytes = 1 B traceback code per DP cell (SURVEY 8d); the kernel is "
                                  "INT32-issue bound, see roofline_int32"},
             "roofline_int32": {"bound": "int32_alu", "achieved": cells_s * 9 / 1e9, "peak": int_peak_gops,
