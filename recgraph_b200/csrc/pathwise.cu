@@ -180,7 +180,20 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
             }
             int row_best = NEG_INF;
             uint32_t row_path = 0;
-            for (int j = jb; j < je; j++) {
+            // The column loop is a chain of dependent-looking global loads (scores of the predecessor row); fetch
+            // them U columns ahead so that their L2 latency overlaps (the stores below would otherwise serialise them).
+            constexpr int U = 8;
+            for (int j0 = jb; j0 < je; j0 += U) {
+                int spv[MAXPW][U];
+#pragma unroll
+                for (int ps = 0; ps < MAXPW; ps++)
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        spv[ps][u] = ((uint32_t)ps < PW && gq[ps] >= 0 && j0 + u < je) ? Spq[ps][(size_t)(j0 + u) * Pp] : 0;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                const int j = j0 + u;
+                if (j >= je) break;
                 const int sj = (j >= 1) ? srow[rcode(j)] : 0;
                 int cb_val = NEG_INF;
                 uint32_t cb_path = 0;
@@ -192,7 +205,7 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
                     int nv = 0;
                     unsigned code = 0;
                     if (member) {
-                        const int sp = Spq[ps][(size_t)j * Pp];
+                        const int sp = spv[ps][u];
                         if (j == 0) {
                             nv = col0[ps];
                         } else {
@@ -241,6 +254,7 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
                     const bool memb = (g.node_bits[(size_t)i * PW + cb_path / 32] >> (cb_path % 32)) & 1u;
                     d.colbest[(size_t)i * Lp + j] = make_int2(cb_val, (int)(cb_path | (memb ? 0x80000000u : 0u)));
                 }
+            }
             }
             if (track_best && je == L && jb < je && lane == 0 && row_best > NEG_INF / 2) {
                 // …_semiglobal.rs:269-273: a row replaces the incumbent only if strictly better

@@ -13,9 +13,11 @@ ap.add_argument("--read-len", type=int, default=1000)
 ap.add_argument("--graph-bp", type=int, default=100000)
 ap.add_argument("--paths", type=int, default=8)
 ap.add_argument("--passes", type=int, default=1)
+ap.add_argument("--mosaic", type=int, default=0)
+ap.add_argument("--err", type=float, default=0.05)
 a = ap.parse_args()
 g = synth.make_graph(a.graph_bp, a.paths, seed=1)
-reads = synth.make_reads(g, a.reads, a.read_len, err=0.05, seed=3)
+reads = synth.make_reads(g, a.reads, a.read_len, err=a.err, seed=3, mosaic_breaks=a.mosaic)
 al = Aligner(0)
 al.load_gfa_text(g.gfa())
 al.set_scoring()
@@ -29,4 +31,5 @@ print("cells", sum(res.reads[i].cells for i in range(res.n_reads)))
 import numpy as np
 dp = np.array([res.reads[i].fen for i in range(res.n_reads)], dtype=np.float64)
 tb = np.array([res.reads[i].rsn for i in range(res.n_reads)], dtype=np.float64)
-print("kcycles per read: forward mean %.0f, traceback mean %.0f (%.1f%% of total); runs/read %.0f" % (dp.mean(), tb.mean(), 100 * tb.sum() / (dp.sum() + tb.sum()), res.n_runs_total / max(1, res.n_reads)))
+if a.mode == 2:
+    print("kcycles per read: forward mean %.0f, traceback mean %.0f (%.1f%% of total); runs/read %.0f" % (dp.mean(), tb.mean(), 100 * tb.sum() / (dp.sum() + tb.sum()), res.n_runs_total / max(1, res.n_reads)))
