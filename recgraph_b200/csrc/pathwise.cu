@@ -28,7 +28,7 @@
 namespace rg {
 
 constexpr int PT = 256;    // threads per CTA
-constexpr int MAXPW = 4;   // up to 128 paths
+constexpr int MAXPW = 4;   // up to 128 paths (kernels are instantiated for 1..4 words of 32 paths)
 enum { MV_D = 1, MV_U = 2, MV_L = 3 };
 
 __device__ __forceinline__ int block_excl_max(int z, int tid, int* s_w) {
@@ -61,6 +61,7 @@ struct PwDir {  // buffers of one DP direction for the read in flight
 };
 
 // One DP pass over all rows. Returns nothing; mode-5 best end and mode-4 results are left in shared memory.
+template <int TPW>
 __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, const int32_t* s_sc,
                       const uint8_t* read, int L, uint32_t Lp, uint32_t Pp, bool rev, bool free_border, bool track_best,
                       bool track_results, int g_gr, int g_rd, int* s_best_val, int* s_best_set, uint32_t* s_best_row,
@@ -138,17 +139,16 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
         {
             const int jb = warp * chunk, je = min(L, jb + chunk);
             // per pass (32 paths) state
-            int gq[MAXPW];
-            const int32_t* Spq[MAXPW];
-            bool quirk[MAXPW];
-            int col0[MAXPW], prev_new[MAXPW], sp_prev[MAXPW];
+            int gq[TPW];
+            const int32_t* Spq[TPW];
+            bool quirk[TPW];
+            int col0[TPW], prev_new[TPW], sp_prev[TPW];
 #pragma unroll
-            for (int ps = 0; ps < MAXPW; ps++) {
+            for (int ps = 0; ps < TPW; ps++) {
                 gq[ps] = -1;
                 Spq[ps] = d.S;
                 quirk[ps] = false;
                 col0[ps] = prev_new[ps] = sp_prev[ps] = 0;
-                if ((uint32_t)ps >= PW) continue;
                 const uint32_t q = ps * 32 + lane;
                 uint32_t pq = 0;
                 if (q < P)
@@ -184,12 +184,12 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
             // them U columns ahead so that their L2 latency overlaps (the stores below would otherwise serialise them).
             constexpr int U = 8;
             for (int j0 = jb; j0 < je; j0 += U) {
-                int spv[MAXPW][U];
+                int spv[TPW][U];
 #pragma unroll
-                for (int ps = 0; ps < MAXPW; ps++)
+                for (int ps = 0; ps < TPW; ps++)
 #pragma unroll
                     for (int u = 0; u < U; u++)
-                        spv[ps][u] = ((uint32_t)ps < PW && gq[ps] >= 0 && j0 + u < je) ? Spq[ps][(size_t)(j0 + u) * Pp] : 0;
+                        spv[ps][u] = (gq[ps] >= 0 && j0 + u < je) ? Spq[ps][(size_t)(j0 + u) * Pp] : 0;
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                 const int j = j0 + u;
@@ -198,9 +198,8 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
                 int cb_val = NEG_INF;
                 uint32_t cb_path = 0;
 #pragma unroll
-                for (int ps = 0; ps < MAXPW; ps++) {
-                    if ((uint32_t)ps >= PW) continue;
-                    const uint32_t q = ps * 32 + lane;
+                for (int ps = 0; ps < TPW; ps++) {
+                        const uint32_t q = ps * 32 + lane;
                     const bool member = gq[ps] >= 0;
                     int nv = 0;
                     unsigned code = 0;
@@ -335,6 +334,7 @@ __device__ __forceinline__ void rec_merge2(RecBest& a, const RecBest& o) {
     }
 }
 
+template <int TPW>
 __global__ void __launch_bounds__(PT) k_pathwise(DevPathGraph g, DevPathGraph rg_, DevScoring sc, PwWorkspace ws,
                                                   PwRecWorkspace rw, PoaBatch b, int mode) {
     extern __shared__ unsigned char s_dyn[];
@@ -416,10 +416,10 @@ __global__ void __launch_bounds__(PT) k_pathwise(DevPathGraph g, DevPathGraph rg
             sm.end[q] = 0;
         }
         __syncthreads();
-        pw_dp(g, fwd, sm, s_sc, read, L, Lp, Pp, false, !global_mode, mode == RG_MODE_PATHWISE_SEMIGLOBAL,
+        pw_dp<TPW>(g, fwd, sm, s_sc, read, L, Lp, Pp, false, !global_mode, mode == RG_MODE_PATHWISE_SEMIGLOBAL,
               mode == RG_MODE_PATHWISE_GLOBAL, g_gr, g_rd, &s_best_val, &s_best_set, &s_best_row, &s_best_path);
         if (rec_mode)
-            pw_dp(rg_, rvd, sm, s_sc, read, L, Lp, Pp, true, !global_mode, false, false, g_gr, g_rd, &s_best_val,
+            pw_dp<TPW>(rg_, rvd, sm, s_sc, read, L, Lp, Pp, true, !global_mode, false, false, g_gr, g_rd, &s_best_val,
                   &s_best_set, &s_best_row, &s_best_path);
 
         if (!rec_mode) {
@@ -761,22 +761,39 @@ size_t pathwise_smem_bytes(const DevPathGraph& g, const DevPathGraph& rg_, const
     return (((size_t)mg * ws.Lp + 15) & ~(size_t)15) + (size_t)ws.Lp * 4 + (size_t)ws.Pp * 8 + (rec ? REC_SURV * 4 : 0);
 }
 
+static const void* pw_kernel(uint32_t PW) {
+    switch (PW) {
+        case 1: return (const void*)k_pathwise<1>;
+        case 2: return (const void*)k_pathwise<2>;
+        case 3: return (const void*)k_pathwise<3>;
+        case 4: return (const void*)k_pathwise<4>;
+        default: return nullptr;
+    }
+}
+
 int launch_pathwise(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwWorkspace& ws,
                     const PwRecWorkspace& rw, const PoaBatch& b, int blocks, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
     const size_t smem = pathwise_smem_bytes(g, rg_, ws, rec);
-    if (smem > 200 * 1024) return -3;
-    if (cudaFuncSetAttribute(k_pathwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    k_pathwise<<<blocks, PT, smem, st>>>(g, rg_, s, ws, rw, b, mode);
+    const void* k = pw_kernel(g.PW);
+    if (smem > 200 * 1024 || !k) return -3;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    switch (g.PW) {
+        case 1: k_pathwise<1><<<blocks, PT, smem, st>>>(g, rg_, s, ws, rw, b, mode); break;
+        case 2: k_pathwise<2><<<blocks, PT, smem, st>>>(g, rg_, s, ws, rw, b, mode); break;
+        case 3: k_pathwise<3><<<blocks, PT, smem, st>>>(g, rg_, s, ws, rw, b, mode); break;
+        default: k_pathwise<4><<<blocks, PT, smem, st>>>(g, rg_, s, ws, rw, b, mode); break;
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 int pathwise_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const PwWorkspace& ws, bool rec, int* nb) {
     const size_t smem = pathwise_smem_bytes(g, rg_, ws, rec);
-    if (smem > 200 * 1024) return -3;
-    if (cudaFuncSetAttribute(k_pathwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k_pathwise, PT, smem) == cudaSuccess ? 0 : -1;
+    const void* k = pw_kernel(g.PW);
+    if (smem > 200 * 1024 || !k) return -3;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, PT, smem) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace rg
