@@ -183,13 +183,21 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
             // The column loop is a chain of dependent-looking global loads (scores of the predecessor row); fetch
             // them U columns ahead so that their L2 latency overlaps (the stores below would otherwise serialise them).
             constexpr int U = 8;
+            int spv[TPW][U], spn[TPW][U];
+#pragma unroll
+            for (int ps = 0; ps < TPW; ps++)
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    spn[ps][u] = (gq[ps] >= 0 && jb + u < je) ? Spq[ps][(size_t)(jb + u) * Pp] : 0;
             for (int j0 = jb; j0 < je; j0 += U) {
-                int spv[TPW][U];
+                // double buffer: the next batch's loads are in flight while this batch is computed
 #pragma unroll
                 for (int ps = 0; ps < TPW; ps++)
 #pragma unroll
-                    for (int u = 0; u < U; u++)
-                        spv[ps][u] = (gq[ps] >= 0 && j0 + u < je) ? Spq[ps][(size_t)(j0 + u) * Pp] : 0;
+                    for (int u = 0; u < U; u++) {
+                        spv[ps][u] = spn[ps][u];
+                        spn[ps][u] = (gq[ps] >= 0 && j0 + U + u < je) ? Spq[ps][(size_t)(j0 + U + u) * Pp] : 0;
+                    }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                 const int j = j0 + u;
@@ -335,7 +343,7 @@ __device__ __forceinline__ void rec_merge2(RecBest& a, const RecBest& o) {
 }
 
 template <int TPW>
-__global__ void __launch_bounds__(PT) k_pathwise(DevPathGraph g, DevPathGraph rg_, DevScoring sc, PwWorkspace ws,
+__global__ void __launch_bounds__(PT, 2) k_pathwise(DevPathGraph g, DevPathGraph rg_, DevScoring sc, PwWorkspace ws,
                                                   PwRecWorkspace rw, PoaBatch b, int mode) {
     extern __shared__ unsigned char s_dyn[];
     __shared__ int32_t s_sc[48];
