@@ -131,6 +131,7 @@ struct rg_ctx {
     double kernel_ms = 0;
     uint64_t launches = 0, cells = 0;
     uint32_t slots_used = 0;
+    bool no_s16 = getenv("RG_NO_S16") != nullptr;                // testing: 32-bit paths only
     bool force_striped = getenv("RG_FORCE_STRIPED") != nullptr;  // testing: keep the generic striped kernel
     PinnedBuf<unsigned long long> h_counters;
 
@@ -564,6 +565,7 @@ static int align_poa(rg_ctx* c, int mode) {
         ws.run_cap = run_cap;
         ws.wstride = wstride;
         ws.slots = slots;
+        ws.use16 = c->no_s16 ? 0u : 1u;
         PoaBatch b{};
         b.reads = c->d_reads.p;
         b.read_off = c->d_read_off.p;

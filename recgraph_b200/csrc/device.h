@@ -63,6 +63,7 @@ struct PoaWorkspace {
     uint32_t run_cap;    // runs per slot
     uint32_t wstride;    // ints per ring row (>= max L, multiple of 32)
     uint32_t slots;
+    uint32_t use16;      // mode 2: allow the packed 16-bit fast path (RG_NO_S16 disables it for A/B tests)
 };
 
 struct PoaBatch {

@@ -46,6 +46,12 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int (&v)[C]) {
     for (int j = 0; j < C; j += 4) reinterpret_cast<int4*>(dst)[j / 4] = make_int4(v[j], v[j + 1], v[j + 2], v[j + 3]);
 }
 
+// ---- packed 16-bit helpers (sm_100a: VIADD.16x2, VIMNMX.S16x2 with one predicate per half, VIADDMNMX.S16x2)
+#define FLOOR16 (-30000)
+__device__ __forceinline__ unsigned pk16(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+__device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(unsigned v) { return (int)v >> 16; }
+
 template <int C, typename TC, int SB, bool SIMPLE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
     k_gap_global_blk(DevGraph g, DevScoring sc, PoaWorkspace ws, PoaBatch b) {
@@ -59,6 +65,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
     if (threadIdx.x < 48) s_sc[threadIdx.x] = (&sc.sc[0][0])[threadIdx.x];
     __syncthreads();
     if (slot >= ws.slots) return;
+    // 16-bit packed fast path: two cells per register, pair r of a lane = columns (r, r + C/2) of its block.
+    // Substitution scores of the pairs for each graph base: [5 bases][C/2 pairs][32 lanes] words per warp.
+    constexpr int H = C / 2;
+    extern __shared__ unsigned s_subtab[];
+    unsigned* const subtab = s_subtab + (size_t)wib * 5 * H * 32;
 
     const uint32_t n = g.n;
     const uint32_t RM = g.ring - 1;
@@ -134,6 +145,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             }
         }
         const int s_match = sc.sc[0][0], s_mis = sc.sc[0][1];
+        // exact while no 16-bit lane can wrap: small scores, strictly negative gap steps
+        bool en16 = SIMPLE && (e + max(o, 0) < 0) && (o + e < 0) && abs(o) <= 60 && abs(e) <= 60 && abs(s_match) <= 60 &&
+                    abs(s_mis) <= 60 && ws.use16;
+        if (SIMPLE && en16) {
+#pragma unroll
+            for (int r = 0; r < H; r++) {
+                const unsigned rl = (rcw[r / 4] >> (8 * (r % 4))) & 0xffu, rh = (rcw[(r + H) / 4] >> (8 * ((r + H) % 4))) & 0xffu;
+#pragma unroll
+                for (unsigned bse = 0; bse < 5; bse++)
+                    subtab[(bse * H + r) * 32 + lane] = pk16((bse < 4 && rl == bse) ? s_match : s_mis, (bse < 4 && rh == bse) ? s_match : s_mis);
+            }
+            __syncwarp();
+        }
+        bool rep16 = false;   // the previous row is held packed (A[r], B[r] for r < H hold m and y + e relative to base16)
+        int base16 = 0, rows16 = 0, prev_tmax = 0;
+        const unsigned C1C1 = pk16(e + max(o, 0), e + max(o, 0)), C2C2 = pk16(o + e, o + e), EE = pk16(e, e), OO1 = pk16(o + 1, o + 1);
         const long long t_start = clock64();
         int A[C], B[C];  // previous row: m and y of my columns (NEG_INF outside its band)
         int status = 0;
@@ -190,7 +217,142 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             // previous row's band, so every active cell has its vertical and diagonal source and none of the
             // availability / fallback logic of gap_global_abpoa.rs:110-141 can trigger.
             const bool fast = (i > 0) && !nwp && left == 0 && prev_left == 0 && right <= prev_right;
-            if (fast) {
+
+            bool f16 = en16 && fast && right == (uint32_t)L && prev_right == (uint32_t)L;
+            if (f16 && !rep16) {
+                // 32-bit -> packed: every real cell must fit comfortably; padding columns (c >= L) and the unused
+                // y of the first-column cell start at the floor and become "healthy" within a row or two
+                bool ok = true;
+#pragma unroll
+                for (int k = 0; k < C; k++) {
+                    const int c = cbase + k;
+                    if (c < L) {
+                        ok = ok && (A[k] - prev_tmax >= -24000) && (A[k] - prev_tmax <= 2000);
+                        if (c != 0) ok = ok && (B[k] + e - prev_tmax >= -24000) && (B[k] + e - prev_tmax <= 2000);
+                    }
+                }
+                if (__all_sync(FULL, ok)) {
+                    base16 = prev_tmax;
+#pragma unroll
+                    for (int r = 0; r < H; r++) {
+                        const int cl = cbase + r, ch = cbase + r + H;
+                        const int al = (cl < L) ? A[r] - base16 : FLOOR16, ah = (ch < L) ? A[r + H] - base16 : FLOOR16;
+                        const int yl = (cl < L && cl != 0) ? B[r] + e - base16 : FLOOR16, yh = (ch < L) ? B[r + H] + e - base16 : FLOOR16;
+                        A[r] = (int)pk16(al, ah);
+                        B[r] = (int)pk16(yl, yh);
+                    }
+                    rep16 = true;
+                    rows16 = 0;
+                } else {
+                    f16 = false;
+                }
+            }
+            if (!f16 && rep16) {
+                // packed -> 32-bit (padding columns are outside the band: NEG_INF; y[i][0] is 0 by definition)
+#pragma unroll
+                for (int r = H - 1; r >= 0; r--) {
+                    const unsigned pa = (unsigned)A[r], py = (unsigned)B[r];
+                    const int cl = cbase + r, ch = cbase + r + H;
+                    A[r + H] = (ch < L) ? base16 + hi16(pa) : NEG_INF;
+                    B[r + H] = (ch < L) ? base16 + hi16(py) - e : NEG_INF;
+                    A[r] = (cl < L) ? base16 + lo16(pa) : NEG_INF;
+                    B[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py) - e) : NEG_INF;
+                }
+                rep16 = false;
+            }
+            if (f16) {
+                const unsigned* tab = subtab + (size_t)li * H * 32 + lane;
+                unsigned D16[H], YV[H], X16[H];
+                unsigned ybl = 0, ybh = 0;
+                // ---- pass A: y and d of both halves of every pair (descending: A[r-1] is still the previous row)
+                const unsigned up = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
+                const unsigned dg0 = __byte_perm(up, (unsigned)A[H - 1], 0x5432);  // lo <- cell cbase-1, hi <- cell H-1
+#pragma unroll
+                for (int r = H - 1; r >= 0; r--) {
+                    const unsigned um2 = __vadd2((unsigned)A[r], C2C2);              // m + o + e
+                    bool ph, pl;
+                    const unsigned yv = __vibmax_s16x2(um2, (unsigned)B[r], &ph, &pl);  // max(m + o, y) + e ; p = (m + o >= y)
+                    if (!pl) ybl |= 1u << r;
+                    if (!ph) ybh |= 1u << r;
+                    const unsigned dd = __vadd2((r == 0) ? dg0 : (unsigned)A[r - 1], tab[r * 32]);
+                    D16[r] = dd;
+                    YV[r] = yv;
+                    A[r] = (int)__vmaxs2(dd, yv);  // h
+                }
+                if (lane == 0) {  // first-column cell (gap_global_abpoa.rs:78-92): m = x only
+                    D16[0] = (D16[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu);
+                    YV[0] = (YV[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu);
+                    A[0] = (int)(((unsigned)A[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu));
+                }
+                // ---- pass B: two in-lane chains (lo cells 0..H-1, hi cells H..C-1); generator of cell c is h[c-1] + c2
+                const unsigned hup = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
+                unsigned g0 = __vadd2(__byte_perm(hup, (unsigned)A[H - 1], 0x5432), C2C2);
+                if (lane == 0) g0 = (g0 & 0xffff0000u) | ((unsigned)(o + e * (best_p + 1) - base16) & 0xffffu);  // seed, :88
+                {
+                    unsigned xl = pk16(FLOOR16, FLOOR16);
+#pragma unroll
+                    for (int r = 0; r < H; r++) {
+                        const unsigned gen = (r == 0) ? g0 : __vadd2((unsigned)A[r - 1], C2C2);
+                        xl = __viaddmax_s16x2(xl, C1C1, gen);
+                        X16[r] = xl;
+                    }
+                }
+                // cross-lane max-plus scan on the in-lane value of my last column
+                const int c1s = e + max(o, 0);
+                const int xlo_end = lo16(X16[H - 1]);
+                const int agg = max(hi16(X16[H - 1]), xlo_end + H * c1s);
+                const int z = agg - (cbase + C - 1) * c1s;
+                const int winc = warp_incl_max(z, lane);
+                int wexc = __shfl_up_sync(FULL, winc, 1);
+                if (lane == 0) wexc = NEG_INF;
+                const int xin = max(wexc + cbase * c1s, FLOOR16);            // x entering my first column
+                const int xf = max(xlo_end, xin + (H - 1) * c1s);            // final x of my column H-1
+                unsigned CP = pk16(xin, max(xf + c1s, FLOOR16));              // carries of the lo / hi chains
+                // ---- pass C
+                unsigned bestp = pk16(-32768, -32768);
+                int idx_lo = 0, idx_hi = 0;
+                bool xn_l = false, xn_h = false;
+#pragma unroll
+                for (int r = 0; r < H; r++) {
+                    const unsigned x = __vmaxs2(X16[r], CP);
+                    CP = __vadd2(CP, C1C1);
+                    bool dh, dl, th, tl;
+                    const unsigned t = __vibmax_s16x2(D16[r], x, &dh, &dl);   // p = (dd >= x)
+                    const unsigned m = __vibmax_s16x2(t, YV[r], &th, &tl);    // p = (max(dd, x) >= y)
+                    unsigned cl = tl ? (dl ? (unsigned)DIR_D : (unsigned)DIR_L) : (unsigned)DIR_U;
+                    unsigned ch = th ? (dh ? (unsigned)DIR_D : (unsigned)DIR_L) : (unsigned)DIR_U;
+                    if ((ybl >> r) & 1u) cl |= 8u;
+                    if ((ybh >> r) & 1u) ch |= 8u;
+                    if (r > 0 && xn_l) cl |= 4u;   // path_x: x[c-1] > m[c-1] + o of the cell to the left
+                    if (r > 0 && xn_h) ch |= 4u;
+                    (void)__vibmax_s16x2(x, __vadd2(m, OO1), &xn_h, &xn_l);   // p = (x >= m + o + 1)
+                    bool bh, bl;
+                    bestp = __vibmax_s16x2(m, bestp, &bh, &bl);              // p = (m >= best): right-most maximum
+                    if (bl) idx_lo = r;
+                    if (bh) idx_hi = r;
+                    code[r] = cl;
+                    code[r + H] = ch;
+                    A[r] = (int)m;
+                    B[r] = (int)__vadd2(YV[r], EE);
+                }
+                if (lane == 0) code[0] = DIR_U | ((mps & SMASK) << (4 + SB));
+                {
+                    const unsigned lastbits = (xn_l ? 1u : 0u) | (xn_h ? 2u : 0u);
+                    const unsigned upbits = __shfl_up_sync(FULL, lastbits, 1);
+                    if (lane != 0 && (upbits & 2u)) code[0] |= 4u;  // left neighbour = previous lane's last column
+                    if (lastbits & 1u) code[H] |= 4u;               // left neighbour = my column H-1
+                }
+                {
+                    const int blo = lo16(bestp), bhi = hi16(bestp);
+                    if (bhi >= blo) {
+                        bestv = base16 + bhi;
+                        bcol = cbase + H + idx_hi;
+                    } else {
+                        bestv = base16 + blo;
+                        bcol = cbase + idx_lo;
+                    }
+                }
+            } else if (fast) {
                 const int32_t* srow = s_sc + li * 8;
                 const unsigned em = li == 0 ? eqm0 : (li == 1 ? eqm1 : (li == 2 ? eqm2 : (li == 3 ? eqm3 : 0u)));
                 int up = __shfl_up_sync(FULL, A[C - 1], 1);
@@ -455,10 +617,52 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             }
             // ---- row arg-max, right-most (>=)  (gap_global_abpoa.rs:198-203)
             const int tmax = __reduce_max_sync(FULL, bestv);
+            prev_tmax = tmax;
             const unsigned eq = __ballot_sync(FULL, bestv == tmax && bestv > NEGH);
             const uint32_t row_bsp = (uint32_t)__shfl_sync(FULL, bcol, 31 - __clz(eq));
             // ---- stores: packed trace codes, ring copy for predecessor rows, row meta
             store_codes<C, TC>(trace + (size_t)i * STRIDE + cbase, code);
+            if (rep16) {
+                rows16++;
+                const bool need32 = (rf & (RF_IS_PRED | RF_F_PRED)) || i == n - 2;
+                bool leave = need32;
+                if ((rows16 & 63) == 0) {
+                    // range guard + re-basing: real cells drift by a few units per row, so checking every 64 rows keeps
+                    // every packed lane far from wrapping
+                    unsigned mn = (unsigned)A[0];
+                    unsigned y0 = (unsigned)B[0];
+                    if (lane == 0) y0 = (y0 & 0xffff0000u) | (mn & 0xffffu);  // the first-column cell's y is unused
+                    mn = __vmins2(mn, y0);
+#pragma unroll
+                    for (int r = 1; r < H; r++) mn = __vmins2(mn, __vmins2((unsigned)A[r], (unsigned)B[r]));
+                    const int lm = __reduce_min_sync(FULL, min(lo16(mn), hi16(mn)));
+                    const int rel = tmax - base16;
+                    if (lm - rel < -26000) {
+                        leave = true;
+                        en16 = false;  // this read does not fit 16 bits: stay on the 32-bit paths
+                    } else if (rel > 3000 || rel < -3000) {
+                        const unsigned dl = pk16(-rel, -rel);
+#pragma unroll
+                        for (int r = 0; r < H; r++) {
+                            A[r] = (int)__vadd2((unsigned)A[r], dl);
+                            B[r] = (int)__vadd2((unsigned)B[r], dl);
+                        }
+                        base16 += rel;
+                    }
+                }
+                if (leave) {
+#pragma unroll
+                    for (int r = H - 1; r >= 0; r--) {
+                        const unsigned pa = (unsigned)A[r], py = (unsigned)B[r];
+                        const int cl = cbase + r, ch = cbase + r + H;
+                        A[r + H] = (ch < L) ? base16 + hi16(pa) : NEG_INF;
+                        B[r + H] = (ch < L) ? base16 + hi16(py) - e : NEG_INF;
+                        A[r] = (cl < L) ? base16 + lo16(pa) : NEG_INF;
+                        B[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py) - e) : NEG_INF;
+                    }
+                    rep16 = false;
+                }
+            }
             if (rf & RF_IS_PRED) {
                 store_row<C>(ring_m + (size_t)(i & RM) * STRIDE + cbase, A);
                 store_row<C>(ring_y + (size_t)(i & RM) * STRIDE + cbase, B);
@@ -564,16 +768,20 @@ template <int C>
 static int launch_c(const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b, int trace_bytes,
                     int blocks, cudaStream_t st) {
     const bool simple = simple_scoring(s);
+    const size_t smem = (size_t)WARPS_PER_BLOCK * 5 * (C / 2) * 32 * sizeof(unsigned);
+    const void* k = trace_bytes == 1 ? (simple ? (const void*)k_gap_global_blk<C, uint8_t, 2, true> : (const void*)k_gap_global_blk<C, uint8_t, 2, false>)
+                                     : (simple ? (const void*)k_gap_global_blk<C, uint16_t, 6, true> : (const void*)k_gap_global_blk<C, uint16_t, 6, false>);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     if (trace_bytes == 1) {
         if (simple)
-            k_gap_global_blk<C, uint8_t, 2, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, uint8_t, 2, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
         else
-            k_gap_global_blk<C, uint8_t, 2, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, uint8_t, 2, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
     } else {
         if (simple)
-            k_gap_global_blk<C, uint16_t, 6, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, uint16_t, 6, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
         else
-            k_gap_global_blk<C, uint16_t, 6, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, uint16_t, 6, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -593,7 +801,9 @@ int launch_gap_global_blk(int C, const DevGraph& g, const DevScoring& s, const P
 template <int C>
 static int occ_c(int trace_bytes, int* nb) {
     const void* k = trace_bytes == 1 ? (const void*)k_gap_global_blk<C, uint8_t, 2, true> : (const void*)k_gap_global_blk<C, uint16_t, 6, true>;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, WARPS_PER_BLOCK * 32, 0) == cudaSuccess ? 0 : -1;
+    const size_t smem = (size_t)WARPS_PER_BLOCK * 5 * (C / 2) * 32 * sizeof(unsigned);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, WARPS_PER_BLOCK * 32, smem) == cudaSuccess ? 0 : -1;
 }
 int gap_blk_blocks_per_sm(int C, int trace_bytes, int* nb) {
     switch (C) {
