@@ -48,6 +48,7 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int (&v)[C]) {
 
 // ---- packed 16-bit helpers (sm_100a: VIADD.16x2, VIMNMX.S16x2 with one predicate per half, VIADDMNMX.S16x2)
 #define FLOOR16 (-30000)
+#define PADSUB16 (-3000)
 __device__ __forceinline__ unsigned pk16(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(unsigned v) { return (int)v >> 16; }
@@ -153,8 +154,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             for (int r = 0; r < H; r++) {
                 const unsigned rl = (rcw[r / 4] >> (8 * (r % 4))) & 0xffu, rh = (rcw[(r + H) / 4] >> (8 * ((r + H) % 4))) & 0xffu;
 #pragma unroll
-                for (unsigned bse = 0; bse < 5; bse++)
-                    subtab[(bse * H + r) * 32 + lane] = pk16((bse < 4 && rl == bse) ? s_match : s_mis, (bse < 4 && rh == bse) ? s_match : s_mis);
+                for (unsigned bse = 0; bse < 5; bse++) {
+                    // padding columns (c >= L) get a diagonal score so low that their m never reaches their left
+                    // neighbour's: x and y of a padding cell are already strictly below it (c1, c2 < 0), so a padding
+                    // column can never be the row maximum and needs no band mask in the packed path
+                    const int sl = (cbase + r >= L) ? PADSUB16 : ((bse < 4 && rl == bse) ? s_match : s_mis);
+                    const int sh = (cbase + r + H >= L) ? PADSUB16 : ((bse < 4 && rh == bse) ? s_match : s_mis);
+                    subtab[(bse * H + r) * 32 + lane] = pk16(sl, sh);
+                }
             }
             __syncwarp();
         }
