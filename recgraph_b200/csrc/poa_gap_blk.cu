@@ -47,7 +47,7 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int (&v)[C]) {
 }
 
 // ---- packed 16-bit helpers (sm_100a: VIADD.16x2, VIMNMX.S16x2 with one predicate per half, VIADDMNMX.S16x2)
-#define FLOOR16 (-30000)
+#define FLOOR16 (-28000)  // FLOOR16 + PADSUB16 + a few gap steps must stay above -32768
 #define PADSUB16 (-3000)
 __device__ __forceinline__ unsigned pk16(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
