@@ -4,8 +4,8 @@
 //
 // The DP is the exact ABSOLUTE-score form of SURVEY §3.4: per row and per incoming edge ("group") the LEADER path
 // does a linear-gap DP over the read, every other member path copies the leader's move (D / U / L) applied to its own
-// scores. This is what the reference's delta-encoded tensor computes (checked against the literal restatement in
-// oracle/pathwise.cpp). The reverse pass of modes 8/9 (`rev_align`) is the same routine on the reverse graph, rows
+// scores. This is what the reference's delta-encoded tensor computes (the parity tests check it against a literal CPU
+// restatement). The reverse pass of modes 8/9 (`rev_align`) is the same routine on the reverse graph, rows
 // descending, with the read reversed (column jj = L-1-j).
 //
 // One CTA per read. Scores live in an L2-resident ring of rows, layout [row][column][path] so that a warp whose
