@@ -10,6 +10,8 @@
 // row * 32C + column, so the traceback needs no per-row offset lookup.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "device.h"
 #include "poa_common.cuh"
 #include "poa_walk.cuh"
@@ -177,10 +179,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
         uint32_t best_end_row = 0;
         int last_val = 0;
         bool abort_read = false;
+        int last_nonfull = -1;  // last row whose band is not the whole read [0, L)
+#ifdef RG_ROWSTATS
+        unsigned st_cnt[5] = {0, 0, 0, 0, 0};
+        long long st_cyc[5] = {0, 0, 0, 0, 0};
+#endif
 
         int4 ri_next = reinterpret_cast<const int4*>(g.rowinfo)[0];
         for (uint32_t i = 0; i + 1 < n; i++) {
             // packed row info, fetched one row ahead (hides the L1/L2 latency behind the previous row's work)
+#ifdef RG_ROWSTATS
+            const long long st_t0 = clock64();
+            int st_kind = 4;
+#endif
             const int4 riv = ri_next;
             ri_next = reinterpret_cast<const int4*>(g.rowinfo)[i + 1];
             const uint32_t rbits = (uint32_t)riv.w;
@@ -188,6 +199,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             // a segment start whose only predecessor is row i-1 behaves exactly like a row inside a segment
             const bool nwp = (rf & RF_NWP) && !(rf & RF_SINGLE_PREV);
             const uint32_t pb = (uint32_t)riv.z, pe = pb + (nwp ? (rbits >> 24) : 0u);
+            const int best_p = riv.y;
             uint32_t ms, me;
             if (i == 0) {
                 ms = 0;
@@ -214,18 +226,88 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             }
             cells += right - left;
             const int li = rbits & 0xffu;
-            const int best_p = riv.y;
             const unsigned mps = (rbits >> 16) & 0xffu;
             unsigned code[C];
             int bestv = NEG_INF;
             int bcol = 0;
 
-            // Fast path (the steady state of a row inside a segment): band starts at column 0 and lies inside the
-            // previous row's band, so every active cell has its vertical and diagonal source and none of the
-            // availability / fallback logic of gap_global_abpoa.rs:110-141 can trigger.
-            const bool fast = (i > 0) && !nwp && left == 0 && prev_left == 0 && right <= prev_right;
+            // Fast path (a row inside a segment whose band and whose previous row's band start at column 0): every
+            // active cell below the previous row's right edge has its vertical and diagonal source; cells of a band
+            // that grew to the right take the y fallback of gap_global_abpoa.rs:110-141 and have no diagonal beyond
+            // the first new column.
+            const bool fast = (i > 0) && !nwp;
+            const bool plain = left == 0 && prev_left == 0 && right <= prev_right;
 
-            bool f16 = en16 && fast && right == (uint32_t)L && prev_right == (uint32_t)L;
+            bool f16 = en16 && fast && plain && right == (uint32_t)L && prev_right == (uint32_t)L;
+            // Packed segment-start row: every predecessor row (none of them row 0) and this row span the whole read, so
+            // that no availability / fallback rule of gap_global_abpoa.rs:110-141 can trigger. The predecessor rows are
+            // gathered from the ring straight into the packed representation; per cell the slot of the winning
+            // predecessor (first in list order wins ties, :266-345) is kept as bit planes over my columns.
+            bool g16 = en16 && nwp && i > 0 && left == 0 && right == (uint32_t)L && best_p >= 1 && best_p > last_nonfull;
+            unsigned mm_lo[SB], mm_hi[SB], ym_lo[SB], ym_hi[SB];
+            if (g16) {
+                if (!rep16) base16 = prev_tmax;
+                const int lo_ok = base16 - 24000;
+                bool ok = true;
+#pragma unroll
+                for (int bq = 0; bq < SB; bq++) mm_lo[bq] = mm_hi[bq] = ym_lo[bq] = ym_hi[bq] = 0u;
+                for (uint32_t q = 0; q < pe - pb; q++) {
+                    const uint32_t p = g.pred_idx[pb + q];
+                    const int32_t* mp = ring_m + (size_t)(p & RM) * STRIDE + cbase;
+                    const int32_t* yp = ring_y + (size_t)(p & RM) * STRIDE + cbase;
+                    unsigned wm_lo = 0, wm_hi = 0, wy_lo = 0, wy_hi = 0;  // cells where predecessor q wins
+                    auto take = [&](int r, int vml, int vmh, int vyl, int vyh) {
+                        const int cl = cbase + r, ch = cbase + r + H;
+                        const bool rl = cl < L, rh = ch < L;
+                        ok = ok && (!rl || ((unsigned)(vml - lo_ok) <= 30000u && (cl == 0 || (unsigned)(vyl + e - lo_ok) <= 30000u)));
+                        ok = ok && (!rh || ((unsigned)(vmh - lo_ok) <= 30000u && (unsigned)(vyh + e - lo_ok) <= 30000u));
+                        const unsigned nm = pk16(rl ? vml - base16 : FLOOR16, rh ? vmh - base16 : FLOOR16);
+                        const unsigned ny = pk16((rl && cl != 0) ? vyl + e - base16 : FLOOR16, rh ? vyh + e - base16 : FLOOR16);
+                        if (q == 0) {
+                            A[r] = (int)nm;
+                            B[r] = (int)ny;
+                        } else {
+                            bool ph, pl;
+                            A[r] = (int)__vibmax_s16x2((unsigned)A[r], nm, &ph, &pl);  // p = (current >= new): keep
+                            if (!pl) wm_lo |= 1u << r;
+                            if (!ph) wm_hi |= 1u << r;
+                            B[r] = (int)__vibmax_s16x2((unsigned)B[r], ny, &ph, &pl);
+                            if (!pl) wy_lo |= 1u << r;
+                            if (!ph) wy_hi |= 1u << r;
+                        }
+                    };
+                    if constexpr (H >= 4) {
+#pragma unroll
+                        for (int j = 0; j < H; j += 4) {
+                            const int4 mlv = reinterpret_cast<const int4*>(mp)[j / 4], mhv = reinterpret_cast<const int4*>(mp + H)[j / 4];
+                            const int4 ylv = reinterpret_cast<const int4*>(yp)[j / 4], yhv = reinterpret_cast<const int4*>(yp + H)[j / 4];
+                            take(j, mlv.x, mhv.x, ylv.x, yhv.x);
+                            take(j + 1, mlv.y, mhv.y, ylv.y, yhv.y);
+                            take(j + 2, mlv.z, mhv.z, ylv.z, yhv.z);
+                            take(j + 3, mlv.w, mhv.w, ylv.w, yhv.w);
+                        }
+                    } else {  // C == 4: one 128-bit load holds both halves
+                        const int4 mv = reinterpret_cast<const int4*>(mp)[0], yv = reinterpret_cast<const int4*>(yp)[0];
+                        take(0, mv.x, mv.z, yv.x, yv.z);
+                        take(1, mv.y, mv.w, yv.y, yv.w);
+                    }
+#pragma unroll
+                    for (int bq = 0; bq < SB; bq++) {
+                        const bool on = (q >> bq) & 1u;
+                        mm_lo[bq] = on ? (mm_lo[bq] | wm_lo) : (mm_lo[bq] & ~wm_lo);
+                        mm_hi[bq] = on ? (mm_hi[bq] | wm_hi) : (mm_hi[bq] & ~wm_hi);
+                        ym_lo[bq] = on ? (ym_lo[bq] | wy_lo) : (ym_lo[bq] & ~wy_lo);
+                        ym_hi[bq] = on ? (ym_hi[bq] | wy_hi) : (ym_hi[bq] & ~wy_hi);
+                    }
+                }
+                if (__all_sync(FULL, ok)) {
+                    if (!rep16) rows16 = 0;
+                    rep16 = true;
+                } else {
+                    g16 = false;   // the 32-bit general path gathers from the ring itself: the packed state is dropped
+                    rep16 = false;
+                }
+            }
             if (f16 && !rep16) {
                 // 32-bit -> packed: every real cell must fit comfortably; padding columns (c >= L) and the unused
                 // y of the first-column cell start at the floor and become "healthy" within a row or two
@@ -254,7 +336,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     f16 = false;
                 }
             }
-            if (!f16 && rep16) {
+            if (!f16 && !g16 && rep16 && nwp) rep16 = false;  // segment starts read their predecessors from the ring
+            if (!f16 && !g16 && rep16) {
                 // packed -> 32-bit (padding columns are outside the band: NEG_INF; y[i][0] is 0 by definition)
 #pragma unroll
                 for (int r = H - 1; r >= 0; r--) {
@@ -267,7 +350,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                 }
                 rep16 = false;
             }
-            if (f16) {
+            auto row16 = [&](auto nwp_tag) {
+                constexpr bool NWP = decltype(nwp_tag)::value;
                 const unsigned* tab = subtab + (size_t)li * H * 32 + lane;
                 unsigned D16[H], YV[H], X16[H];
                 unsigned ybl = 0, ybh = 0;
@@ -290,6 +374,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     D16[0] = (D16[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu);
                     YV[0] = (YV[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu);
                     A[0] = (int)(((unsigned)A[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu));
+                }
+                // slot bit planes of the diagonal source (= the m-winner of the cell to the left) and of the vertical
+                // source (the y-winner where y extends, the m-winner where it opens)
+                unsigned dm_lo[SB], dm_hi[SB], um_lo[SB], um_hi[SB];
+                if constexpr (NWP) {
+#pragma unroll
+                    for (int bq = 0; bq < SB; bq++) {
+                        const unsigned upb = __shfl_up_sync(FULL, mm_hi[bq] >> (H - 1), 1) & 1u;
+                        dm_lo[bq] = (mm_lo[bq] << 1) | upb;
+                        dm_hi[bq] = (mm_hi[bq] << 1) | ((mm_lo[bq] >> (H - 1)) & 1u);
+                        um_lo[bq] = (ybl & ym_lo[bq]) | (~ybl & mm_lo[bq]);
+                        um_hi[bq] = (ybh & ym_hi[bq]) | (~ybh & mm_hi[bq]);
+                    }
                 }
                 // ---- pass B: two in-lane chains (lo cells 0..H-1, hi cells H..C-1); generator of cell c is h[c-1] + c2
                 const unsigned hup = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
@@ -332,6 +429,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     if ((ybh >> r) & 1u) ch |= 8u;
                     if (r > 0 && xn_l) cl |= 4u;   // path_x: x[c-1] > m[c-1] + o of the cell to the left
                     if (r > 0 && xn_h) ch |= 4u;
+                    if constexpr (NWP) {
+#pragma unroll
+                        for (int bq = 0; bq < SB; bq++) {
+                            cl |= (((dm_lo[bq] >> r) & 1u) << (4 + bq)) | (((um_lo[bq] >> r) & 1u) << (4 + SB + bq));
+                            ch |= (((dm_hi[bq] >> r) & 1u) << (4 + bq)) | (((um_hi[bq] >> r) & 1u) << (4 + SB + bq));
+                        }
+                    }
                     (void)__vibmax_s16x2(x, __vadd2(m, OO1), &xn_h, &xn_l);   // p = (x >= m + o + 1)
                     bool bh, bl;
                     bestp = __vibmax_s16x2(m, bestp, &bh, &bl);              // p = (m >= best): right-most maximum
@@ -359,10 +463,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                         bcol = cbase + idx_lo;
                     }
                 }
-            } else if (fast) {
+            };
+            // 32-bit row inside a segment (predecessor = row i-1, held in registers). PLAIN: both bands start at column 0
+            // and this one lies inside the previous one, so every active cell has its vertical and diagonal source.
+            // Otherwise cells without a vertical source take the y fallback of gap_global_abpoa.rs:110-141, cells
+            // without a diagonal source have none, and the x chain starts at column `left` (:94-109).
+            auto row32 = [&](auto plain_tag) {
+                constexpr bool PLAIN = decltype(plain_tag)::value;
                 const int32_t* srow = s_sc + li * 8;
                 const unsigned em = li == 0 ? eqm0 : (li == 1 ? eqm1 : (li == 2 ? eqm2 : (li == 3 ? eqm3 : 0u)));
                 int up = __shfl_up_sync(FULL, A[C - 1], 1);
+                if (lane == 0) up = NEG_INF;
+                const int fbq = 2 * o + e * (best_p + 1);  // gap_global_abpoa.rs:117,139
+                const int seed = (left == 0) ? o + e * (best_p + 1) : fbq + e * (int)left;  // :88 / :99
+                const bool fc0 = (lane == 0) && left == 0;
                 unsigned ybits = 0;
                 int D[C];
                 // pass A (descending so that A[k-1] is still the previous row when cell k reads its diagonal)
@@ -370,8 +484,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                 for (int k = C - 1; k >= 0; k--) {
                     const int um = A[k] + o;
                     const int uy = B[k];
-                    const int yv = max(um, uy) + e;
-                    if (uy > um) ybits |= 1u << k;
+                    int yv = max(um, uy) + e;
+                    bool yb = uy > um;
+                    if (!PLAIN && !(A[k] > NEGH)) {
+                        yv = fbq + e * (cbase + k);
+                        yb = false;
+                    }
+                    if (yb) ybits |= 1u << k;
                     int sub;
                     if (SIMPLE) {
                         sub = ((em >> k) & 1u) ? s_match : s_mis;
@@ -379,9 +498,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                         const unsigned rc = (rcw[k / 4] >> (8 * (k % 4))) & 0xffu;
                         sub = srow[rc];
                     }
-                    int dd = ((k == 0) ? up : A[k - 1]) + sub;
+                    const int dsrc = (k == 0) ? up : A[k - 1];
+                    int dd = dsrc + sub;
+                    if (!PLAIN && !(dsrc > NEGH)) dd = NEG_INF;
                     int h = max(dd, yv);
-                    if (k == 0 && lane == 0) {  // first-column cell: m = x only
+                    if (k == 0 && fc0) {  // first-column cell: m = x only
                         dd = NEG_INF;
                         h = NEG_INF;
                     }
@@ -389,7 +510,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     D[k] = dd;
                     A[k] = h;
                 }
-                // pass B: in-lane x chain; generator of column c is h[c-1] + c2, the seed sits at column 0
+                // pass B: in-lane x chain; generator of column c is h[c-1] + c2, the seed sits at column `left`
                 int hprev = __shfl_up_sync(FULL, A[C - 1], 1);
                 int X[C];
                 {
@@ -397,7 +518,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 #pragma unroll
                     for (int k = 0; k < C; k++) {
                         int gen = ((k == 0) ? hprev : A[k - 1]) + c2;
-                        if (k == 0 && lane == 0) gen = o + e * (best_p + 1);  // gap_global_abpoa.rs:88
+                        if (PLAIN) {
+                            if (k == 0 && lane == 0) gen = seed;
+                        } else {
+                            if (cbase + k < (int)left) gen = NEG_INF;
+                            if (cbase + k == (int)left) gen = seed;
+                        }
                         xl = max(xl + c1, gen);
                         X[k] = xl;
                     }
@@ -418,7 +544,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     const int dd = D[k];
                     int yv = B[k];
                     int ye = yv;
-                    if (k == 0 && lane == 0) {
+                    if (k == 0 && fc0) {
                         ye = NEG_INF;
                         yv = 0;
                     }
@@ -426,18 +552,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     const int m = max(t, ye);
                     unsigned cd = (t < ye) ? (unsigned)DIR_U : ((dd < x) ? (unsigned)DIR_L : (unsigned)DIR_D);
                     if ((ybits >> k) & 1u) cd |= 8u;
-                    if (k == 0 && lane == 0) cd = DIR_U | ((mps & SMASK) << (4 + SB));
-                    if (k > 0 && xn_prev) cd |= 4u;
+                    if (k == 0 && fc0) cd = DIR_U | ((mps & SMASK) << (4 + SB));
+                    if (k > 0 && xn_prev && (PLAIN || c > (int)left)) cd |= 4u;
                     xn_prev = (x > m + o) ? 1u : 0u;
                     if (k == C - 1) xn_last = xn_prev;
                     code[k] = cd;
-                    const bool act = c < (int)right;
+                    const bool act = PLAIN ? (c < (int)right) : (c >= (int)left && c < (int)right);
                     A[k] = act ? m : NEG_INF;
                     B[k] = act ? yv : NEG_INF;
                     bestv = max(bestv, A[k]);
                 }
                 unsigned pl = __shfl_up_sync(FULL, xn_last, 1);
-                if (lane != 0 && pl) code[0] |= 4u;
+                if (lane != 0 && pl && (PLAIN || cbase > (int)left)) code[0] |= 4u;
                 // right-most maximum inside the lane (only lanes holding the row maximum matter)
                 {
                     const int lanemax = bestv;
@@ -447,6 +573,25 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                         if (A[k] == lanemax) eqb |= 1u << k;
                     bcol = cbase + (31 - __clz(eqb | 1u));
                 }
+            };
+            if (g16) {
+                row16(std::true_type{});
+#ifdef RG_ROWSTATS
+                st_kind = 1;
+#endif
+            } else if (f16) {
+                row16(std::false_type{});
+#ifdef RG_ROWSTATS
+                st_kind = 0;
+#endif
+            } else if (fast) {
+                if (plain)
+                    row32(std::true_type{});
+                else
+                    row32(std::false_type{});
+#ifdef RG_ROWSTATS
+                st_kind = plain ? 2 : 3;
+#endif
             } else if (i == 0) {
                 // gap_global_abpoa.rs:68-77
 #pragma unroll
@@ -631,28 +776,34 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             store_codes<C, TC>(trace + (size_t)i * STRIDE + cbase, code);
             if (rep16) {
                 rows16++;
-                const bool need32 = (rf & (RF_IS_PRED | RF_F_PRED)) || i == n - 2;
+                const bool need32 = (rf & RF_F_PRED) || i == n - 2;
                 bool leave = need32;
                 if ((rows16 & 63) == 0) {
                     // range guard + re-basing: real cells drift by a few units per row, so checking every 64 rows keeps
                     // every packed lane far from wrapping
-                    unsigned mn = (unsigned)A[0];
-                    unsigned y0 = (unsigned)B[0];
-                    if (lane == 0) y0 = (y0 & 0xffff0000u) | (mn & 0xffffu);  // the first-column cell's y is unused
-                    mn = __vmins2(mn, y0);
+                    // padding columns (c >= L) are ignored: they sit at the floor right after a packed gather
+                    unsigned mn = pk16(32767, 32767);
 #pragma unroll
-                    for (int r = 1; r < H; r++) mn = __vmins2(mn, __vmins2((unsigned)A[r], (unsigned)B[r]));
+                    for (int r = 0; r < H; r++) {
+                        unsigned yy = (unsigned)B[r];
+                        if (r == 0 && lane == 0) yy = (yy & 0xffff0000u) | ((unsigned)A[0] & 0xffffu);  // the first-column cell's y is unused
+                        const unsigned v = __vmins2((unsigned)A[r], yy);
+                        const unsigned real = pk16((cbase + r < L) ? -32768 : 32767, (cbase + r + H < L) ? -32768 : 32767);
+                        mn = __vmins2(mn, __vmaxs2(v, real));
+                    }
                     const int lm = __reduce_min_sync(FULL, min(lo16(mn), hi16(mn)));
                     const int rel = tmax - base16;
                     if (lm - rel < -26000) {
                         leave = true;
                         en16 = false;  // this read does not fit 16 bits: stay on the 32-bit paths
                     } else if (rel > 3000 || rel < -3000) {
-                        const unsigned dl = pk16(-rel, -rel);
+                        // |rel| stays below ~7000 (3000 + 64 rows of drift): no packed lane can wrap here; lanes that would
+                        // sink below the floor (padding) are pulled back to it
+                        const unsigned dl = pk16(-rel, -rel), fl = pk16(FLOOR16, FLOOR16);
 #pragma unroll
                         for (int r = 0; r < H; r++) {
-                            A[r] = (int)__vadd2((unsigned)A[r], dl);
-                            B[r] = (int)__vadd2((unsigned)B[r], dl);
+                            A[r] = (int)__vmaxs2(__vaddss2((unsigned)A[r], dl), fl);
+                            B[r] = (int)__vmaxs2(__vaddss2((unsigned)B[r], dl), fl);
                         }
                         base16 += rel;
                     }
@@ -670,9 +821,28 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     rep16 = false;
                 }
             }
+            if (left != 0 || right != (uint32_t)L) last_nonfull = (int)i;
             if (rf & RF_IS_PRED) {
-                store_row<C>(ring_m + (size_t)(i & RM) * STRIDE + cbase, A);
-                store_row<C>(ring_y + (size_t)(i & RM) * STRIDE + cbase, B);
+                int32_t* mp = ring_m + (size_t)(i & RM) * STRIDE + cbase;
+                int32_t* yp = ring_y + (size_t)(i & RM) * STRIDE + cbase;
+                if (rep16) {
+                    // the ring keeps 32-bit rows (padding columns NEG_INF, y[i][0] = 0): unpack on the way out
+                    int VM[C], VY[C];
+#pragma unroll
+                    for (int r = 0; r < H; r++) {
+                        const unsigned pa = (unsigned)A[r], py = (unsigned)B[r];
+                        const int cl = cbase + r, ch = cbase + r + H;
+                        VM[r] = (cl < L) ? base16 + lo16(pa) : NEG_INF;
+                        VM[r + H] = (ch < L) ? base16 + hi16(pa) : NEG_INF;
+                        VY[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py) - e) : NEG_INF;
+                        VY[r + H] = (ch < L) ? base16 + hi16(py) - e : NEG_INF;
+                    }
+                    store_row<C>(mp, VM);
+                    store_row<C>(yp, VY);
+                } else {
+                    store_row<C>(mp, A);
+                    store_row<C>(yp, B);
+                }
             }
             if (lane == 0) {
                 RowMeta rm;
@@ -683,6 +853,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                 rowmeta[i] = rm;
             }
             __syncwarp();
+#ifdef RG_ROWSTATS
+            {
+                const long long dt = clock64() - st_t0;
+#pragma unroll
+                for (int q = 0; q < 5; q++)
+                    if (st_kind == q) {
+                        st_cnt[q]++;
+                        st_cyc[q] += dt;
+                    }
+            }
+#endif
             prev_bsp = row_bsp;
             prev_left = left;
             prev_right = right;
@@ -748,6 +929,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             const long long t_end = clock64();
             res.fen = (uint32_t)((t_dp - t_start) >> 10);
             res.rsn = (uint32_t)((t_end - t_dp) >> 10);
+#ifdef RG_ROWSTATS
+            res.best_path = st_cnt[0];
+            res.rev_best_path = st_cnt[1];
+            res.rec_col = st_cnt[2];
+            res.rev_end_row = st_cnt[3];
+            res.displacement = (int32_t)st_cnt[4];
+            res.score_f32 = (float)(st_cyc[0] >> 10);
+            res.n_runs_rev = (uint32_t)(st_cyc[1] >> 10);
+            res.end_col = (uint32_t)(st_cyc[2] >> 10);   // diagnostics build only: overwrites result fields
+            res.start_row = (uint32_t)(st_cyc[3] >> 10);
+            res.start_col = (uint32_t)(st_cyc[4] >> 10);
+#endif
         }
         if (lane == 0) b.results[ridx] = res;
         __syncwarp();

@@ -33,3 +33,10 @@ dp = np.array([res.reads[i].fen for i in range(res.n_reads)], dtype=np.float64)
 tb = np.array([res.reads[i].rsn for i in range(res.n_reads)], dtype=np.float64)
 if a.mode == 2:
     print("kcycles per read: forward mean %.0f, traceback mean %.0f (%.1f%% of total); runs/read %.0f" % (dp.mean(), tb.mean(), 100 * tb.sum() / (dp.sum() + tb.sum()), res.n_runs_total / max(1, res.n_reads)))
+if a.mode == 2 and os.environ.get("RG_ROWSTATS"):
+    f = lambda name: np.array([float(getattr(res.reads[i], name)) for i in range(res.n_reads)]).sum()
+    cnt = [f("best_path"), f("rev_best_path"), f("rec_col"), f("rev_end_row"), f("displacement")]
+    cyc = [f("score_f32"), f("n_runs_rev"), f("end_col"), f("start_row"), f("start_col")]
+    tot = sum(cnt)
+    for nm, c, k in zip(["f16", "g16", "plain32", "band32", "general/i0"], cnt, cyc):
+        print("%-10s rows %6.2f%%  cycles %6.2f%%  cycles/row %8.0f" % (nm, 100 * c / tot, 100 * k / sum(cyc), 1024 * k / max(1, c)))
