@@ -82,7 +82,8 @@ struct rg_ctx {
     bool has_graph = false;
     FlatGraph fg;
     DevBuf<uint8_t> d_lnz, d_rowflags, d_min_pred_slot, d_prev_slot;
-    DevBuf<uint32_t> d_pred_off, d_pred_idx, d_min_pred;
+    DevBuf<uint32_t> d_pred_off, d_pred_idx, d_min_pred, d_nwp_ord;
+    uint32_t n_gather = 0;
     DevBuf<int32_t> d_r_values;
     DevBuf<RowInfo> d_rowinfo;
     DevGraph dg{};
@@ -275,6 +276,10 @@ static int upload_graph(rg_ctx* c) {
     if (f.n > 2 && f.nwp[1])
         for (uint32_t k = f.pred_off[1]; k < f.pred_off[2]; k++) rowflags[f.pred_idx[k]] |= RF_IS_PRED;
     for (uint32_t k = f.pred_off[f.n - 1]; k < f.pred_off[f.n]; k++) rowflags[f.pred_idx[k]] |= RF_F_PRED;
+    std::vector<uint32_t> nwp_ord(f.n, 0);
+    c->n_gather = 0;
+    for (uint32_t i = 0; i < f.n; i++)
+        if ((rowflags[i] & RF_NWP) && !(rowflags[i] & RF_SINGLE_PREV)) nwp_ord[i] = c->n_gather++;
     std::vector<RowInfo> rowinfo(f.n);
     for (uint32_t i = 0; i < f.n; i++) {
         uint32_t np = f.nwp[i] ? f.pred_off[i + 1] - f.pred_off[i] : 0;
@@ -291,7 +296,8 @@ static int upload_graph(rg_ctx* c) {
     bool ok = c->d_rowinfo.upload(rowinfo, st) && c->d_lnz.upload(f.lnz, st) && c->d_rowflags.upload(rowflags, st) &&
               c->d_pred_off.upload(f.pred_off, st) && c->d_pred_idx.upload(f.pred_idx, st) &&
               c->d_min_pred.upload(f.min_pred, st) && c->d_min_pred_slot.upload(f.min_pred_slot, st) &&
-              c->d_prev_slot.upload(f.prev_slot, st) && c->d_r_values.upload(f.r_values, st);
+              c->d_prev_slot.upload(f.prev_slot, st) && c->d_r_values.upload(f.r_values, st) &&
+              c->d_nwp_ord.upload(nwp_ord, st);
     if (!ok || cudaStreamSynchronize(st) != cudaSuccess) return c->cuda_fail("graph upload");
     uint32_t ring = 2;
     while (ring <= f.max_lookback) ring <<= 1;
@@ -306,6 +312,8 @@ static int upload_graph(rg_ctx* c) {
     c->dg.r_values = c->d_r_values.p;
     c->dg.rowinfo = c->d_rowinfo.p;
     c->dg.ring = ring;
+    c->dg.nwp_ord = c->d_nwp_ord.p;
+    c->dg.n_gather = c->n_gather;
     c->has_graph = true;
     c->results_ready = false;
     return RG_OK;
@@ -521,7 +529,14 @@ static int align_poa(rg_ctx* c, int mode) {
     // memory already held by this ctx's work-space is reusable
     free_b += (c->d_rowmeta.cap * sizeof(RowMeta)) + (c->d_ring_m.cap + c->d_ring_y.cap) * 4 + c->d_trace.cap +
               (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
-    const uint64_t full = blkC ? (uint64_t)n * wstride  // fixed row stride, absolute columns
+    // blocked mode-2 kernel: 4 bit planes per cell (32 * C/8 words per row) + predecessor-slot planes of the gathering rows
+    const bool blk2 = blkC && !lin;
+    const int SBk = trace_bytes == 1 ? 2 : 6;
+    const uint64_t plane_bytes = (((uint64_t)n * 128u * std::max(1, blkC / 8)) + 255) & ~255ull;
+    const uint64_t side_bytes = (uint64_t)c->n_gather * 2u * SBk * 128u;
+    const int tb_alloc = blk2 ? 1 : trace_bytes;
+    const uint64_t full = blk2 ? plane_bytes + side_bytes
+                          : blkC ? (uint64_t)n * wstride  // fixed row stride, absolute columns
                               : std::min<uint64_t>((uint64_t)n * Lmax, 0x7ffffe00ull);  // the band can open to the whole row
     const uint32_t run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)(n / 4 + 2 * Lmax)), 1u << 22);
     const size_t per_slot_fixed = (size_t)n * sizeof(RowMeta) + (size_t)c->dg.ring * wstride * 8 + (size_t)run_cap * sizeof(rg_run);
@@ -535,7 +550,7 @@ static int align_poa(rg_ctx* c, int mode) {
         // Reads in flight are limited by trace memory: prefer the full n x L trace per slot (never overflows),
         // shrink the number of slots down to one block per SM before shrinking the trace.
         uint64_t trace_cap = full;
-        size_t per_slot = per_slot_fixed + (size_t)trace_cap * trace_bytes;
+        size_t per_slot = per_slot_fixed + (size_t)trace_cap * tb_alloc;
         if ((size_t)slots * per_slot > budget) {
             uint32_t min_slots = std::min<uint32_t>(slots, std::max<uint32_t>(8, (uint32_t)c->sms * 8 >> attempt));
             uint32_t fit = (uint32_t)std::min<size_t>(budget / per_slot, 1u << 20) / 8 * 8;
@@ -545,13 +560,13 @@ static int align_poa(rg_ctx* c, int mode) {
                 slots = min_slots;
                 size_t each = budget / slots;
                 if (each <= per_slot_fixed + 4096) return c->fail(RG_ERR_NOMEM, "not enough device memory for the alignment work-space");
-                trace_cap = std::min<uint64_t>(full, (each - per_slot_fixed) / trace_bytes);
+                trace_cap = std::min<uint64_t>(full, (each - per_slot_fixed) / tb_alloc);
             }
         }
         trace_cap = (trace_cap + 255) & ~255ull;  // round UP: `full` must always fit
         bool ok = c->d_rowmeta.ensure((size_t)slots * n) && c->d_ring_m.ensure((size_t)slots * c->dg.ring * wstride) &&
                   c->d_ring_y.ensure((size_t)slots * c->dg.ring * wstride) &&
-                  c->d_trace.ensure((size_t)slots * trace_cap * trace_bytes) &&
+                  c->d_trace.ensure((size_t)slots * trace_cap * tb_alloc) &&
                   c->d_slot_runs.ensure((size_t)slots * run_cap) && c->d_out_runs.ensure(out_runs_cap) &&
                   c->d_results.ensure(c->n_reads + 1) && c->d_counters.ensure(4);
         if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
@@ -566,6 +581,7 @@ static int align_poa(rg_ctx* c, int mode) {
         ws.wstride = wstride;
         ws.slots = slots;
         ws.use16 = c->no_s16 ? 0u : 1u;
+        ws.side_off = plane_bytes;
         PoaBatch b{};
         b.reads = c->d_reads.p;
         b.read_off = c->d_read_off.p;

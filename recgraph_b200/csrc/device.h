@@ -33,6 +33,8 @@ struct DevGraph {
     const int32_t* r_values;        // n
     const RowInfo* rowinfo;         // n
     uint32_t ring;                  // power of two > max look-back: depth of the predecessor-row ring
+    const uint32_t* nwp_ord;        // n: ordinal of the row among segment starts that gather predecessors (RF_NWP && !RF_SINGLE_PREV)
+    uint32_t n_gather;              // number of such rows
 };
 
 struct DevScoring {
@@ -64,6 +66,7 @@ struct PoaWorkspace {
     uint32_t wstride;    // ints per ring row (>= max L, multiple of 32)
     uint32_t slots;
     uint32_t use16;      // mode 2: allow the packed 16-bit fast path (RG_NO_S16 disables it for A/B tests)
+    uint64_t side_off;   // blocked mode-2 kernel: byte offset of the predecessor-slot planes inside a slot's trace region
 };
 
 struct PoaBatch {

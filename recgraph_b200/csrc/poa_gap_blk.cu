@@ -20,26 +20,97 @@ namespace rg {
 
 #define NEGH (NEG_INF / 2)  // anything below is "no value"
 
-template <int C, typename TC>
-__device__ __forceinline__ void store_codes(TC* dst, const unsigned (&code)[C]) {
-    constexpr int PER = 4 / sizeof(TC);  // codes per 32-bit word
-    constexpr int NW = C / PER;
-    unsigned w[NW];
-#pragma unroll
-    for (int j = 0; j < NW; j++) {
-        unsigned v = 0;
-#pragma unroll
-        for (int q = 0; q < PER; q++) v |= code[j * PER + q] << (q * 8 * sizeof(TC));
-        w[j] = v;
-    }
-    if constexpr (NW >= 4) {
-#pragma unroll
-        for (int j = 0; j < NW; j += 4) reinterpret_cast<uint4*>(dst)[j / 4] = make_uint4(w[j], w[j + 1], w[j + 2], w[j + 3]);
-    } else if constexpr (NW == 2) {
-        reinterpret_cast<uint2*>(dst)[0] = make_uint2(w[0], w[1]);
+// ---- trace layout of this kernel: four bit planes per row (instead of one code byte per cell)
+//   plane 0 (T): the cell's m is max(d, x), i.e. the move is not vertical     plane 2 (X): path_x flag (x extends)
+//   plane 1 (D): d >= x, i.e. diagonal rather than horizontal when T is set   plane 3 (Y): path_y flag (y extends)
+// Lane t owns the 4*C bits of its C columns: bit p*C + k = plane p of column t*C + k, stored in NW = max(1, C/8)
+// words at word offset row * 32*NW + t*NW. Rows that gather several predecessors additionally keep 2*SB slot planes
+// (diagonal source, vertical source) in a side array indexed by DevGraph::nwp_ord.
+template <int C>
+struct PlaneFmt {
+    static constexpr int NW = (C >= 8) ? C / 8 : 1;
+    static constexpr int ROWW = 32 * NW;
+};
+
+template <int C>
+__device__ __forceinline__ void store_planes(uint32_t* dst, const unsigned (&P)[4]) {
+    if constexpr (C == 32) {
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(P[0], P[1], P[2], P[3]);
+    } else if constexpr (C == 16) {
+        reinterpret_cast<uint2*>(dst)[0] = make_uint2(P[0] | (P[1] << 16), P[2] | (P[3] << 16));
     } else {
-        reinterpret_cast<unsigned*>(dst)[0] = w[0];
+        dst[0] = P[0] | (P[1] << C) | (P[2] << (2 * C)) | (P[3] << (3 * C));
     }
+}
+
+// code byte layout of the 32-bit producers (dir 2 | x 1 | y 1 | dslot SB | uslot SB) -> planes
+template <int C, int SB>
+__device__ __forceinline__ void planes_from_codes(const unsigned (&code)[C], unsigned (&P)[4], unsigned (&SD)[SB], unsigned (&SU)[SB]) {
+    P[0] = P[1] = P[2] = P[3] = 0u;
+#pragma unroll
+    for (int q = 0; q < SB; q++) SD[q] = SU[q] = 0u;
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+        const unsigned cd = code[k], dir = cd & 3u;
+        P[0] |= (dir != (unsigned)DIR_U ? 1u : 0u) << k;
+        P[1] |= (dir == (unsigned)DIR_D ? 1u : 0u) << k;
+        P[2] |= ((cd >> 2) & 1u) << k;
+        P[3] |= ((cd >> 3) & 1u) << k;
+#pragma unroll
+        for (int q = 0; q < SB; q++) {
+            SD[q] |= ((cd >> (4 + q)) & 1u) << k;
+            SU[q] |= ((cd >> (4 + SB + q)) & 1u) << k;
+        }
+    }
+}
+
+// Reader side (traceback): rebuilds the code byte of one cell.
+template <int C, int SB>
+struct PlaneTrace {
+    const uint32_t* planes;
+    const uint32_t* side;
+    const uint8_t* rowflags;
+    const uint32_t* nwp_ord;
+    __device__ __forceinline__ uint32_t code(int64_t rr, int64_t cc) const {
+        constexpr int NW = PlaneFmt<C>::NW;
+        const uint32_t ln = (uint32_t)cc / C, k = (uint32_t)cc % C;
+        const uint32_t* w = planes + (size_t)rr * PlaneFmt<C>::ROWW + ln * NW;
+        unsigned t, d, x, y;
+        if constexpr (C == 32) {
+            const uint4 v = *reinterpret_cast<const uint4*>(w);
+            t = (v.x >> k) & 1u, d = (v.y >> k) & 1u, x = (v.z >> k) & 1u, y = (v.w >> k) & 1u;
+        } else if constexpr (C == 16) {
+            const uint2 v = *reinterpret_cast<const uint2*>(w);
+            t = (v.x >> k) & 1u, d = (v.x >> (16 + k)) & 1u, x = (v.y >> k) & 1u, y = (v.y >> (16 + k)) & 1u;
+        } else {
+            const unsigned v = w[0];
+            t = (v >> k) & 1u, d = (v >> (C + k)) & 1u, x = (v >> (2 * C + k)) & 1u, y = (v >> (3 * C + k)) & 1u;
+        }
+        uint32_t cd = (t ? (d ? (unsigned)DIR_D : (unsigned)DIR_L) : (unsigned)DIR_U) | (x << 2) | (y << 3);
+        if (rr == 0 && cc == 0) cd = DIR_O;
+        const uint8_t rf = rowflags[rr];
+        if ((rf & RF_NWP) && !(rf & RF_SINGLE_PREV)) {
+            const uint32_t* sp = side + (size_t)nwp_ord[rr] * (2 * SB * 32) + ln;
+#pragma unroll
+            for (int q = 0; q < SB; q++) {
+                cd |= ((sp[q * 32] >> k) & 1u) << (4 + q);
+                cd |= ((sp[(SB + q) * 32] >> k) & 1u) << (4 + SB + q);
+            }
+        }
+        return cd;
+    }
+};
+
+// max.s16x2 whose two result predicates (a >= b per half; INV: a < b) set bit `bl` / `bh` of two accumulators.
+// Plain selects and ORs on purpose: a predicated read-modify-write chain on the accumulator makes ptxas keep dozens of
+// predicates alive (it hoists the maxima) and spill them through general registers.
+template <bool INV>
+__device__ __forceinline__ unsigned vmax_flag(unsigned a, unsigned b, unsigned& acc_lo, unsigned& acc_hi, unsigned bl, unsigned bh) {
+    bool ph, pl;
+    const unsigned val = __vibmax_s16x2(a, b, &ph, &pl);
+    acc_lo |= (pl != INV) ? bl : 0u;
+    acc_hi |= (ph != INV) ? bh : 0u;
+    return val;
 }
 
 template <int C>
@@ -49,14 +120,31 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int (&v)[C]) {
 }
 
 // ---- packed 16-bit helpers (sm_100a: VIADD.16x2, VIMNMX.S16x2 with one predicate per half, VIADDMNMX.S16x2)
-#define FLOOR16 (-28000)  // FLOOR16 + PADSUB16 + a few gap steps must stay above -32768
-#define PADSUB16 (-3000)
+// Packed rows keep BIASED fields: field = (score - base16) + 32768 as an unsigned 16-bit number, two cells per register.
+// With every field of every operand inside [lowest garbage, highest real] and that span below 32768, plain 32-bit
+// additions and subtractions of packed words are exact per field (no carry or borrow crosses the halves), so they can
+// issue on either integer pipe, and "a >= b" of both halves is bit 15 / bit 31 of a + 0x80008000 - b.
+#define FLOOR16 (-24000)  // padding columns / unused cells start here (relative to base16)
+#define PADSUB16 (-2000)  // diagonal "score" of padding columns: keeps them strictly below their left neighbour
+#define BIAS2 0x80008000u
+#define PK_ENTER_LO (-12000)  // a row may enter the packed form when its real cells lie in base16 + [LO, HI]
+#define PK_ENTER_HI (1000)
+#define PK_GATHER_LO (-20000)  // predecessor rows gathered while packed (base16 may be up to ~4000 stale)
+#define PK_GATHER_HI (5000)
+#define PK_SPREAD (14000)     // guard: leave the packed form when a real cell falls this far below the row maximum
+#define PK_REBASE (2000)      // guard: re-base when the row maximum drifted this far from base16
+#define PK_GUARD_ROWS 32      // rows between two guards; scores move by at most 60 per row (see en16)
 __device__ __forceinline__ unsigned pk16(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(unsigned v) { return (int)v >> 16; }
+__device__ __forceinline__ unsigned pk16b(int lo, int hi) { return pk16(lo, hi) ^ BIAS2; }   // signed pair -> biased fields
+__device__ __forceinline__ unsigned add2(int c) { return (unsigned)c * 65537u; }                // addend: c on both fields
 
-template <int C, typename TC, int SB, bool SIMPLE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+#ifndef RG_BLK_CTAS
+#define RG_BLK_CTAS 1
+#endif
+template <int C, int SB, bool SIMPLE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
     k_gap_global_blk(DevGraph g, DevScoring sc, PoaWorkspace ws, PoaBatch b) {
     static_assert(C % 4 == 0, "C must be a multiple of 4");
     constexpr int STRIDE = 32 * C;
@@ -79,7 +167,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
     RowMeta* rowmeta = ws.rowmeta + (size_t)slot * n;
     int32_t* ring_m = ws.ring_m + (size_t)slot * g.ring * STRIDE;
     int32_t* ring_y = ws.ring_y + (size_t)slot * g.ring * STRIDE;
-    TC* trace = reinterpret_cast<TC*>(ws.trace) + (size_t)slot * ws.trace_cap;
+    uint32_t* planes = reinterpret_cast<uint32_t*>(ws.trace + (size_t)slot * ws.trace_cap);
+    uint32_t* side = reinterpret_cast<uint32_t*>(ws.trace + (size_t)slot * ws.trace_cap + ws.side_off);
+    constexpr int NW = PlaneFmt<C>::NW;
     rg_run* runs = ws.runs + (size_t)slot * ws.run_cap;
     const int o = sc.o, e = sc.e;
     const int c1 = e + max(o, 0), c2 = o + e;
@@ -114,7 +204,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
         res.run_off = 0;
         res.n_runs = 0;
         res.n_runs_rev = 0;
-        if (L > STRIDE || (uint64_t)n * STRIDE > ws.trace_cap) {  // host sizes the launch so that this never happens
+        if (L > STRIDE || (uint64_t)n * PlaneFmt<C>::ROWW * 4 > ws.side_off ||
+            ws.side_off + (uint64_t)g.n_gather * 2 * SB * 128 > ws.trace_cap) {  // host sizes the launch so that this never happens
             res.status = RG_READ_TRACE_OVERFLOW;
             if (lane == 0) b.results[ridx] = res;
             continue;
@@ -149,8 +240,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
         }
         const int s_match = sc.sc[0][0], s_mis = sc.sc[0][1];
         // exact while no 16-bit lane can wrap: small scores, strictly negative gap steps
-        bool en16 = SIMPLE && (e + max(o, 0) < 0) && (o + e < 0) && abs(o) <= 60 && abs(e) <= 60 && abs(s_match) <= 60 &&
-                    abs(s_mis) <= 60 && ws.use16;
+        bool en16 = SIMPLE && (e + max(o, 0) < 0) && (o + e < 0) && abs(o) <= 30 && abs(e) <= 30 && abs(s_match) <= 30 &&
+                    abs(s_mis) <= 30 && ws.use16;
         if (SIMPLE && en16) {
 #pragma unroll
             for (int r = 0; r < H; r++) {
@@ -162,14 +253,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                     // column can never be the row maximum and needs no band mask in the packed path
                     const int sl = (cbase + r >= L) ? PADSUB16 : ((bse < 4 && rl == bse) ? s_match : s_mis);
                     const int sh = (cbase + r + H >= L) ? PADSUB16 : ((bse < 4 && rh == bse) ? s_match : s_mis);
-                    subtab[(bse * H + r) * 32 + lane] = pk16(sl, sh);
+                    subtab[(bse * H + r) * 32 + lane] = (unsigned)(sh * 65536 + sl);  // addend: sl on the lo field, sh on the hi field
                 }
             }
             __syncwarp();
         }
         bool rep16 = false;   // the previous row is held packed (A[r], B[r] for r < H hold m and y + e relative to base16)
         int base16 = 0, rows16 = 0, prev_tmax = 0;
-        const unsigned C1C1 = pk16(e + max(o, 0), e + max(o, 0)), C2C2 = pk16(o + e, o + e), EE = pk16(e, e), OO1 = pk16(o + 1, o + 1);
+        const unsigned C1F = pk16(e + max(o, 0), e + max(o, 0));  // per-field operand of VIADDMNMX.U16x2
+        const unsigned C1A = add2(e + max(o, 0)), C2A = add2(o + e), EEA = add2(e);   // 32-bit addends
+        const unsigned KY = BIAS2 - add2(1), KX = BIAS2 - add2(o + 1);
         const long long t_start = clock64();
         int A[C], B[C];  // previous row: m and y of my columns (NEG_INF outside its band)
         int status = 0;
@@ -185,8 +278,330 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
         long long st_cyc[5] = {0, 0, 0, 0, 0};
 #endif
 
+        // per-row values shared by the row bodies below
+        int li = 0;                  // graph base of the row
+        int best_p = 0;              // smallest predecessor (seed of the first column, gap_global_abpoa.rs:88)
+        unsigned P[4];               // trace planes of my columns (T, D, X, Y)
+        bool have_planes = false;
+        int bestv = NEG_INF;
+        int bcol = 0;
+        // Packed row (two cells per register) for a row whose band and whose predecessor row(s) span the whole read.
+        // A / B hold the (gathered) predecessor row on entry and this row on exit; leaves P, bestv, bcol.
+        auto row16 = [&]() {
+            const unsigned* tab = subtab + (size_t)li * H * 32 + lane;
+            unsigned D16[H], YV[H], X16[H];
+            // flag accumulators: bit r <- lo cell r, bit 16 + r <- hi cell r
+            unsigned fy = 0, fd = 0, ft = 0, fx = 0, fb = 0;
+            auto flag = [](unsigned& acc, unsigned f, int r) {
+                acc |= (f >> (15 - r)) & ((1u << r) | (1u << (16 + r)));
+            };
+            // ---- pass A: y and d of both halves of every pair (descending: A[r-1] is still the previous row)
+            const unsigned up = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
+            const unsigned dg0 = __byte_perm(up, (unsigned)A[H - 1], 0x5432);  // lo <- cell cbase-1, hi <- cell H-1
+#pragma unroll
+            for (int r = H - 1; r >= 0; r--) {
+                const unsigned um2 = (unsigned)A[r] + C2A;                    // m + o + e
+                const unsigned yv = __vmaxu2(um2, (unsigned)B[r]);            // max(m + o, y) + e
+                flag(fy, (unsigned)B[r] + KY - um2, r);                       // Y: y > m + o
+                const unsigned dd = ((r == 0) ? dg0 : (unsigned)A[r - 1]) + tab[r * 32];
+                D16[r] = dd;
+                YV[r] = yv;
+                A[r] = (int)__vmaxu2(dd, yv);  // h
+            }
+            const unsigned FLB = (unsigned)(FLOOR16 + 32768);
+            if (lane == 0) {  // first-column cell (gap_global_abpoa.rs:78-92): m = x only
+                D16[0] = (D16[0] & 0xffff0000u) | FLB;
+                YV[0] = (YV[0] & 0xffff0000u) | FLB;
+                A[0] = (int)(((unsigned)A[0] & 0xffff0000u) | FLB);
+            }
+            // ---- pass B: two in-lane chains (lo cells 0..H-1, hi cells H..C-1); generator of cell c is h[c-1] + c2
+            const unsigned hup = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
+            unsigned g0 = __byte_perm(hup, (unsigned)A[H - 1], 0x5432) + C2A;
+            if (lane == 0) g0 = (g0 & 0xffff0000u) | ((unsigned)(o + e * (best_p + 1) - base16 + 32768) & 0xffffu);  // seed, :88
+            {
+                unsigned xl = FLB | (FLB << 16);
+#pragma unroll
+                for (int r = 0; r < H; r++) {
+                    const unsigned gen = (r == 0) ? g0 : (unsigned)A[r - 1] + C2A;
+                    xl = __viaddmax_u16x2(xl, C1F, gen);
+                    X16[r] = xl;
+                }
+            }
+            // cross-lane max-plus scan on the in-lane value of my last column (biased integers)
+            const int c1s = e + max(o, 0);
+            const int xlo_end = (int)(X16[H - 1] & 0xffffu);
+            const int agg = max((int)(X16[H - 1] >> 16), xlo_end + H * c1s);
+            const int z = agg - (cbase + C - 1) * c1s;
+            const int winc = warp_incl_max(z, lane);
+            int wexc = __shfl_up_sync(FULL, winc, 1);
+            if (lane == 0) wexc = NEG_INF;
+            const int xin = max(wexc + cbase * c1s, (int)FLB);            // x entering my first column
+            const int xf = max(xlo_end, xin + (H - 1) * c1s);             // final x of my column H-1
+            unsigned CP = (unsigned)xin | ((unsigned)max(xf + c1s, (int)FLB) << 16);  // carries of the lo / hi chains
+            // ---- pass C
+            unsigned bestp = FLB | (FLB << 16);
+#pragma unroll
+            for (int r = 0; r < H; r++) {
+                const unsigned x = __vmaxu2(X16[r], CP);
+                CP += C1A;
+                const unsigned t = __vmaxu2(D16[r], x);
+                flag(fd, D16[r] + BIAS2 - x, r);        // D: dd >= x
+                const unsigned m = __vmaxu2(t, YV[r]);
+                flag(ft, t + BIAS2 - YV[r], r);         // T: max(dd, x) >= y
+                flag(fx, x + KX - m, r);                // x > m + o
+                flag(fb, m + BIAS2 - bestp, r);         // m >= best so far: right-most maximum
+                bestp = __vmaxu2(m, bestp);
+                A[r] = (int)m;
+                B[r] = (int)(YV[r] + EEA);
+            }
+            if constexpr (H < 16) {  // accumulators are laid out for 16 pairs: close the gap between the halves
+                auto squeeze = [](unsigned v) { return (v & ((1u << H) - 1u)) | ((v >> 16) << H); };
+                fy = squeeze(fy), fd = squeeze(fd), ft = squeeze(ft), fx = squeeze(fx), fb = squeeze(fb);
+            }
+            unsigned carry = __shfl_up_sync(FULL, fx >> (C - 1), 1) & 1u;   // fx bit k: x[c] > m[c] + o of my column k
+            if (lane == 0) carry = 0;
+            P[0] = ft;
+            P[1] = fd;
+            P[2] = (fx << 1) | carry;            // path_x of column c: x[c-1] > m[c-1] + o (gap_global_abpoa.rs:358-364)
+            if constexpr (C < 32) P[2] &= (1u << C) - 1u;
+            P[3] = fy;
+            if (lane == 0) {                     // first-column cell: vertical move to the smallest predecessor, no flags
+                P[0] &= ~1u;
+                P[1] &= ~1u;
+                P[2] &= ~1u;
+                P[3] &= ~1u;
+            }
+            have_planes = true;
+            {
+                const int blo = (int)(bestp & 0xffffu), bhi = (int)(bestp >> 16);
+                const unsigned fbl = fb & ((1u << H) - 1u), fbh = fb >> H;
+                if (bhi >= blo) {
+                    bestv = base16 + bhi - 32768;
+                    bcol = cbase + H + 31 - __clz(fbh | 1u);
+                } else {
+                    bestv = base16 + blo - 32768;
+                    bcol = cbase + 31 - __clz(fbl | 1u);
+                }
+            }
+        };
+
+        // Packed gather of the predecessor rows of a segment start (all of them span the whole read, none is row 0):
+        // ring rows -> biased pairs in A / B, winner slots as bit planes. Returns false (A / B garbage) when a value
+        // does not fit the packed range.
+        unsigned mm_lo[SB], mm_hi[SB], ym_lo[SB], ym_hi[SB];
+        auto gather16 = [&](uint32_t pb, uint32_t np) -> bool {
+        const int lo_ok = base16 + PK_GATHER_LO;
+        bool ok = true;
+#pragma unroll
+        for (int bq = 0; bq < SB; bq++) mm_lo[bq] = mm_hi[bq] = ym_lo[bq] = ym_hi[bq] = 0u;
+        for (uint32_t q = 0; q < np; q++) {
+            const uint32_t p = g.pred_idx[pb + q];
+            const int32_t* mp = ring_m + (size_t)(p & RM) * STRIDE + cbase;
+            const int32_t* yp = ring_y + (size_t)(p & RM) * STRIDE + cbase;
+            unsigned wm_lo = 0, wm_hi = 0, wy_lo = 0, wy_hi = 0;  // cells where predecessor q wins
+            auto take = [&](int r, int vml, int vmh, int vyl, int vyh) {
+                const int cl = cbase + r, ch = cbase + r + H;
+                const bool rl = cl < L, rh = ch < L;
+                ok = ok && (!rl || ((unsigned)(vml - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO) && (cl == 0 || (unsigned)(vyl + e - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO))));
+                ok = ok && (!rh || ((unsigned)(vmh - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO) && (unsigned)(vyh + e - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO)));
+                const unsigned nm = pk16(rl ? vml - base16 : FLOOR16, rh ? vmh - base16 : FLOOR16);
+                const unsigned ny = pk16((rl && cl != 0) ? vyl + e - base16 : FLOOR16, rh ? vyh + e - base16 : FLOOR16);
+                if (q == 0) {
+                    A[r] = (int)nm;
+                    B[r] = (int)ny;
+                } else {
+                    bool ph, pl;
+                    A[r] = (int)__vibmax_s16x2((unsigned)A[r], nm, &ph, &pl);  // p = (current >= new): keep
+                    if (!pl) wm_lo |= 1u << r;
+                    if (!ph) wm_hi |= 1u << r;
+                    B[r] = (int)__vibmax_s16x2((unsigned)B[r], ny, &ph, &pl);
+                    if (!pl) wy_lo |= 1u << r;
+                    if (!ph) wy_hi |= 1u << r;
+                }
+            };
+            if constexpr (H >= 4) {
+#pragma unroll
+                for (int j = 0; j < H; j += 4) {
+                    const int4 mlv = reinterpret_cast<const int4*>(mp)[j / 4], mhv = reinterpret_cast<const int4*>(mp + H)[j / 4];
+                    const int4 ylv = reinterpret_cast<const int4*>(yp)[j / 4], yhv = reinterpret_cast<const int4*>(yp + H)[j / 4];
+                    take(j, mlv.x, mhv.x, ylv.x, yhv.x);
+                    take(j + 1, mlv.y, mhv.y, ylv.y, yhv.y);
+                    take(j + 2, mlv.z, mhv.z, ylv.z, yhv.z);
+                    take(j + 3, mlv.w, mhv.w, ylv.w, yhv.w);
+                }
+            } else {  // C == 4: one 128-bit load holds both halves
+                const int4 mv = reinterpret_cast<const int4*>(mp)[0], yv = reinterpret_cast<const int4*>(yp)[0];
+                take(0, mv.x, mv.z, yv.x, yv.z);
+                take(1, mv.y, mv.w, yv.y, yv.w);
+            }
+#pragma unroll
+            for (int bq = 0; bq < SB; bq++) {
+                const bool on = (q >> bq) & 1u;
+                mm_lo[bq] = on ? (mm_lo[bq] | wm_lo) : (mm_lo[bq] & ~wm_lo);
+                mm_hi[bq] = on ? (mm_hi[bq] | wm_hi) : (mm_hi[bq] & ~wm_hi);
+                ym_lo[bq] = on ? (ym_lo[bq] | wy_lo) : (ym_lo[bq] & ~wy_lo);
+                ym_hi[bq] = on ? (ym_hi[bq] | wy_hi) : (ym_hi[bq] & ~wy_hi);
+            }
+        }
+            if (!__all_sync(FULL, ok)) return false;
+#pragma unroll
+            for (int r = 0; r < H; r++) {   // the gather compares signed pairs; rows are kept biased
+                A[r] = (int)((unsigned)A[r] ^ BIAS2);
+                B[r] = (int)((unsigned)B[r] ^ BIAS2);
+            }
+            return true;
+        };
+        // slot planes of a gathered row: the diagonal source of column c is the m-winner of column c-1, the vertical source
+        // is the y-winner where y extends and the m-winner where it opens; the first-column cell goes to the smallest
+        // predecessor (slot mps)
+        auto slots16 = [&](unsigned mps, unsigned (&SD)[SB], unsigned (&SU)[SB]) {
+#pragma unroll
+            for (int bq = 0; bq < SB; bq++) {
+                const unsigned mm = mm_lo[bq] | (mm_hi[bq] << H), ym = ym_lo[bq] | (ym_hi[bq] << H);
+                unsigned cin = __shfl_up_sync(FULL, mm >> (C - 1), 1) & 1u;
+                if (lane == 0) cin = 0;
+                SD[bq] = (mm << 1) | cin;
+                if constexpr (C < 32) SD[bq] &= (1u << C) - 1u;
+                SU[bq] = (P[3] & ym) | (~P[3] & mm);
+                if (lane == 0) SU[bq] = (SU[bq] & ~1u) | ((mps >> bq) & 1u);
+            }
+        };
+        auto side_store = [&](uint32_t row, const unsigned (&SD)[SB], const unsigned (&SU)[SB]) {
+            uint32_t* sp = side + (size_t)g.nwp_ord[row] * (2 * SB * 32) + lane;
+#pragma unroll
+            for (int bq = 0; bq < SB; bq++) {
+                sp[bq * 32] = SD[bq];
+                sp[(SB + bq) * 32] = SU[bq];
+            }
+        };
+        // packed -> 32-bit row (padding columns are outside the band: NEG_INF; y[i][0] is 0 by definition)
+        auto unpack16 = [&](int (&VM)[C], int (&VY)[C]) {
+#pragma unroll
+            for (int r = H - 1; r >= 0; r--) {
+                const unsigned pa = (unsigned)A[r] ^ BIAS2, py = (unsigned)B[r] ^ BIAS2;
+                const int cl = cbase + r, ch = cbase + r + H;
+                VM[r + H] = (ch < L) ? base16 + hi16(pa) : NEG_INF;
+                VY[r + H] = (ch < L) ? base16 + hi16(py) - e : NEG_INF;
+                VM[r] = (cl < L) ? base16 + lo16(pa) : NEG_INF;
+                VY[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py) - e) : NEG_INF;
+            }
+        };
+        // the ring keeps 32-bit rows: unpack on the way out
+        auto ring_store16 = [&](uint32_t row) {
+            int VM[C], VY[C];
+            unpack16(VM, VY);
+            store_row<C>(ring_m + (size_t)(row & RM) * STRIDE + cbase, VM);
+            store_row<C>(ring_y + (size_t)(row & RM) * STRIDE + cbase, VY);
+        };
+        // Range guard + re-basing, every PK_GUARD_ROWS packed rows (biased fields compare like the scores). Padding
+        // columns (c >= L) are ignored: they sit at the floor right after a packed gather. Returns true when the read no
+        // longer fits the packed range.
+        auto guard16 = [&](int tmax) -> bool {
+            unsigned mn = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < H; r++) {
+                unsigned yy = (unsigned)B[r];
+                if (r == 0 && lane == 0) yy = (yy & 0xffff0000u) | ((unsigned)A[0] & 0xffffu);  // the first-column cell's y is unused
+                const unsigned v = __vminu2((unsigned)A[r], yy);
+                const unsigned real = ((cbase + r < L) ? 0u : 0xffffu) | ((cbase + r + H < L) ? 0u : 0xffff0000u);
+                mn = __vminu2(mn, __vmaxu2(v, real));
+            }
+            const int lm = __reduce_min_sync(FULL, (int)min(mn & 0xffffu, mn >> 16)) - 32768;
+            const int rel = tmax - base16;
+            if (lm - rel < -PK_SPREAD) return true;
+            if (rel > PK_REBASE || rel < -PK_REBASE) {
+                // |rel| <= PK_REBASE + PK_GUARD_ROWS * 60: no field can leave its half; padding is pulled back to the floor
+                const unsigned dl = add2(-rel), fl = (unsigned)(FLOOR16 + 32768) * 65537u;
+#pragma unroll
+                for (int r = 0; r < H; r++) {
+                    A[r] = (int)__vmaxu2((unsigned)A[r] + dl, fl);
+                    B[r] = (int)__vmaxu2((unsigned)B[r] + dl, fl);
+                }
+                base16 += rel;
+            }
+            return false;
+        };
+
         int4 ri_next = reinterpret_cast<const int4*>(g.rowinfo)[0];
         for (uint32_t i = 0; i + 1 < n; i++) {
+            // ---- steady state: consecutive rows in the packed representation whose band (and whose predecessors' bands)
+            // span the whole read. One compact loop: the row body is straight-line code, everything that only some rows
+            // need (gathering predecessors, slot planes, ring copy, range guard) is a side block. Any other kind of row
+            // (32-bit rows, end-cell candidates, shifted bands, row 0 as predecessor) leaves the loop and goes through
+            // the dispatcher below.
+            if (rep16) {
+                for (; i + 2 < n; i++) {
+#ifdef RG_ROWSTATS
+                    const long long st_t1 = clock64();
+#endif
+                    const int4 rv = ri_next;  // rowinfo[i]
+                    const uint32_t rb = (uint32_t)rv.w;
+                    const uint32_t rfl = (rb >> 8) & 0xffu;
+                    if (rfl & RF_F_PRED) break;
+                    const bool gat = (rfl & (RF_NWP | RF_SINGLE_PREV)) == RF_NWP;
+                    uint32_t ms = prev_bsp + 1, me = prev_bsp + 1;
+                    if (gat) {
+                        if (rv.y < 1 || rv.y <= last_nonfull) break;
+                        const uint32_t pb = (uint32_t)rv.z, np = rb >> 24;
+                        uint32_t pl = 0xffffffffu, pr = 0;
+                        for (uint32_t k = 0; k < np; k++) {
+                            const uint32_t p = g.pred_idx[pb + k];
+                            const uint32_t bs = (p == i - 1) ? prev_bsp : rowmeta[p].bsp;
+                            pl = min(pl, bs);
+                            pr = max(pr, bs);
+                        }
+                        ms = pl + 1;
+                        me = pr + 1;
+                    }
+                    uint32_t lf, rt;
+                    band_for_row(ms, me, rv.x, L, bta, lf, rt);
+                    if (lf != 0 || rt != (uint32_t)L) break;
+                    if (gat && !gather16((uint32_t)rv.z, rb >> 24)) {
+                        rep16 = false;  // A / B are garbage now; the dispatcher's general path gathers from the ring itself
+                        break;
+                    }
+                    ri_next = reinterpret_cast<const int4*>(g.rowinfo)[i + 1];
+                    li = rb & 0xffu;
+                    best_p = rv.y;
+                    row16();
+                    const int tmax = __reduce_max_sync(FULL, bestv);
+                    const unsigned eq = __ballot_sync(FULL, bestv == tmax);
+                    const uint32_t row_bsp = (uint32_t)__shfl_sync(FULL, bcol, 31 - __clz(eq));
+                    store_planes<C>(planes + (size_t)i * PlaneFmt<C>::ROWW + lane * NW, P);
+                    if (lane == 0) {
+                        RowMeta rm;
+                        rm.base = 0;
+                        rm.left = 0;
+                        rm.right = (uint32_t)L;
+                        rm.bsp = row_bsp;
+                        rowmeta[i] = rm;
+                    }
+                    if (gat) {
+                        unsigned SD[SB], SU[SB];
+                        slots16((rb >> 16) & 0xffu, SD, SU);
+                        side_store(i, SD, SU);
+                    }
+                    prev_tmax = tmax;
+                    prev_bsp = row_bsp;
+                    cells += (uint32_t)L;
+                    rows16++;
+#ifdef RG_ROWSTATS
+                    st_cnt[gat ? 1 : 0]++;
+                    st_cyc[gat ? 1 : 0] += clock64() - st_t1;
+#endif
+                    if ((rows16 & (PK_GUARD_ROWS - 1)) == 0 && guard16(tmax)) {
+                        en16 = false;  // this read does not fit 16 bits: stay on the 32-bit paths
+                        if (rfl & RF_IS_PRED) ring_store16(i);
+                        unpack16(A, B);
+                        rep16 = false;
+                        i++;
+                        break;
+                    }
+                    if (rfl & RF_IS_PRED) ring_store16(i);
+                    __syncwarp();
+                }
+                if (i + 1 >= n) break;
+            }
             // packed row info, fetched one row ahead (hides the L1/L2 latency behind the previous row's work)
 #ifdef RG_ROWSTATS
             const long long st_t0 = clock64();
@@ -199,7 +614,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             // a segment start whose only predecessor is row i-1 behaves exactly like a row inside a segment
             const bool nwp = (rf & RF_NWP) && !(rf & RF_SINGLE_PREV);
             const uint32_t pb = (uint32_t)riv.z, pe = pb + (nwp ? (rbits >> 24) : 0u);
-            const int best_p = riv.y;
+            best_p = riv.y;
             uint32_t ms, me;
             if (i == 0) {
                 ms = 0;
@@ -225,11 +640,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                 break;
             }
             cells += right - left;
-            const int li = rbits & 0xffu;
+            li = rbits & 0xffu;
             const unsigned mps = (rbits >> 16) & 0xffu;
-            unsigned code[C];
-            int bestv = NEG_INF;
-            int bcol = 0;
+            unsigned code[C];            // 32-bit producers: one code per cell, converted to planes below
+            unsigned SD[SB], SU[SB];     // predecessor-slot planes (rows that gather predecessors)
+            have_planes = false;
+            bestv = NEG_INF;
+            bcol = 0;
 
             // Fast path (a row inside a segment whose band and whose previous row's band start at column 0): every
             // active cell below the previous row's right edge has its vertical and diagonal source; cells of a band
@@ -244,63 +661,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             // gathered from the ring straight into the packed representation; per cell the slot of the winning
             // predecessor (first in list order wins ties, :266-345) is kept as bit planes over my columns.
             bool g16 = en16 && nwp && i > 0 && left == 0 && right == (uint32_t)L && best_p >= 1 && best_p > last_nonfull;
-            unsigned mm_lo[SB], mm_hi[SB], ym_lo[SB], ym_hi[SB];
             if (g16) {
                 if (!rep16) base16 = prev_tmax;
-                const int lo_ok = base16 - 24000;
-                bool ok = true;
-#pragma unroll
-                for (int bq = 0; bq < SB; bq++) mm_lo[bq] = mm_hi[bq] = ym_lo[bq] = ym_hi[bq] = 0u;
-                for (uint32_t q = 0; q < pe - pb; q++) {
-                    const uint32_t p = g.pred_idx[pb + q];
-                    const int32_t* mp = ring_m + (size_t)(p & RM) * STRIDE + cbase;
-                    const int32_t* yp = ring_y + (size_t)(p & RM) * STRIDE + cbase;
-                    unsigned wm_lo = 0, wm_hi = 0, wy_lo = 0, wy_hi = 0;  // cells where predecessor q wins
-                    auto take = [&](int r, int vml, int vmh, int vyl, int vyh) {
-                        const int cl = cbase + r, ch = cbase + r + H;
-                        const bool rl = cl < L, rh = ch < L;
-                        ok = ok && (!rl || ((unsigned)(vml - lo_ok) <= 30000u && (cl == 0 || (unsigned)(vyl + e - lo_ok) <= 30000u)));
-                        ok = ok && (!rh || ((unsigned)(vmh - lo_ok) <= 30000u && (unsigned)(vyh + e - lo_ok) <= 30000u));
-                        const unsigned nm = pk16(rl ? vml - base16 : FLOOR16, rh ? vmh - base16 : FLOOR16);
-                        const unsigned ny = pk16((rl && cl != 0) ? vyl + e - base16 : FLOOR16, rh ? vyh + e - base16 : FLOOR16);
-                        if (q == 0) {
-                            A[r] = (int)nm;
-                            B[r] = (int)ny;
-                        } else {
-                            bool ph, pl;
-                            A[r] = (int)__vibmax_s16x2((unsigned)A[r], nm, &ph, &pl);  // p = (current >= new): keep
-                            if (!pl) wm_lo |= 1u << r;
-                            if (!ph) wm_hi |= 1u << r;
-                            B[r] = (int)__vibmax_s16x2((unsigned)B[r], ny, &ph, &pl);
-                            if (!pl) wy_lo |= 1u << r;
-                            if (!ph) wy_hi |= 1u << r;
-                        }
-                    };
-                    if constexpr (H >= 4) {
-#pragma unroll
-                        for (int j = 0; j < H; j += 4) {
-                            const int4 mlv = reinterpret_cast<const int4*>(mp)[j / 4], mhv = reinterpret_cast<const int4*>(mp + H)[j / 4];
-                            const int4 ylv = reinterpret_cast<const int4*>(yp)[j / 4], yhv = reinterpret_cast<const int4*>(yp + H)[j / 4];
-                            take(j, mlv.x, mhv.x, ylv.x, yhv.x);
-                            take(j + 1, mlv.y, mhv.y, ylv.y, yhv.y);
-                            take(j + 2, mlv.z, mhv.z, ylv.z, yhv.z);
-                            take(j + 3, mlv.w, mhv.w, ylv.w, yhv.w);
-                        }
-                    } else {  // C == 4: one 128-bit load holds both halves
-                        const int4 mv = reinterpret_cast<const int4*>(mp)[0], yv = reinterpret_cast<const int4*>(yp)[0];
-                        take(0, mv.x, mv.z, yv.x, yv.z);
-                        take(1, mv.y, mv.w, yv.y, yv.w);
-                    }
-#pragma unroll
-                    for (int bq = 0; bq < SB; bq++) {
-                        const bool on = (q >> bq) & 1u;
-                        mm_lo[bq] = on ? (mm_lo[bq] | wm_lo) : (mm_lo[bq] & ~wm_lo);
-                        mm_hi[bq] = on ? (mm_hi[bq] | wm_hi) : (mm_hi[bq] & ~wm_hi);
-                        ym_lo[bq] = on ? (ym_lo[bq] | wy_lo) : (ym_lo[bq] & ~wy_lo);
-                        ym_hi[bq] = on ? (ym_hi[bq] | wy_hi) : (ym_hi[bq] & ~wy_hi);
-                    }
-                }
-                if (__all_sync(FULL, ok)) {
+                if (gather16(pb, pe - pb)) {
                     if (!rep16) rows16 = 0;
                     rep16 = true;
                 } else {
@@ -316,8 +679,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                 for (int k = 0; k < C; k++) {
                     const int c = cbase + k;
                     if (c < L) {
-                        ok = ok && (A[k] - prev_tmax >= -24000) && (A[k] - prev_tmax <= 2000);
-                        if (c != 0) ok = ok && (B[k] + e - prev_tmax >= -24000) && (B[k] + e - prev_tmax <= 2000);
+                        ok = ok && (A[k] - prev_tmax >= PK_ENTER_LO) && (A[k] - prev_tmax <= PK_ENTER_HI);
+                        if (c != 0) ok = ok && (B[k] + e - prev_tmax >= PK_ENTER_LO) && (B[k] + e - prev_tmax <= PK_ENTER_HI);
                     }
                 }
                 if (__all_sync(FULL, ok)) {
@@ -327,8 +690,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                         const int cl = cbase + r, ch = cbase + r + H;
                         const int al = (cl < L) ? A[r] - base16 : FLOOR16, ah = (ch < L) ? A[r + H] - base16 : FLOOR16;
                         const int yl = (cl < L && cl != 0) ? B[r] + e - base16 : FLOOR16, yh = (ch < L) ? B[r + H] + e - base16 : FLOOR16;
-                        A[r] = (int)pk16(al, ah);
-                        B[r] = (int)pk16(yl, yh);
+                        A[r] = (int)pk16b(al, ah);
+                        B[r] = (int)pk16b(yl, yh);
                     }
                     rep16 = true;
                     rows16 = 0;
@@ -338,132 +701,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             }
             if (!f16 && !g16 && rep16 && nwp) rep16 = false;  // segment starts read their predecessors from the ring
             if (!f16 && !g16 && rep16) {
-                // packed -> 32-bit (padding columns are outside the band: NEG_INF; y[i][0] is 0 by definition)
-#pragma unroll
-                for (int r = H - 1; r >= 0; r--) {
-                    const unsigned pa = (unsigned)A[r], py = (unsigned)B[r];
-                    const int cl = cbase + r, ch = cbase + r + H;
-                    A[r + H] = (ch < L) ? base16 + hi16(pa) : NEG_INF;
-                    B[r + H] = (ch < L) ? base16 + hi16(py) - e : NEG_INF;
-                    A[r] = (cl < L) ? base16 + lo16(pa) : NEG_INF;
-                    B[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py) - e) : NEG_INF;
-                }
+                unpack16(A, B);
                 rep16 = false;
             }
-            auto row16 = [&](auto nwp_tag) {
-                constexpr bool NWP = decltype(nwp_tag)::value;
-                const unsigned* tab = subtab + (size_t)li * H * 32 + lane;
-                unsigned D16[H], YV[H], X16[H];
-                unsigned ybl = 0, ybh = 0;
-                // ---- pass A: y and d of both halves of every pair (descending: A[r-1] is still the previous row)
-                const unsigned up = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
-                const unsigned dg0 = __byte_perm(up, (unsigned)A[H - 1], 0x5432);  // lo <- cell cbase-1, hi <- cell H-1
-#pragma unroll
-                for (int r = H - 1; r >= 0; r--) {
-                    const unsigned um2 = __vadd2((unsigned)A[r], C2C2);              // m + o + e
-                    bool ph, pl;
-                    const unsigned yv = __vibmax_s16x2(um2, (unsigned)B[r], &ph, &pl);  // max(m + o, y) + e ; p = (m + o >= y)
-                    if (!pl) ybl |= 1u << r;
-                    if (!ph) ybh |= 1u << r;
-                    const unsigned dd = __vadd2((r == 0) ? dg0 : (unsigned)A[r - 1], tab[r * 32]);
-                    D16[r] = dd;
-                    YV[r] = yv;
-                    A[r] = (int)__vmaxs2(dd, yv);  // h
-                }
-                if (lane == 0) {  // first-column cell (gap_global_abpoa.rs:78-92): m = x only
-                    D16[0] = (D16[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu);
-                    YV[0] = (YV[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu);
-                    A[0] = (int)(((unsigned)A[0] & 0xffff0000u) | ((unsigned)FLOOR16 & 0xffffu));
-                }
-                // slot bit planes of the diagonal source (= the m-winner of the cell to the left) and of the vertical
-                // source (the y-winner where y extends, the m-winner where it opens)
-                unsigned dm_lo[SB], dm_hi[SB], um_lo[SB], um_hi[SB];
-                if constexpr (NWP) {
-#pragma unroll
-                    for (int bq = 0; bq < SB; bq++) {
-                        const unsigned upb = __shfl_up_sync(FULL, mm_hi[bq] >> (H - 1), 1) & 1u;
-                        dm_lo[bq] = (mm_lo[bq] << 1) | upb;
-                        dm_hi[bq] = (mm_hi[bq] << 1) | ((mm_lo[bq] >> (H - 1)) & 1u);
-                        um_lo[bq] = (ybl & ym_lo[bq]) | (~ybl & mm_lo[bq]);
-                        um_hi[bq] = (ybh & ym_hi[bq]) | (~ybh & mm_hi[bq]);
-                    }
-                }
-                // ---- pass B: two in-lane chains (lo cells 0..H-1, hi cells H..C-1); generator of cell c is h[c-1] + c2
-                const unsigned hup = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
-                unsigned g0 = __vadd2(__byte_perm(hup, (unsigned)A[H - 1], 0x5432), C2C2);
-                if (lane == 0) g0 = (g0 & 0xffff0000u) | ((unsigned)(o + e * (best_p + 1) - base16) & 0xffffu);  // seed, :88
-                {
-                    unsigned xl = pk16(FLOOR16, FLOOR16);
-#pragma unroll
-                    for (int r = 0; r < H; r++) {
-                        const unsigned gen = (r == 0) ? g0 : __vadd2((unsigned)A[r - 1], C2C2);
-                        xl = __viaddmax_s16x2(xl, C1C1, gen);
-                        X16[r] = xl;
-                    }
-                }
-                // cross-lane max-plus scan on the in-lane value of my last column
-                const int c1s = e + max(o, 0);
-                const int xlo_end = lo16(X16[H - 1]);
-                const int agg = max(hi16(X16[H - 1]), xlo_end + H * c1s);
-                const int z = agg - (cbase + C - 1) * c1s;
-                const int winc = warp_incl_max(z, lane);
-                int wexc = __shfl_up_sync(FULL, winc, 1);
-                if (lane == 0) wexc = NEG_INF;
-                const int xin = max(wexc + cbase * c1s, FLOOR16);            // x entering my first column
-                const int xf = max(xlo_end, xin + (H - 1) * c1s);            // final x of my column H-1
-                unsigned CP = pk16(xin, max(xf + c1s, FLOOR16));              // carries of the lo / hi chains
-                // ---- pass C
-                unsigned bestp = pk16(-32768, -32768);
-                int idx_lo = 0, idx_hi = 0;
-                bool xn_l = false, xn_h = false;
-#pragma unroll
-                for (int r = 0; r < H; r++) {
-                    const unsigned x = __vmaxs2(X16[r], CP);
-                    CP = __vadd2(CP, C1C1);
-                    bool dh, dl, th, tl;
-                    const unsigned t = __vibmax_s16x2(D16[r], x, &dh, &dl);   // p = (dd >= x)
-                    const unsigned m = __vibmax_s16x2(t, YV[r], &th, &tl);    // p = (max(dd, x) >= y)
-                    unsigned cl = tl ? (dl ? (unsigned)DIR_D : (unsigned)DIR_L) : (unsigned)DIR_U;
-                    unsigned ch = th ? (dh ? (unsigned)DIR_D : (unsigned)DIR_L) : (unsigned)DIR_U;
-                    if ((ybl >> r) & 1u) cl |= 8u;
-                    if ((ybh >> r) & 1u) ch |= 8u;
-                    if (r > 0 && xn_l) cl |= 4u;   // path_x: x[c-1] > m[c-1] + o of the cell to the left
-                    if (r > 0 && xn_h) ch |= 4u;
-                    if constexpr (NWP) {
-#pragma unroll
-                        for (int bq = 0; bq < SB; bq++) {
-                            cl |= (((dm_lo[bq] >> r) & 1u) << (4 + bq)) | (((um_lo[bq] >> r) & 1u) << (4 + SB + bq));
-                            ch |= (((dm_hi[bq] >> r) & 1u) << (4 + bq)) | (((um_hi[bq] >> r) & 1u) << (4 + SB + bq));
-                        }
-                    }
-                    (void)__vibmax_s16x2(x, __vadd2(m, OO1), &xn_h, &xn_l);   // p = (x >= m + o + 1)
-                    bool bh, bl;
-                    bestp = __vibmax_s16x2(m, bestp, &bh, &bl);              // p = (m >= best): right-most maximum
-                    if (bl) idx_lo = r;
-                    if (bh) idx_hi = r;
-                    code[r] = cl;
-                    code[r + H] = ch;
-                    A[r] = (int)m;
-                    B[r] = (int)__vadd2(YV[r], EE);
-                }
-                if (lane == 0) code[0] = DIR_U | ((mps & SMASK) << (4 + SB));
-                {
-                    const unsigned lastbits = (xn_l ? 1u : 0u) | (xn_h ? 2u : 0u);
-                    const unsigned upbits = __shfl_up_sync(FULL, lastbits, 1);
-                    if (lane != 0 && (upbits & 2u)) code[0] |= 4u;  // left neighbour = previous lane's last column
-                    if (lastbits & 1u) code[H] |= 4u;               // left neighbour = my column H-1
-                }
-                {
-                    const int blo = lo16(bestp), bhi = hi16(bestp);
-                    if (bhi >= blo) {
-                        bestv = base16 + bhi;
-                        bcol = cbase + H + idx_hi;
-                    } else {
-                        bestv = base16 + blo;
-                        bcol = cbase + idx_lo;
-                    }
-                }
-            };
             // 32-bit row inside a segment (predecessor = row i-1, held in registers). PLAIN: both bands start at column 0
             // and this one lies inside the previous one, so every active cell has its vertical and diagonal source.
             // Otherwise cells without a vertical source take the y fallback of gap_global_abpoa.rs:110-141, cells
@@ -575,12 +815,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
                 }
             };
             if (g16) {
-                row16(std::true_type{});
+                row16();
+                slots16(mps, SD, SU);
 #ifdef RG_ROWSTATS
                 st_kind = 1;
 #endif
             } else if (f16) {
-                row16(std::false_type{});
+                row16();
 #ifdef RG_ROWSTATS
                 st_kind = 0;
 #endif
@@ -773,75 +1014,28 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             const unsigned eq = __ballot_sync(FULL, bestv == tmax && bestv > NEGH);
             const uint32_t row_bsp = (uint32_t)__shfl_sync(FULL, bcol, 31 - __clz(eq));
             // ---- stores: packed trace codes, ring copy for predecessor rows, row meta
-            store_codes<C, TC>(trace + (size_t)i * STRIDE + cbase, code);
+            if (!have_planes) planes_from_codes<C, SB>(code, P, SD, SU);
+            store_planes<C>(planes + (size_t)i * PlaneFmt<C>::ROWW + lane * NW, P);
+            if (nwp) side_store(i, SD, SU);
             if (rep16) {
                 rows16++;
-                const bool need32 = (rf & RF_F_PRED) || i == n - 2;
-                bool leave = need32;
-                if ((rows16 & 63) == 0) {
-                    // range guard + re-basing: real cells drift by a few units per row, so checking every 64 rows keeps
-                    // every packed lane far from wrapping
-                    // padding columns (c >= L) are ignored: they sit at the floor right after a packed gather
-                    unsigned mn = pk16(32767, 32767);
-#pragma unroll
-                    for (int r = 0; r < H; r++) {
-                        unsigned yy = (unsigned)B[r];
-                        if (r == 0 && lane == 0) yy = (yy & 0xffff0000u) | ((unsigned)A[0] & 0xffffu);  // the first-column cell's y is unused
-                        const unsigned v = __vmins2((unsigned)A[r], yy);
-                        const unsigned real = pk16((cbase + r < L) ? -32768 : 32767, (cbase + r + H < L) ? -32768 : 32767);
-                        mn = __vmins2(mn, __vmaxs2(v, real));
-                    }
-                    const int lm = __reduce_min_sync(FULL, min(lo16(mn), hi16(mn)));
-                    const int rel = tmax - base16;
-                    if (lm - rel < -26000) {
-                        leave = true;
-                        en16 = false;  // this read does not fit 16 bits: stay on the 32-bit paths
-                    } else if (rel > 3000 || rel < -3000) {
-                        // |rel| stays below ~7000 (3000 + 64 rows of drift): no packed lane can wrap here; lanes that would
-                        // sink below the floor (padding) are pulled back to it
-                        const unsigned dl = pk16(-rel, -rel), fl = pk16(FLOOR16, FLOOR16);
-#pragma unroll
-                        for (int r = 0; r < H; r++) {
-                            A[r] = (int)__vmaxs2(__vaddss2((unsigned)A[r], dl), fl);
-                            B[r] = (int)__vmaxs2(__vaddss2((unsigned)B[r], dl), fl);
-                        }
-                        base16 += rel;
-                    }
+                bool leave = (rf & RF_F_PRED) || i == n - 2;   // the end-cell candidates are read from the 32-bit row
+                if ((rows16 & (PK_GUARD_ROWS - 1)) == 0 && guard16(tmax)) {
+                    leave = true;
+                    en16 = false;  // this read does not fit 16 bits: stay on the 32-bit paths
                 }
                 if (leave) {
-#pragma unroll
-                    for (int r = H - 1; r >= 0; r--) {
-                        const unsigned pa = (unsigned)A[r], py = (unsigned)B[r];
-                        const int cl = cbase + r, ch = cbase + r + H;
-                        A[r + H] = (ch < L) ? base16 + hi16(pa) : NEG_INF;
-                        B[r + H] = (ch < L) ? base16 + hi16(py) - e : NEG_INF;
-                        A[r] = (cl < L) ? base16 + lo16(pa) : NEG_INF;
-                        B[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py) - e) : NEG_INF;
-                    }
+                    unpack16(A, B);
                     rep16 = false;
                 }
             }
             if (left != 0 || right != (uint32_t)L) last_nonfull = (int)i;
             if (rf & RF_IS_PRED) {
-                int32_t* mp = ring_m + (size_t)(i & RM) * STRIDE + cbase;
-                int32_t* yp = ring_y + (size_t)(i & RM) * STRIDE + cbase;
                 if (rep16) {
-                    // the ring keeps 32-bit rows (padding columns NEG_INF, y[i][0] = 0): unpack on the way out
-                    int VM[C], VY[C];
-#pragma unroll
-                    for (int r = 0; r < H; r++) {
-                        const unsigned pa = (unsigned)A[r], py = (unsigned)B[r];
-                        const int cl = cbase + r, ch = cbase + r + H;
-                        VM[r] = (cl < L) ? base16 + lo16(pa) : NEG_INF;
-                        VM[r + H] = (ch < L) ? base16 + hi16(pa) : NEG_INF;
-                        VY[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py) - e) : NEG_INF;
-                        VY[r + H] = (ch < L) ? base16 + hi16(py) - e : NEG_INF;
-                    }
-                    store_row<C>(mp, VM);
-                    store_row<C>(yp, VY);
+                    ring_store16(i);
                 } else {
-                    store_row<C>(mp, A);
-                    store_row<C>(yp, B);
+                    store_row<C>(ring_m + (size_t)(i & RM) * STRIDE + cbase, A);
+                    store_row<C>(ring_y + (size_t)(i & RM) * STRIDE + cbase, B);
                 }
             }
             if (lane == 0) {
@@ -901,7 +1095,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
             // ---- traceback (gaf_output.rs:96-253) fused with band_ampl_enough (gap_global_abpoa.rs:371-455)
             RunEmitter em;
             em.init(runs, ws.run_cap);
-            const WalkOut wo = walk_affine<TC, SB, STRIDE>(trace, rowmeta, g, read, L, row, col, em, lane);
+            PlaneTrace<C, SB> tr;
+            tr.planes = planes;
+            tr.side = side;
+            tr.rowflags = g.rowflags;
+            tr.nwp_ord = g.nwp_ord;
+            const WalkOut wo = walk_affine<SB>(tr, rowmeta, g, read, L, row, col, em, lane);
             row = wo.row;
             col = wo.col;
             const int bandchk = wo.bandchk;
@@ -969,19 +1168,19 @@ static int launch_c(const DevGraph& g, const DevScoring& s, const PoaWorkspace& 
                     int blocks, cudaStream_t st) {
     const bool simple = simple_scoring(s);
     const size_t smem = (size_t)WARPS_PER_BLOCK * 5 * (C / 2) * 32 * sizeof(unsigned);
-    const void* k = trace_bytes == 1 ? (simple ? (const void*)k_gap_global_blk<C, uint8_t, 2, true> : (const void*)k_gap_global_blk<C, uint8_t, 2, false>)
-                                     : (simple ? (const void*)k_gap_global_blk<C, uint16_t, 6, true> : (const void*)k_gap_global_blk<C, uint16_t, 6, false>);
+    const void* k = trace_bytes == 1 ? (simple ? (const void*)k_gap_global_blk<C, 2, true> : (const void*)k_gap_global_blk<C, 2, false>)
+                                     : (simple ? (const void*)k_gap_global_blk<C, 6, true> : (const void*)k_gap_global_blk<C, 6, false>);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     if (trace_bytes == 1) {
         if (simple)
-            k_gap_global_blk<C, uint8_t, 2, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, 2, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
         else
-            k_gap_global_blk<C, uint8_t, 2, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, 2, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
     } else {
         if (simple)
-            k_gap_global_blk<C, uint16_t, 6, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, 6, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
         else
-            k_gap_global_blk<C, uint16_t, 6, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, 6, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1000,7 +1199,7 @@ int launch_gap_global_blk(int C, const DevGraph& g, const DevScoring& s, const P
 
 template <int C>
 static int occ_c(int trace_bytes, int* nb) {
-    const void* k = trace_bytes == 1 ? (const void*)k_gap_global_blk<C, uint8_t, 2, true> : (const void*)k_gap_global_blk<C, uint16_t, 6, true>;
+    const void* k = trace_bytes == 1 ? (const void*)k_gap_global_blk<C, 2, true> : (const void*)k_gap_global_blk<C, 6, true>;
     const size_t smem = (size_t)WARPS_PER_BLOCK * 5 * (C / 2) * 32 * sizeof(unsigned);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, WARPS_PER_BLOCK * 32, smem) == cudaSuccess ? 0 : -1;

@@ -1,4 +1,5 @@
-// Warp-cooperative traceback for the affine-gap trace layout (fixed row stride, absolute columns).
+// Warp-cooperative traceback for the affine-gap trace (any layout: TRACE::code(row, column) returns the cell's code
+// dir 2 | x 1 | y 1 | diagonal slot SB | vertical slot SB).
 //
 // Semantics are those of gaf_of_gap_abpoa (gaf_output.rs:96-253) fused with band_ampl_enough
 // (gap_global_abpoa.rs:371-455); the output is the run-length step list of include/recgraph_b200.h.
@@ -20,8 +21,8 @@ struct WalkOut {
     bool panic;
 };
 
-template <typename TC, int SB, int STRIDE>
-__device__ __forceinline__ WalkOut walk_affine(const TC* __restrict__ trace, const RowMeta* __restrict__ rowmeta,
+template <int SB, typename TRACE>
+__device__ __forceinline__ WalkOut walk_affine(const TRACE& trace, const RowMeta* __restrict__ rowmeta,
                                                const DevGraph& g, const uint8_t* __restrict__ read, int32_t L,
                                                uint32_t row, uint32_t col, RunEmitter& em, int lane) {
     constexpr unsigned SMASK = (1u << SB) - 1;
@@ -45,7 +46,7 @@ __device__ __forceinline__ WalkOut walk_affine(const TC* __restrict__ trace, con
         unsigned pslot = PREV_NONE_SLOT;
         bool is_match = false;
         if (valid) {
-            cd = trace[(size_t)rr * STRIDE + (size_t)cc];
+            cd = trace.code(rr, cc);
             mt = rowmeta[rr];
             pslot = g.prev_slot[rr];
             if (mode == WM_D && cc >= 1) is_match = g.lnz[rr] == read[cc - 1];
