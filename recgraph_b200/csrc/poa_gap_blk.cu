@@ -263,6 +263,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
         const unsigned C1F = pk16(e + max(o, 0), e + max(o, 0));  // per-field operand of VIADDMNMX.U16x2
         const unsigned C1A = add2(e + max(o, 0)), C2A = add2(o + e), EEA = add2(e);   // 32-bit addends
         const unsigned KY = BIAS2 - add2(1), KX = BIAS2 - add2(o + 1);
+        // The integer ALU pipe issues one warp instruction every two clocks and so does the multiply-add pipe. The row
+        // body is ALU-bound (maxima, shifts, logic), so the differences behind the flags are written as multiply-adds
+        // with multipliers the compiler cannot fold (ws.use16 is 1 whenever this code runs): they issue as IMAD.
+        const unsigned ONE = ws.use16, NEG1 = 0u - ONE;
         const long long t_start = clock64();
         int A[C], B[C];  // previous row: m and y of my columns (NEG_INF outside its band)
         int status = 0;
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
         // A / B hold the (gathered) predecessor row on entry and this row on exit; leaves P, bestv, bcol.
         auto row16 = [&]() {
             const unsigned* tab = subtab + (size_t)li * H * 32 + lane;
-            unsigned D16[H], YV[H], X16[H];
+            unsigned D16[H], YV[H];
             // flag accumulators: bit r <- lo cell r, bit 16 + r <- hi cell r
             unsigned fy = 0, fd = 0, ft = 0, fx = 0, fb = 0;
             auto flag = [](unsigned& acc, unsigned f, int r) {
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
             for (int r = H - 1; r >= 0; r--) {
                 const unsigned um2 = (unsigned)A[r] + C2A;                    // m + o + e
                 const unsigned yv = __vmaxu2(um2, (unsigned)B[r]);            // max(m + o, y) + e
-                flag(fy, (unsigned)B[r] + KY - um2, r);                       // Y: y > m + o
+                flag(fy, (unsigned)B[r] * ONE + (um2 * NEG1 + KY), r);        // Y: y > m + o   (B + KY - um2)
                 const unsigned dd = ((r == 0) ? dg0 : (unsigned)A[r - 1]) + tab[r * 32];
                 D16[r] = dd;
                 YV[r] = yv;
@@ -314,42 +318,49 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                 YV[0] = (YV[0] & 0xffff0000u) | FLB;
                 A[0] = (int)(((unsigned)A[0] & 0xffff0000u) | FLB);
             }
-            // ---- pass B: two in-lane chains (lo cells 0..H-1, hi cells H..C-1); generator of cell c is h[c-1] + c2
+            // ---- pass B: two in-lane chains (lo cells 0..H-1, hi cells H..C-1); generator of cell c is h[c-1] + c2.
+            // Only the value leaving my last column is needed here (for the cross-lane scan); pass C runs the chain again
+            // from the true incoming value instead of keeping 16 intermediate registers.
             const unsigned hup = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
             unsigned g0 = __byte_perm(hup, (unsigned)A[H - 1], 0x5432) + C2A;
             if (lane == 0) g0 = (g0 & 0xffff0000u) | ((unsigned)(o + e * (best_p + 1) - base16 + 32768) & 0xffffu);  // seed, :88
+            unsigned xe;
             {
                 unsigned xl = FLB | (FLB << 16);
 #pragma unroll
                 for (int r = 0; r < H; r++) {
                     const unsigned gen = (r == 0) ? g0 : (unsigned)A[r - 1] + C2A;
                     xl = __viaddmax_u16x2(xl, C1F, gen);
-                    X16[r] = xl;
                 }
+                xe = xl;
             }
             // cross-lane max-plus scan on the in-lane value of my last column (biased integers)
             const int c1s = e + max(o, 0);
-            const int xlo_end = (int)(X16[H - 1] & 0xffffu);
-            const int agg = max((int)(X16[H - 1] >> 16), xlo_end + H * c1s);
+            const int xlo_end = (int)(xe & 0xffffu);
+            const int agg = max((int)(xe >> 16), xlo_end + H * c1s);
             const int z = agg - (cbase + C - 1) * c1s;
             const int winc = warp_incl_max(z, lane);
             int wexc = __shfl_up_sync(FULL, winc, 1);
             if (lane == 0) wexc = NEG_INF;
             const int xin = max(wexc + cbase * c1s, (int)FLB);            // x entering my first column
             const int xf = max(xlo_end, xin + (H - 1) * c1s);             // final x of my column H-1
-            unsigned CP = (unsigned)xin | ((unsigned)max(xf + c1s, (int)FLB) << 16);  // carries of the lo / hi chains
+            // chain state "one column before my first": the first step adds c1 back
+            unsigned xl = (unsigned)(xin - c1s) | ((unsigned)(max(xf + c1s, (int)FLB) - c1s) << 16);
             // ---- pass C
             unsigned bestp = FLB | (FLB << 16);
+            unsigned hprev = 0;
 #pragma unroll
             for (int r = 0; r < H; r++) {
-                const unsigned x = __vmaxu2(X16[r], CP);
-                CP += C1A;
+                const unsigned gen = (r == 0) ? g0 : hprev + C2A;
+                hprev = (unsigned)A[r];
+                xl = __viaddmax_u16x2(xl, C1F, gen);
+                const unsigned x = xl;
                 const unsigned t = __vmaxu2(D16[r], x);
-                flag(fd, D16[r] + BIAS2 - x, r);        // D: dd >= x
+                flag(fd, D16[r] * ONE + (x * NEG1 + BIAS2), r);      // D: dd >= x
                 const unsigned m = __vmaxu2(t, YV[r]);
-                flag(ft, t + BIAS2 - YV[r], r);         // T: max(dd, x) >= y
-                flag(fx, x + KX - m, r);                // x > m + o
-                flag(fb, m + BIAS2 - bestp, r);         // m >= best so far: right-most maximum
+                flag(ft, t * ONE + (YV[r] * NEG1 + BIAS2), r);       // T: max(dd, x) >= y
+                flag(fx, m * NEG1 + (x * ONE + KX), r);              // x > m + o
+                flag(fb, m * ONE + (bestp * NEG1 + BIAS2), r);       // m >= best so far: right-most maximum
                 bestp = __vmaxu2(m, bestp);
                 A[r] = (int)m;
                 B[r] = (int)(YV[r] + EEA);
