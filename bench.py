@@ -257,9 +257,9 @@ def main():
             "clocks": summarize_clocks(samples),
             "roofline": {"bound": "hbm", "achieved": cells_s * 1.0 / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": cells_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_gap_global_blk<32,u8,2> (csrc/poa_gap_blk.cu)",
-                         "note": "algorithmic bytes = 1 B traceback code per DP cell (SURVEY 8d); the kernel is "
-                                 "INT32-issue bound, see roofline_int32"},
+                         "kernel": "k_gap_global_blk<32,2,true> (csrc/poa_gap_blk.cu)",
+                         "note": "algorithmic bytes = 1 B of traceback per DP cell (SURVEY 8d figure; the kernel stores 4 bit "
+                                 "planes = 0.5 B per cell); the kernel is integer-ALU bound, see roofline_int32"},
             "roofline_int32": {"bound": "int32_alu", "achieved": cells_s * 9 / 1e9, "peak": int_peak_gops,
                                "unit": "Gop/s", "frac": cells_s * 9 / 1e9 / int_peak_gops,
                                "ops_per_cell": 9, "peak_source": "rg_int_peak microbenchmark on this GPU "

@@ -182,7 +182,11 @@ int rg_last_kernel_stats(const rg_ctx* ctx, double* kernel_ms, uint64_t* launche
 /* Replaces GAFStruct::to_string (gaf_output.rs:70-94) and the six gaf_of_* / build_alignment / gaf_output_*
  * builders' string work. Writes what the reference prints to stdout for this read — warning lines included —
  * into buf (NUL-terminated, '\n'-terminated lines). Returns the length needed (excluding NUL); call again with a
- * larger buffer if the return value >= cap. read_codes is this read's codes (needed for nothing but length today). */
+ * larger buffer if the return value >= cap.
+ * amb_mode: 0 for a forward alignment; for the `-s` reverse-strand retries (main.rs:82-101,150-164,198-214,233-249)
+ * 1 = strand '-' and segment ids through the reversed handle map (utils.rs:144-165, amb_mode = true), or an OR of
+ * RG_AMB_HANDLES / RG_AMB_STRAND (mode 3 passes amb_mode = false with the reversed map, main.rs:242). */
+enum { RG_AMB_HANDLES = 2, RG_AMB_STRAND = 4 };
 int64_t rg_format_gaf(rg_ctx* ctx, int mode, const rg_batch_result* res, int32_t read_index, const char* read_name,
                       uint32_t read_len, int amb_mode, char* buf, size_t cap);
 

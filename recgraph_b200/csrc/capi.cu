@@ -504,6 +504,10 @@ static int align_poa(rg_ctx* c, int mode) {
         for (int k = 1; k < 5; k++)
             if (c->scoring.score[k][5] != c->scoring.score[0][5])
                 return c->fail(RG_ERR_UNSUPPORTED, "modes 0/1 need one gap score for all characters (true for every matrix the reference builds)");
+    if (mode == RG_MODE_GLOBAL_SCALAR)
+        for (int k = 0; k < 5; k++)
+            if (c->scoring.score[k][5] != c->scoring.score[0][5] || c->scoring.score[5][k] != c->scoring.score[0][5])
+                return c->fail(RG_ERR_UNSUPPORTED, "scalar mode 0 needs one gap score for all characters (true for every matrix the reference builds)");
     uint32_t wstride = (Lmax + 31) & ~31u;
     int ws_cols = 64, blocks_per_sm = 1;
     // register-blocked kernel (lane-owned column blocks) whenever the longest read fits 32*C columns
@@ -723,6 +727,7 @@ int rg_align_staged(rg_ctx* c, int mode) {
         case RG_MODE_GLOBAL:
         case RG_MODE_LOCAL:
         case RG_MODE_GAP_LOCAL:
+        case RG_MODE_GLOBAL_SCALAR:
         case RG_MODE_GAP_GLOBAL: rc = align_poa(c, mode); break;
         case RG_MODE_PATHWISE_GLOBAL:
         case RG_MODE_PATHWISE_SEMIGLOBAL:
@@ -781,7 +786,7 @@ int64_t rg_format_gaf(rg_ctx* c, int mode, const rg_batch_result* res, int32_t r
                       uint32_t read_len, int amb_mode, char* buf, size_t cap) {
     if (!c || !res || read_index < 0 || read_index >= res->n_reads || !c->has_graph) return RG_ERR_INVALID;
     std::string s;
-    format_gaf(c->fg, mode, res->reads[read_index], res->runs, read_name ? read_name : "", read_len, amb_mode != 0, s);
+    format_gaf(c->fg, mode, res->reads[read_index], res->runs, read_name ? read_name : "", read_len, amb_mode == 1 ? (RG_AMB_STRAND | RG_AMB_HANDLES) : amb_mode, s);
     if (buf && cap) {
         size_t k = std::min(cap - 1, s.size());
         memcpy(buf, s.data(), k);

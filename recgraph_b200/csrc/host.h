@@ -38,6 +38,8 @@ struct FlatGraph {
     std::vector<uint8_t> is_pred_row;    // row is somebody's predecessor through pred_idx
     std::vector<uint64_t> row_seg_id;    // hofp as integers: segment id of each row (0 for rows 0 and n-1)
     std::vector<uint32_t> row_seg;       // dense segment index per row (UINT32_MAX for rows 0, n-1)
+    std::vector<uint64_t> seg_ids;       // id of each dense segment (row order); `-s` retries print them in reverse
+                                         // order (utils.rs:144-165 with amb_mode: handles sorted, reversed)
     std::vector<uint32_t> seg_first_row; // per dense segment
     uint32_t n_segments = 0;
     uint32_t max_indeg = 1;
@@ -79,6 +81,6 @@ std::string f32_display(float v);  // Rust `{}` for f32
 // GAF text for one read from its numeric record + runs (gaf_output.rs / pathwise_alignment_output.rs /
 // recombination_output.rs string work). Appends everything the reference prints to stdout for the read.
 void format_gaf(const FlatGraph& g, int mode, const rg_read_result& r, const rg_run* runs, const char* name,
-                uint32_t read_len, bool amb_mode, std::string& out);
+                uint32_t read_len, int amb_flags, std::string& out);  // amb_flags: RG_AMB_STRAND | RG_AMB_HANDLES
 
 }  // namespace rg

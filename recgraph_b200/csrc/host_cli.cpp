@@ -189,41 +189,104 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
 
     const int mode = a.alignment_mode;
     if (mode < 0 || mode > 9) return panic("Alignment mode must be in [0..9]");
-    if (a.amb_strand == "true") {
-        err += "recgraph_b200: -s true (ambiguous strand, experimental in the reference) is not implemented yet\n";
-        return finish(3);
-    }
-    rg_batch_result res;
-    rc = rg_align_batch(ctx, mode, reads.n_reads, reads.codes, reads.off, &res);
-    if (rc == RG_ERR_REF_PANIC) return panic(rg_last_error(ctx));
-    if (rc != RG_OK) {
-        err += std::string("recgraph_b200: ") + rg_strerror(rc) + ": " + rg_last_error(ctx) + "\n";
-        return finish(3);
-    }
+    const bool amb_strand = a.amb_strand == "true";
+    // One batch through the device + the text of every read, split into the lines the reference println!s while
+    // aligning (warnings) and the GAF record.
+    struct Batch {
+        std::vector<std::string> warn, record;
+        std::vector<int32_t> score;
+    };
     std::vector<char> buf(1 << 16);
+    int fail_code = 0;
+    auto run_batch = [&](int dev_mode, int32_t n, const uint8_t* codes, const uint64_t* off, const std::vector<int32_t>& idx,
+                         int amb_flags, Batch& bt) -> bool {
+        rg_batch_result res;
+        int r = rg_align_batch(ctx, dev_mode, n, codes, off, &res);
+        if (r == RG_ERR_REF_PANIC) {
+            fail_code = panic(rg_last_error(ctx));
+            return false;
+        }
+        if (r != RG_OK) {
+            err += std::string("recgraph_b200: ") + rg_strerror(r) + ": " + rg_last_error(ctx) + "\n";
+            fail_code = finish(3);
+            return false;
+        }
+        bt.warn.resize(n);
+        bt.record.resize(n);
+        bt.score.resize(n);
+        for (int32_t k = 0; k < n; k++) {
+            const int32_t i = idx.empty() ? k : idx[k];
+            if (res.reads[k].status & RG_READ_REF_PANIC) {
+                fail_code = panic("reference panic while aligning read " + std::to_string(i + 1) + " (see DESIGN.md, reference quirks)");
+                return false;
+            }
+            if (res.reads[k].status & RG_READ_TRACE_OVERFLOW) {
+                err += "recgraph_b200: trace buffers overflowed for read " + std::to_string(i + 1) + "\n";
+                fail_code = finish(3);
+                return false;
+            }
+            uint32_t len = (uint32_t)(off[k + 1] - off[k]);
+            int64_t need = rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
+            if (need < 0) {
+                fail_code = finish(3);
+                return false;
+            }
+            if ((size_t)need >= buf.size()) {
+                buf.resize((size_t)need + 1);
+                rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
+            }
+            std::string text(buf.data(), (size_t)need);
+            size_t cut = text.size() > 1 ? text.rfind('\n', text.size() - 2) : std::string::npos;
+            if (cut != std::string::npos) {
+                bt.warn[k] = text.substr(0, cut + 1);
+                text.erase(0, cut + 1);
+            }
+            bt.record[k] = std::move(text);
+            bt.score[k] = res.reads[k].score;
+        }
+        return true;
+    };
+    Batch fwd;
+    if (!run_batch(mode, reads.n_reads, reads.codes, reads.off, {}, 0, fwd)) return fail_code;
+    // ---- -s true: reverse-complement retries (main.rs:82-101 mode 0, 150-164 mode 1, 198-214 mode 2, 233-249 mode 3)
+    Batch rev;
+    std::vector<int32_t> rev_of(reads.n_reads, -1);
+    if (amb_strand && mode <= 3) {
+        std::vector<int32_t> idx;
+        for (int32_t i = 0; i < reads.n_reads; i++)
+            if (mode == 1 || mode == 3 || fwd.score[i] < 0) {  // modes 0 / 2 retry only when the forward score is negative
+                rev_of[i] = (int32_t)idx.size();
+                idx.push_back(i);
+            }
+        if (!idx.empty()) {
+            std::vector<uint8_t> rc;
+            std::vector<uint64_t> roff{0};
+            for (int32_t i : idx) {
+                for (uint64_t k = reads.off[i + 1]; k-- > reads.off[i];) {  // sequences.rs:64-82
+                    uint8_t c = reads.codes[k];
+                    rc.push_back(c < 4 ? (uint8_t)(3 - c) : c);
+                }
+                roff.push_back(rc.size());
+            }
+            // mode 0 retries with the scalar routine (global_abpoa::exec); mode 3 keeps amb_mode = false (main.rs:242)
+            const int rmode = mode == 0 ? RG_MODE_GLOBAL_SCALAR : mode;
+            const int flags = mode == 3 ? RG_AMB_HANDLES : (RG_AMB_HANDLES | RG_AMB_STRAND);
+            if (!run_batch(rmode, (int32_t)idx.size(), rc.data(), roff.data(), idx, flags, rev)) return fail_code;
+        }
+    }
     for (int32_t i = 0; i < reads.n_reads; i++) {
-        if (res.reads[i].status & RG_READ_REF_PANIC)
-            return panic("reference panic while aligning read " + std::to_string(i + 1) + " (see DESIGN.md, reference quirks)");
-        if (res.reads[i].status & RG_READ_TRACE_OVERFLOW) {
-            err += "recgraph_b200: trace buffers overflowed for read " + std::to_string(i + 1) + "\n";
-            return finish(3);
-        }
-        uint32_t len = (uint32_t)(reads.off[i + 1] - reads.off[i]);
-        int64_t need = rg_format_gaf(ctx, mode, &res, i, reads.names[i], len, 0, buf.data(), buf.size());
-        if (need < 0) return finish(3);
-        if ((size_t)need >= buf.size()) {
-            buf.resize((size_t)need + 1);
-            rg_format_gaf(ctx, mode, &res, i, reads.names[i], len, 0, buf.data(), buf.size());
-        }
         size_t number = mode <= 3 ? (size_t)i + 1 : (size_t)i;
-        std::string text(buf.data(), (size_t)need);
         // warning lines are println!'d to stdout by the reference even with -o; only the record goes to the file
-        size_t cut = text.size() > 1 ? text.rfind('\n', text.size() - 2) : std::string::npos;
-        if (a.out_file != "standard output" && cut != std::string::npos) {
-            out += text.substr(0, cut + 1);
-            text.erase(0, cut + 1);
+        out += fwd.warn[i];
+        const std::string* rec = &fwd.record[i];
+        if (rev_of[i] >= 0) {
+            const int32_t k = rev_of[i];
+            out += rev.warn[k];
+            const bool take_rev = mode == 1 ? !(fwd.score[i] < rev.score[k])  // main.rs:160-164 keeps the LOWER score
+                                            : rev.score[k] > fwd.score[i];
+            if (take_rev) rec = &rev.record[k];
         }
-        if (!write_gaf(a, text, number, out)) return panic("unable to create file");
+        if (!write_gaf(a, *rec, number, out)) return panic("unable to create file");
     }
     auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
     err += "Done in " + std::to_string(secs) + ".\n";  // main.rs:322

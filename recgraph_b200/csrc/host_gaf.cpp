@@ -15,6 +15,14 @@ struct Chunk {  // part of a run that lies inside one segment
     uint32_t op, row, len;
 };
 
+// `-s` retries (main.rs:82-101,150-164,198-214,233-249) print segment ids through a handle map built from the handles in
+// REVERSE sorted order (utils.rs:144-165 with amb_mode = true) while the rows stay those of the forward linearisation.
+thread_local bool t_rev_handles = false;
+inline uint64_t sid(const FlatGraph& g, uint32_t row) {
+    if (!t_rev_handles) return g.row_seg_id[row];
+    const uint32_t seg = g.row_seg[row];
+    return seg == UINT32_MAX ? g.row_seg_id[row] : g.seg_ids[g.n_segments - 1 - seg];
+}
 inline uint32_t run_op(const rg_run& r) { return r.op_count >> 28; }
 inline uint32_t run_count(const rg_run& r) { return r.op_count & 0x0fffffffu; }
 inline bool consumes_graph(uint32_t op) { return op != RG_OP_L && op != RG_OP_LPAD; }
@@ -133,7 +141,7 @@ void format_segment_cigar(const FlatGraph& g, const rg_read_result& r, const rg_
         last_dir = dir;
     };
     for_each_chunk(g, runs, r.n_runs, false, [&](const Chunk& c) {
-        uint64_t h = g.row_seg_id[c.row];
+        uint64_t h = sid(g, c.row);
         bool row0 = c.row == 0;  // hofp[0] == "-1": only 'L' steps happen there
         uint64_t hkey = row0 ? UINT64_MAX : h;
         switch (c.op) {
@@ -234,7 +242,7 @@ void flat_parts(const FlatGraph& g, const rg_run* fwd, uint32_t n_fwd, const rg_
         if (consumes_graph(c.op)) {
             uint32_t lo = c.row - c.len + 1;
             for (uint32_t rrow = lo; rrow <= c.row; rrow++) fp.path_sequence += CODE_CHARS[g.lnz[rrow]];
-            uint64_t h = g.row_seg_id[c.row];
+            uint64_t h = sid(g, c.row);
             if (fp.handles.empty() || fp.handles.back() != h) fp.handles.push_back(h);
             fp.graph_steps += c.len;
             fchars += c.len;
@@ -337,8 +345,15 @@ uint64_t node_offset(const FlatGraph& g, uint32_t row) {
 }  // namespace
 
 void format_gaf(const FlatGraph& g, int mode, const rg_read_result& r, const rg_run* all_runs, const char* name,
-                uint32_t read_len, bool amb_mode, std::string& out) {
+                uint32_t read_len, int amb_flags, std::string& out) {
     const rg_run* runs = all_runs + r.run_off;
+    const bool amb_mode = (amb_flags & RG_AMB_STRAND) != 0;
+    struct RevGuard {
+        bool old;
+        explicit RevGuard(bool on) : old(t_rev_handles) { t_rev_handles = on; }
+        ~RevGuard() { t_rev_handles = old; }
+    } rev_guard((amb_flags & RG_AMB_HANDLES) != 0 &&
+                (mode <= RG_MODE_GAP_LOCAL || mode == RG_MODE_GLOBAL_SCALAR || mode == RG_MODE_LOCAL_SCALAR));
     switch (mode) {
         case RG_MODE_GAP_GLOBAL:
         case RG_MODE_GLOBAL_SCALAR:

@@ -285,6 +285,8 @@ int flat_from_lnz(uint32_t n, const uint8_t* lnz_codes, const uint8_t* nwp, cons
         f.row_seg_id[i] = seg_id ? seg_id[i] : (uint64_t)cur + 1;
     }
     f.n_segments = (uint32_t)f.seg_first_row.size();
+    f.seg_ids.resize(f.n_segments);
+    for (uint32_t k = 0; k < f.n_segments; k++) f.seg_ids[k] = f.row_seg_id[f.seg_first_row[k]];
     finish_lnz(f);
     return RG_OK;
 }
@@ -316,6 +318,7 @@ int flatten_graph(const GfaGraph& g, FlatGraph& f, std::string& err) {
     f.row_seg_id.assign(n, 0);
     f.seg_first_row.resize(S);
     f.n_segments = S;
+    f.seg_ids.assign(g.seg_id.begin(), g.seg_id.end());
     std::vector<uint32_t> seg_last(S);
     f.lnz[0] = CODE_START;
     uint32_t row = 1;

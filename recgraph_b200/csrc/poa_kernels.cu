@@ -18,7 +18,10 @@
 
 namespace rg {
 
-template <typename TC, int SB>
+// LIN = true: the scalar linear-gap routine global_abpoa::exec (global_abpoa.rs:260-427; the `-s` retry of mode 0 and
+// the non-AVX2 path). It is the same banded recurrence with o = 0, e = gap score and no y matrix (x[c] then equals
+// m[c-1] + gap), different fall-backs for unavailable sources (:331-366) and get_max_d_u_l's tie order (utils.rs:129-140).
+template <typename TC, int SB, bool LIN>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     k_poa_gap_global(DevGraph g, DevScoring sc, PoaWorkspace ws, PoaBatch b, int WS) {
     // dynamic shared memory: per warp two (m, y) row buffers of WS columns each
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     int32_t* ring_y = ws.ring_y + (size_t)slot * g.ring * ws.wstride;
     TC* trace = reinterpret_cast<TC*>(ws.trace) + (size_t)slot * ws.trace_cap;
     rg_run* runs = ws.runs + (size_t)slot * ws.run_cap;
-    const int o = sc.o, e = sc.e;
+    const int o = LIN ? 0 : sc.o, e = LIN ? sc.sc[0][5] : sc.e;  // LIN: one gap score for every character (checked by the host)
     const int c1 = e + max(o, 0), c2 = o + e;
     constexpr uint32_t SMASK = (1u << SB) - 1;
 
@@ -117,6 +120,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
             int32_t* rg_y = ring_y + (size_t)(i & RM) * ws.wstride;
             const bool prev_in_smem = (prev_right - prev_left) <= (uint32_t)WS;
 
+            int lin_seed0 = 0;  // LIN, left == 0: m[best_p][0] + gap (global_abpoa.rs:318-321; index 0 of the stored row)
+            if (LIN && i > 0 && left == 0) {
+                const int32_t* mp0;
+                if (best_p == i - 1 && prev_in_smem)
+                    mp0 = s_mw + (cur ^ 1) * WS;
+                else
+                    mp0 = ring_m + (size_t)(best_p & RM) * ws.wstride;
+                lin_seed0 = mp0[0] + e;
+            }
             int carry_u = NEG_INF;   // running prefix max of the x scan (in "minus c1*col" space)
             int carry_h = NEG_INF;   // h of the last column of the previous tile
             unsigned carry_xn = 0;   // "next cell comes from x" flag of the previous tile's last column
@@ -171,7 +183,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                                 yp = ring_y + (size_t)(p & RM) * ws.wstride;
                             }
                             if (c >= lp && c < rp) {
-                                int cum = mp[c - lp] + o, cuy = yp[c - lp];
+                                int cum = mp[c - lp] + o, cuy = LIN ? NEG_INF : yp[c - lp];
                                 if (ufirst) {
                                     ufirst = false;
                                     u_m = cum;
@@ -197,8 +209,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                                 }
                             }
                         }
-                        if (ufirst) {  // gap_global_abpoa.rs:132-141
-                            yval = 2 * o + e * (int)(best_p + 1) + e * (int)c;
+                        if (ufirst) {  // gap_global_abpoa.rs:132-141 / global_abpoa.rs:343-346
+                            yval = LIN ? e * (int)(i + c) : 2 * o + e * (int)(best_p + 1) + e * (int)c;
                             uslot = mps;
                         } else if (u_y > u_m) {
                             yval = u_y + e;
@@ -209,6 +221,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                             uslot = u_m_slot;
                         }
                         if (dav) dd += sco;
+                        if (LIN && !dav) {  // global_abpoa.rs:355-358: d = gap * (i + left), predecessor = best_p
+                            dd = e * (int)(i + left);
+                            dslot = mps;
+                            dav = true;
+                        }
                         hval = dav ? max(dd, yval) : yval;
                     }
                     // ---- horizontal (x): max-plus prefix scan  x[c] = max(x[c-1] + c1, h[c-1] + c2)
@@ -218,6 +235,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                         if (c == left) {
                             int seed = (left == 0) ? o + e * (int)(best_p + 1)                           // :88
                                                    : 2 * o + e * (int)(best_p + 1) + e * (int)c;          // :117
+                            if (LIN) seed = (left == 0) ? lin_seed0 : e * (int)(i + c);  // global_abpoa.rs:318-321,334-337
                             A = seed - c1 * (int)c;
                         } else {
                             A = (hprev == NEG_INF ? NEG_INF : hprev + c2) - c1 * (int)c;
@@ -237,6 +255,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                             dir = DIR_U;
                             uslot = mps;
                             yflag = false;
+                        } else if (LIN) {  // get_max_d_u_l(d, u, l), utils.rs:129-140
+                            if (dd < yval) {
+                                if (yval < xval) {
+                                    dir = DIR_L;
+                                    mval = xval;
+                                } else {
+                                    dir = DIR_U;
+                                    mval = yval;
+                                }
+                            } else if (dd < xval) {
+                                dir = DIR_L;
+                                mval = xval;
+                            } else {
+                                dir = DIR_D;
+                                mval = dd;
+                            }
                         } else if (dav) {
                             if (dd < xval) {
                                 if (xval < yval) {
@@ -438,7 +472,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 
 static const void* poa_kernel(int mode, int trace_bytes) {
     if (mode == RG_MODE_GAP_GLOBAL)
-        return trace_bytes == 1 ? (const void*)k_poa_gap_global<uint8_t, 2> : (const void*)k_poa_gap_global<uint16_t, 6>;
+        return trace_bytes == 1 ? (const void*)k_poa_gap_global<uint8_t, 2, false> : (const void*)k_poa_gap_global<uint16_t, 6, false>;
+    if (mode == RG_MODE_GLOBAL_SCALAR)
+        return trace_bytes == 1 ? (const void*)k_poa_gap_global<uint8_t, 2, true> : (const void*)k_poa_gap_global<uint16_t, 6, true>;
     return nullptr;
 }
 
@@ -463,9 +499,16 @@ int launch_poa(int mode, const DevGraph& g, const DevScoring& s, const PoaWorksp
     size_t smem = (size_t)WARPS_PER_BLOCK * 4 * ws_cols * sizeof(int32_t);
     if (mode == RG_MODE_GAP_GLOBAL) {
         if (trace_bytes == 1)
-            k_poa_gap_global<uint8_t, 2><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b, ws_cols);
+            k_poa_gap_global<uint8_t, 2, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b, ws_cols);
         else
-            k_poa_gap_global<uint16_t, 6><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b, ws_cols);
+            k_poa_gap_global<uint16_t, 6, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b, ws_cols);
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    }
+    if (mode == RG_MODE_GLOBAL_SCALAR) {
+        if (trace_bytes == 1)
+            k_poa_gap_global<uint8_t, 2, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b, ws_cols);
+        else
+            k_poa_gap_global<uint16_t, 6, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b, ws_cols);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
     return -2;

@@ -217,3 +217,57 @@ def test_api_rs_entry_points_match_cli():
         g3 = rb.align_local_gap(seqs[k], al, (names[k], k + 1))
         assert g3.to_string() == exp3[k]
         assert g3.path == [int(x) for x in exp3[k].split("\t")[5].split(">") if x]
+
+
+# ---- -s true: reverse-complement retries (main.rs:82-101 mode 0 via the scalar routine, 150-164 mode 1, 198-214 mode 2,
+# 233-249 mode 3), reversed handle map and strand in the GAF record
+@pytest.fixture(scope="module")
+def strand_files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("strand")
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    out = {}
+    for name, (bp, paths, nreads, rlen, err, seed) in {"mix": (1500, 5, 20, 180, 0.04, 41), "mix_long": (5000, 6, 12, 600, 0.05, 42)}.items():
+        g = synth.make_graph(bp, paths, seed=seed)
+        reads = synth.make_reads(g, nreads, rlen, err=err, seed=seed + 100)
+        reads = [r if k % 2 == 0 else "".join(comp[c] for c in reversed(r)) for k, r in enumerate(reads)]
+        gfa, fa = d / f"{name}.gfa", d / f"{name}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        out[name] = (str(fa), str(gfa))
+    return out
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("name", ["mix", "mix_long"])
+@pytest.mark.parametrize("extra", [[], ["-b", "40", "-f", "0.1"]])
+def test_amb_strand_synthetic(strand_files, mode, name, extra):
+    fa, gfa = strand_files[name]
+    _assert_same(["-m", str(mode), "-s", "true"] + extra + [fa, gfa])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_amb_strand_example(mode):
+    _assert_same(["-m", str(mode), "-s", "true", "-b", "50", os.path.join(EXAMPLE, "reads.fa"), os.path.join(EXAMPLE, "graph.gfa")])
+
+
+def test_scalar_mode0_reference_unit_vectors():
+    """The reference's inline tests of the scalar routine (global_abpoa.rs:577-754) through RG_MODE_GLOBAL_SCALAR."""
+    from recgraph_b200 import Aligner
+    from tests.test_oracle_golden import POA_CASES
+    al = Aligner()
+    idx = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 4, "-": 5}
+    n = 0
+    for variant, (lnz, nwp, preds), read, scores, o, e, bta, expected, cite in POA_CASES:
+        if variant != 0:
+            continue
+        table = [[-1] * 6 for _ in range(6)]  # one gap score for all characters (the vectors only define A / C)
+        for (a, b), v in scores.items():
+            table[idx[a]][idx[b]] = v
+        table[5][5] = 0
+        al.set_lnz_graph(lnz, nwp, preds)
+        al.set_scoring(table=table, fixed_bta=bta)
+        recs, _ = al.align(10, [read[1:]])
+        assert recs[0].status & 4 == 0, cite
+        assert recs[0].score == expected, cite
+        n += 1
+    assert n == 4
