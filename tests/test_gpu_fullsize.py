@@ -78,3 +78,36 @@ def test_c2_sample_against_oracle_pred32(c2):
                            capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr
         assert out == r.stdout
+
+
+def _cli_vs_oracle(mode, g, reads, extra=(), timeout=1500):
+    from recgraph_b200 import run_cli
+    from tests import oracle_lib
+    with tempfile.TemporaryDirectory() as d:
+        gfa, fa = os.path.join(d, "g.gfa"), os.path.join(d, "r.fa")
+        open(gfa, "w").write(g.gfa())
+        open(fa, "w").write(synth.fasta(reads))
+        args = ["-m", str(mode)] + list(extra) + [fa, gfa]
+        rc, out, err = run_cli(args)
+        assert rc == 0, err
+        oracle_lib.build()
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_build", "recgraph_oracle")] + args, capture_output=True,
+                           text=True, timeout=timeout)
+        assert r.returncode == 0, r.stderr
+        assert out == r.stdout
+
+
+def test_c3_mode5_sample_against_oracle():
+    """BASELINE config 3 at full size: -m 5, 32 haplotype paths, 10 kbp graph, 2 kbp reads (a sample of the 10k reads;
+    the oracle needs ~3 GB and tens of seconds per read for its n x L x P tensor)."""
+    g = synth.make_graph(10000, 32, seed=1)
+    reads = synth.make_reads(g, 2, 2000, err=0.05, seed=3)
+    _cli_vs_oracle(5, g, reads)
+
+
+def test_c4_mode9_sample_against_oracle():
+    """BASELINE config 4 at full size: -m 9 (R=4, r=0.1, B=1), 64 paths, 5 kbp graph, 1 kbp reads copied from
+    2-breakpoint path mosaics with 2 % errors (one read: best_alignment is O(n^2 L) on the CPU)."""
+    g = synth.make_graph(5000, 64, seed=1)
+    reads = synth.make_reads(g, 1, 1000, err=0.02, seed=3, mosaic_breaks=2)
+    _cli_vs_oracle(9, g, reads, extra=["-R", "4", "-r", "0.1", "-B", "1"])
