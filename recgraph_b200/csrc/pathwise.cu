@@ -47,15 +47,18 @@ __device__ __forceinline__ int block_excl_max(int z, int tid, int* s_w) {
 struct PwSmem {
     unsigned char* mv;  // [max_groups][Lp]
     int32_t* du;        // [Lp]
+    int32_t* sj;        // [Lp] substitution score of the current row against every read column
     int32_t* res;       // [Pp]
     uint32_t* end;      // [Pp]
+    long long* cb;      // [Lp] modes 8/9: per column max of (score << 8 | path) over all path slots
+    long long* rowbest; // [1]  best last-column (score << 8 | 255 - path) among the member paths of the row
     int* w;             // [PT/32]
 };
 
 struct PwDir {  // buffers of one DP direction for the read in flight
-    int32_t* S;
+    int32_t* S;        // ring of rows, [row & RM][path][column]
     int32_t* lead;
-    uint32_t* trace;
+    uint32_t* trace;   // [row][path][column / 32] x {plane 0, plane 1}
     int2* colbest;     // modes 8/9: per (row, column): {max over all slots, path | member << 31}
     int32_t* lastcol;  // forward: [row][Pp] scores of the last column
 };
@@ -67,17 +70,19 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
                       bool track_results, int g_gr, int g_rd, int* s_best_val, int* s_best_set, uint32_t* s_best_row,
                       uint32_t* s_best_path) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = PT / 32;
     const uint32_t n = g.n, P = g.P, PW = g.PW, RM = g.ring - 1;
+    const uint32_t LT = Lp / 32;  // column tiles of 32
+    const size_t rowsz = (size_t)Pp * Lp;
     const uint32_t base_row = rev ? n - 1 : 0;
+    const long long KEY_MIN = -(1ll << 62);
     auto rcode = [&](int jj) -> unsigned { return rev ? read[L - 1 - jj] : read[jj - 1]; };
     // ---- base row: every path carries the accumulated read gaps (pathwise_alignment_semiglobal.rs:26-32,
     //      pathwise_alignment_recombination.rs:148-155)
     {
-        int32_t* Sb = d.S + (size_t)(base_row & RM) * Lp * Pp;
-        for (uint32_t idx = tid; idx < (uint32_t)L * Pp; idx += PT) {
-            const uint32_t j = idx / Pp, q = idx % Pp;
-            Sb[(size_t)j * Pp + q] = (q < P) ? (int)j * g_rd : 0;
-        }
+        int32_t* Sb = d.S + (size_t)(base_row & RM) * rowsz;
+        for (uint32_t q = warp; q < Pp; q += NWARP)
+            for (int j = lane; j < L; j += 32) Sb[(size_t)q * Lp + j] = (q < P) ? j * g_rd : 0;
         int32_t* lb = d.lead + (size_t)(base_row & RM) * Lp;
         for (int j = tid; j < L; j += PT) lb[j] = j * g_rd;
         if (d.lastcol && !rev)
@@ -85,7 +90,7 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
     }
     __syncthreads();
     const int Cc = (L - 1 + PT - 1) / PT;
-    const int chunk = (L + PT / 32 - 1) / (PT / 32);
+    const int ntile = (L + 31) / 32;
 
     for (uint32_t t = 1; t + 1 < n; t++) {
         const uint32_t i = rev ? n - 1 - t : t;
@@ -93,21 +98,36 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
         const int li = g.lnz[i];
         const int32_t* srow = s_sc + li * 8;
         const uint32_t alpha_i = g.alphas[i];
-        int32_t* Si = d.S + (size_t)(i & RM) * Lp * Pp;
+        int32_t* Si = d.S + (size_t)(i & RM) * rowsz;
         int32_t* lead_i = d.lead + (size_t)(i & RM) * Lp;
+        // ================= phase 0: per-column data shared by every path of the row =================
+        for (int j = tid; j < L; j += PT) sm.sj[j] = (j >= 1) ? srow[rcode(j)] : 0;
+        if (d.colbest) {
+            // slots of paths that do not go through the row hold 0 (as in the reference): start every column's
+            // (score, path) maximum from the highest such slot
+            long long init = KEY_MIN;
+            for (uint32_t q = 0; q < P; q++)
+                if (!((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u)) init = (long long)q;  // (0 << 8) | q
+            for (int j = tid; j < L; j += PT) sm.cb[j] = init;
+        }
+        if (d.lastcol && !rev)
+            for (uint32_t q = tid; q < Pp; q += PT) d.lastcol[(size_t)i * Pp + q] = 0;
+        if (tid == 0) *sm.rowbest = KEY_MIN;
+        __syncthreads();
         // ================= phase 1: the leader's DP of every group =================
         for (uint32_t gi = g0; gi < g1; gi++) {
             const PwGroup gr = g.grp[gi];
             unsigned char* mv = sm.mv + (size_t)(gi - g0) * Lp;
             const int32_t* lp = gr.lead_is_alpha_of_pred ? d.lead + (size_t)(gr.pred & RM) * Lp : nullptr;
-            const int32_t* Sp = d.S + (size_t)(gr.pred & RM) * Lp * Pp + gr.leader;
-            const int m0 = free_border ? 0 : (lp ? lp[0] : Sp[0]) + g_gr;
+            const int32_t* Sp = d.S + (size_t)(gr.pred & RM) * rowsz + (size_t)gr.leader * Lp;
+            const int32_t* src = lp ? lp : Sp;
+            const int m0 = free_border ? 0 : src[0] + g_gr;
             const int jb = 1 + tid * Cc, je = min(L, jb + Cc);
             int v = NEG_INF;
-            int pl = (jb < L) ? (lp ? lp[jb - 1] : Sp[(size_t)(jb - 1) * Pp]) : 0;
+            int pl = (jb < L) ? src[jb - 1] : 0;
             for (int j = jb; j < je; j++) {
-                const int pc = lp ? lp[j] : Sp[(size_t)j * Pp];
-                const int dd = pl + srow[rcode(j)];
+                const int pc = src[j];
+                const int dd = pl + sm.sj[j];
                 const int u = pc + g_gr;
                 const int du = max(dd, u);
                 sm.du[j] = du;
@@ -136,141 +156,120 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
         }
         __syncthreads();
         // ================= phase 2: members apply their leader's move =================
-        {
-            const int jb = warp * chunk, je = min(L, jb + chunk);
-            // per pass (32 paths) state
-            int gq[TPW];
-            const int32_t* Spq[TPW];
-            bool quirk[TPW];
-            int col0[TPW], prev_new[TPW], sp_prev[TPW];
+        // One warp per path, lanes over 32 consecutive columns. A run of L moves starts at the last column whose move
+        // is D or U (or at column 0): its value there comes from the predecessor row, so every cell of the row is
+        // independent of its left neighbour and the whole tile is computed at once.
+        for (uint32_t q = warp; q < P; q += NWARP) {
+            int gq = -1;
+            uint32_t pq = 0;
+            for (uint32_t gi = g0; gi < g1; gi++)
+                if ((g.grp_mask[(size_t)gi * PW + q / 32] >> (q % 32)) & 1u) {
+                    gq = (int)(gi - g0);
+                    pq = g.grp[gi].pred;
+                }
+            if (gq < 0) continue;
+            const int32_t* Spq = d.S + (size_t)(pq & RM) * rowsz + (size_t)q * Lp;
+            int32_t* Siq = Si + (size_t)q * Lp;
+            const unsigned char* mvq = sm.mv + (size_t)gq * Lp;
+            uint2* trq = reinterpret_cast<uint2*>(d.trace) + ((size_t)i * Pp + q) * LT;
+            // reverse pass: the 'F' row is never made absolute by the reference (absolute_scores stops before it,
+            // pathwise_alignment_recombination.rs:748), so its traceback sees 0 for every path but path 0
+            const bool quirk = rev && pq == n - 1 && q != 0;
+            const int col0 = free_border ? 0 : Spq[0] + g_gr;
+            int carry_rs = 0, carry_nv = 0, carry_sp = 0, carry_base = col0;
+            // the predecessor row is read PF tiles ahead (double-buffered): a tile is one dependent load otherwise
+            constexpr int PF = 4;
+            int spn[PF];
 #pragma unroll
-            for (int ps = 0; ps < TPW; ps++) {
-                gq[ps] = -1;
-                Spq[ps] = d.S;
-                quirk[ps] = false;
-                col0[ps] = prev_new[ps] = sp_prev[ps] = 0;
-                const uint32_t q = ps * 32 + lane;
-                uint32_t pq = 0;
-                if (q < P)
-                    for (uint32_t gi = g0; gi < g1; gi++)
-                        if ((g.grp_mask[(size_t)gi * PW + ps] >> lane) & 1u) {
-                            gq[ps] = (int)(gi - g0);
-                            pq = g.grp[gi].pred;
-                        }
-                if (gq[ps] < 0) continue;
-                Spq[ps] = d.S + (size_t)(pq & RM) * Lp * Pp + q;
-                // reverse pass: the 'F' row is never made absolute by the reference (absolute_scores stops before it,
-                // pathwise_alignment_recombination.rs:748), so its traceback sees 0 for every path but path 0
-                quirk[ps] = rev && pq == n - 1 && q != 0;
-                col0[ps] = free_border ? 0 : Spq[ps][0] + g_gr;
-                if (jb > 0 && jb < je) {
-                    const unsigned char* mv = sm.mv + (size_t)gq[ps] * Lp;
-                    int j0 = jb - 1;
-                    while (j0 >= 1 && mv[j0] == MV_L) j0--;
-                    int base;
-                    if (j0 == 0)
-                        base = col0[ps];
-                    else if (mv[j0] == MV_D)
-                        base = Spq[ps][(size_t)(j0 - 1) * Pp] + srow[rcode(j0)];
-                    else
-                        base = Spq[ps][(size_t)j0 * Pp] + g_gr;
-                    prev_new[ps] = base + (jb - 1 - j0) * g_rd;
-                    sp_prev[ps] = Spq[ps][(size_t)(jb - 1) * Pp];
+            for (int u = 0; u < PF; u++) spn[u] = (u * 32 + lane < L) ? Spq[u * 32 + lane] : 0;
+            for (int tile0 = 0; tile0 < ntile; tile0 += PF) {
+                int spv[PF];
+#pragma unroll
+                for (int u = 0; u < PF; u++) {
+                    spv[u] = spn[u];
+                    const int jn = (tile0 + PF + u) * 32 + lane;
+                    spn[u] = (jn < L) ? Spq[jn] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < PF; u++) {
+                const int tile = tile0 + u;  // tiles past the read's end do nothing (act is false for all lanes)
+                const int j = tile * 32 + lane;
+                const bool act = j < L;
+                const int sp = spv[u];
+                int spm1 = __shfl_up_sync(FULL, sp, 1);
+                if (lane == 0) spm1 = carry_sp;
+                const unsigned m = (act && j >= 1) ? mvq[j] : (unsigned)MV_D;
+                const int sj = act ? sm.sj[j] : 0;
+                const bool isL = m == MV_L;
+                const unsigned mask = __ballot_sync(FULL, !isL);
+                // value of a cell whose move is D or U (column 0: the border value); cells of an L run take the value
+                // at the run's start (a D / U cell of this tile or of an earlier one) plus the gaps since then
+                int nv = (j == 0) ? col0 : ((m == MV_D) ? spm1 + sj : sp + g_gr);
+                const unsigned below = mask & (0xffffffffu >> (31 - lane));
+                const int srcl = below ? 31 - __clz(below) : 0;
+                const int bv = __shfl_sync(FULL, nv, srcl);
+                if (isL) {
+                    const int rs = below ? tile * 32 + srcl : carry_rs;
+                    nv = (below ? bv : carry_base) + (j - rs) * g_rd;
+                }
+                {
+                    const int top = mask ? 31 - __clz(mask) : 0;
+                    const int tv = __shfl_sync(FULL, nv, top);
+                    if (mask) {
+                        carry_rs = tile * 32 + top;
+                        carry_base = tv;
+                    }
+                }
+                int nvm1 = __shfl_up_sync(FULL, nv, 1);
+                if (lane == 0) nvm1 = carry_nv;
+                unsigned code = 0;
+                if (act && j >= 1) {
+                    // own arg-max in build_alignment's order: d, then u, else l
+                    const int lq = nvm1 + g_rd;
+                    const int dq = (quirk ? 0 : spm1) + sj, uq = (quirk ? 0 : sp) + g_gr;
+                    const int bq = max(dq, max(uq, lq));
+                    code = (bq == dq) ? MV_D : ((bq == uq) ? MV_U : MV_L);
+                }
+                if (act) Siq[j] = nv;
+                const unsigned p0 = __ballot_sync(FULL, code & 1u), p1 = __ballot_sync(FULL, code & 2u);
+                if (lane == 0 && tile < ntile) trq[tile] = make_uint2(p0, p1);
+                carry_nv = __shfl_sync(FULL, nv, 31);
+                carry_sp = __shfl_sync(FULL, sp, 31);
+                // max of (score, path) over ALL slots; the highest path id wins ties (…_recombination.rs:809-830)
+                if (d.colbest && act) atomicMax(&sm.cb[j], ((long long)nv << 8) | (long long)q);
+                if (act && j == L - 1 && !rev) {
+                    if (d.lastcol) d.lastcol[(size_t)i * Pp + q] = nv;
+                    // first strict maximum in path order among the member paths
+                    atomicMax(sm.rowbest, ((long long)nv << 8) | (long long)(255 - q));
+                    if (track_results)
+                        for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
+                            if (g.grp[fg].pred == i && ((g.grp_mask[(size_t)fg * PW + q / 32] >> (q % 32)) & 1u)) {
+                                sm.res[q] = nv;   // pathwise_alignment.rs:305-319
+                                sm.end[q] = i;
+                            }
+                }
                 }
             }
-            int row_best = NEG_INF;
-            uint32_t row_path = 0;
-            // The column loop is a chain of dependent-looking global loads (scores of the predecessor row); fetch
-            // them U columns ahead so that their L2 latency overlaps (the stores below would otherwise serialise them).
-            constexpr int U = 8;
-            int spv[TPW][U], spn[TPW][U];
-#pragma unroll
-            for (int ps = 0; ps < TPW; ps++)
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    spn[ps][u] = (gq[ps] >= 0 && jb + u < je) ? Spq[ps][(size_t)(jb + u) * Pp] : 0;
-            for (int j0 = jb; j0 < je; j0 += U) {
-                // double buffer: the next batch's loads are in flight while this batch is computed
-#pragma unroll
-                for (int ps = 0; ps < TPW; ps++)
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        spv[ps][u] = spn[ps][u];
-                        spn[ps][u] = (gq[ps] >= 0 && j0 + U + u < je) ? Spq[ps][(size_t)(j0 + U + u) * Pp] : 0;
-                    }
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                const int j = j0 + u;
-                if (j >= je) break;
-                const int sj = (j >= 1) ? srow[rcode(j)] : 0;
-                int cb_val = NEG_INF;
-                uint32_t cb_path = 0;
-#pragma unroll
-                for (int ps = 0; ps < TPW; ps++) {
-                        const uint32_t q = ps * 32 + lane;
-                    const bool member = gq[ps] >= 0;
-                    int nv = 0;
-                    unsigned code = 0;
-                    if (member) {
-                        const int sp = spv[ps][u];
-                        if (j == 0) {
-                            nv = col0[ps];
-                        } else {
-                            const unsigned m = sm.mv[(size_t)gq[ps] * Lp + j];
-                            const int lq = prev_new[ps] + g_rd;
-                            nv = (m == MV_D) ? sp_prev[ps] + sj : ((m == MV_U) ? sp + g_gr : lq);
-                            // own arg-max in build_alignment's order: d, then u, else l
-                            const int dq = (quirk[ps] ? 0 : sp_prev[ps]) + sj, uq = (quirk[ps] ? 0 : sp) + g_gr;
-                            const int bq = max(dq, max(uq, lq));
-                            code = (bq == dq) ? MV_D : ((bq == uq) ? MV_U : MV_L);
-                        }
-                        sp_prev[ps] = sp;
-                        prev_new[ps] = nv;
-                    }
-                    Si[(size_t)j * Pp + q] = nv;
-                    const unsigned p0 = __ballot_sync(FULL, code & 1u), p1 = __ballot_sync(FULL, code & 2u);
-                    if (lane == 0) reinterpret_cast<uint2*>(d.trace)[((size_t)i * Lp + j) * PW + ps] = make_uint2(p0, p1);
-                    if (d.colbest) {
-                        // max of (score, path) over ALL slots; the highest path id wins ties (…_recombination.rs:809-830)
-                        const int val = (q < P) ? nv : NEG_INF;
-                        const int mx = __reduce_max_sync(FULL, val);
-                        if (mx >= cb_val) {
-                            const unsigned eq = __ballot_sync(FULL, val == mx);
-                            cb_val = mx;
-                            cb_path = ps * 32 + (31 - __clz(eq));
-                        }
-                    }
-                    if (j == L - 1 && !rev) {
-                        if (d.lastcol) d.lastcol[(size_t)i * Pp + q] = nv;
-                        const int cand = member ? nv : NEG_INF;
-                        const int mx = __reduce_max_sync(FULL, cand);
-                        const unsigned eq = __ballot_sync(FULL, member && cand == mx);
-                        if (eq && mx > row_best) {  // first strict maximum in path order
-                            row_best = mx;
-                            row_path = ps * 32 + (__ffs(eq) - 1);
-                        }
-                        if (track_results && member)
-                            for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
-                                if (g.grp[fg].pred == i && ((g.grp_mask[(size_t)fg * PW + ps] >> lane) & 1u)) {
-                                    sm.res[q] = nv;   // pathwise_alignment.rs:305-319
-                                    sm.end[q] = i;
-                                }
-                    }
-                }
-                if (d.colbest && lane == 0) {
-                    const bool memb = (g.node_bits[(size_t)i * PW + cb_path / 32] >> (cb_path % 32)) & 1u;
-                    d.colbest[(size_t)i * Lp + j] = make_int2(cb_val, (int)(cb_path | (memb ? 0x80000000u : 0u)));
-                }
+        }
+        __syncthreads();
+        // ================= phase 3: per-row results =================
+        if (d.colbest)
+            for (int j = tid; j < L; j += PT) {
+                const long long key = sm.cb[j];
+                const uint32_t cb_path = (uint32_t)(key & 0xff);
+                const int cb_val = (int)(key >> 8);
+                const bool memb = (g.node_bits[(size_t)i * PW + cb_path / 32] >> (cb_path % 32)) & 1u;
+                d.colbest[(size_t)i * Lp + j] = make_int2(cb_val, (int)(cb_path | (memb ? 0x80000000u : 0u)));
             }
-            }
-            if (track_best && je == L && jb < je && lane == 0 && row_best > NEG_INF / 2) {
-                // …_semiglobal.rs:269-273: a row replaces the incumbent only if strictly better
-                if (!*s_best_set || row_best > *s_best_val) {
-                    *s_best_set = 1;
-                    *s_best_val = row_best;
-                    *s_best_row = i;
-                    *s_best_path = row_path;
-                }
+        if (track_best && tid == 0 && *sm.rowbest != KEY_MIN) {
+            // …_semiglobal.rs:269-273: a row replaces the incumbent only if strictly better
+            const long long key = *sm.rowbest;
+            const int row_best = (int)(key >> 8);
+            if (!*s_best_set || row_best > *s_best_val) {
+                *s_best_set = 1;
+                *s_best_val = row_best;
+                *s_best_row = i;
+                *s_best_path = 255u - (uint32_t)(key & 0xff);
             }
         }
         __syncthreads();
@@ -279,8 +278,8 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
 
 // own-argmax code of path q at (row, col) in one direction's trace
 __device__ __forceinline__ unsigned pw_code(const uint32_t* trace, uint32_t Lp, uint32_t PW, uint32_t row, int col, uint32_t q) {
-    const uint2 pl = reinterpret_cast<const uint2*>(trace)[((size_t)row * Lp + col) * PW + q / 32];
-    return ((pl.x >> (q % 32)) & 1u) | (((pl.y >> (q % 32)) & 1u) << 1);
+    const uint2 pl = reinterpret_cast<const uint2*>(trace)[((size_t)row * (PW * 32) + q) * (Lp / 32) + (uint32_t)col / 32];
+    return ((pl.x >> (col % 32)) & 1u) | (((pl.y >> (col % 32)) & 1u) << 1);
 }
 __device__ __forceinline__ uint32_t pw_pred(const DevPathGraph& g, uint32_t row, uint32_t q, uint32_t dflt) {
     uint32_t pred = dflt;
@@ -356,6 +355,7 @@ __global__ void __launch_bounds__(PT, 2) k_pathwise(DevPathGraph g, DevPathGraph
     __shared__ int s_red_i[PT / 32];
     __shared__ RecBest s_rb;
     __shared__ int s_nsurv;
+    __shared__ long long s_rowbest;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t slot = blockIdx.x;
     if (tid < 48) s_sc[tid] = (&sc.sc[0][0])[tid];
@@ -363,10 +363,17 @@ __global__ void __launch_bounds__(PT, 2) k_pathwise(DevPathGraph g, DevPathGraph
     const uint32_t mg = max(g.max_groups, rg_.max_groups);
     PwSmem sm;
     sm.mv = s_dyn;
-    sm.du = reinterpret_cast<int32_t*>(s_dyn + (((size_t)mg * Lp + 15) & ~(size_t)15));
-    sm.res = sm.du + Lp;
-    sm.end = reinterpret_cast<uint32_t*>(sm.res + Pp);
+    {
+        size_t off = (((size_t)mg * Lp + 15) & ~(size_t)15);
+        sm.cb = reinterpret_cast<long long*>(s_dyn + off);       // 8-byte aligned (off is a multiple of 16)
+        off += (size_t)Lp * 8;
+        sm.du = reinterpret_cast<int32_t*>(s_dyn + off);
+        sm.sj = sm.du + Lp;
+        sm.res = sm.sj + Lp;
+        sm.end = reinterpret_cast<uint32_t*>(sm.res + Pp);
+    }
     sm.w = s_w;
+    sm.rowbest = &s_rowbest;
     uint32_t* s_surv = sm.end + Pp;  // [REC_SURV] survivors of one column (modes 8/9)
     const bool rec_mode = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
     const bool global_mode = mode == RG_MODE_PATHWISE_GLOBAL || mode == RG_MODE_REC_GLOBAL;
@@ -766,7 +773,7 @@ __global__ void __launch_bounds__(PT, 2) k_pathwise(DevPathGraph g, DevPathGraph
 
 size_t pathwise_smem_bytes(const DevPathGraph& g, const DevPathGraph& rg_, const PwWorkspace& ws, bool rec) {
     const uint32_t mg = rec ? (g.max_groups > rg_.max_groups ? g.max_groups : rg_.max_groups) : g.max_groups;
-    return (((size_t)mg * ws.Lp + 15) & ~(size_t)15) + (size_t)ws.Lp * 4 + (size_t)ws.Pp * 8 + (rec ? REC_SURV * 4 : 0);
+    return (((size_t)mg * ws.Lp + 15) & ~(size_t)15) + (size_t)ws.Lp * 16 + (size_t)ws.Pp * 8 + (rec ? REC_SURV * 4 : 0);
 }
 
 static const void* pw_kernel(uint32_t PW) {
