@@ -271,3 +271,16 @@ def test_scalar_mode0_reference_unit_vectors():
         assert recs[0].score == expected, cite
         n += 1
     assert n == 4
+
+
+# Packed 16-bit rows of the mode-2 kernel under scores at the edge of their domain (|score| <= 30): fast drift of the row
+# maximum (re-basing), wide score spread (the range guard leaves the packed form), cheap gaps (long L / U runs).
+@pytest.mark.parametrize("name", ["small", "mid"])
+@pytest.mark.parametrize("extra", [["-M", "30", "-X", "30", "-O", "30", "-E", "30", "-b", "3000"],
+                                   ["-M", "10", "-X", "20", "-O", "25", "-E", "5", "-b", "3000"],
+                                   ["-M", "30", "-X", "1", "-O", "1", "-E", "1", "-b", "3000"],
+                                   ["-M", "1", "-X", "30", "-O", "0", "-E", "1", "-b", "3000"],
+                                   ["-M", "31", "-X", "4", "-O", "4", "-E", "2", "-b", "3000"]])
+def test_mode2_packed_rows_score_extremes(synth_files, name, extra):
+    fa, gfa = synth_files[name]
+    _assert_same(["-m", "2"] + extra + [fa, gfa])

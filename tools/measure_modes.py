@@ -38,3 +38,19 @@ for name, mode, bp, paths, nreads, rlen, err, mosaic, sc in [
                  "gcups_row_col": dirs * rows_cols / (best * 1e-3) / 1e9,
                  "path_cells_per_s_upper": dirs * rows_cols * P / (best * 1e-3), "rows": n_rows, "paths": P, "bad_status": bad}
     print(name, json.dumps(out[name]), flush=True)
+
+# POA modes with full-matrix semantics (0: AVX2 routine of global_abpoa, 1: local, 3: affine local) on the headline graph
+g = synth.make_graph(100000, 8, seed=1)
+reads = synth.make_reads(g, 296, 1000, err=0.05, seed=3)
+al = Aligner(0)
+al.load_gfa_text(g.gfa())
+al.set_scoring()
+codes, off = al.pack_reads(reads)
+al.upload(codes, off)
+for mode in (0, 1, 3):
+    al.align_staged(mode)
+    al.align_staged(mode)
+    ms, _nl, _c = al.kernel_stats()
+    res = al.fetch()
+    cells = sum(res.reads[i].cells for i in range(res.n_reads))
+    print("C2 graph -m %d: 296 reads x 1 kbp" % mode, json.dumps({"kernel_ms": ms, "reads_per_s": 296 / (ms * 1e-3), "gcups": cells / (ms * 1e-3) / 1e9}), flush=True)
