@@ -284,3 +284,13 @@ def test_scalar_mode0_reference_unit_vectors():
 def test_mode2_packed_rows_score_extremes(synth_files, name, extra):
     fa, gfa = synth_files[name]
     _assert_same(["-m", "2"] + extra + [fa, gfa])
+
+
+def test_mode2_packed_blocked32_and_striped_kernels_agree():
+    """Three independent implementations of mode 2 (packed 16-bit rows, 32-bit blocked rows, striped kernel) produce the
+    same records and run lists on the example, synthetic sets and read lengths at every lane-width boundary."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ab_s16", os.path.join(ROOT, "tools", "ab_s16.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main() == 0

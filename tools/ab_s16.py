@@ -48,7 +48,15 @@ def run_case(name, gfa_text, reads, **sc):
     b.set_scoring(**sc)
     rb = records(b, reads)
     os.environ.pop("RG_NO_S16", None)
-    bad = [i for i in range(len(reads)) if ra[i] != rb[i]]
+    os.environ["RG_FORCE_STRIPED"] = "1"
+    c = Aligner(0)
+    c.load_gfa_text(gfa_text)
+    c.set_scoring(**sc)
+    rc_ = records(c, reads)
+    os.environ.pop("RG_FORCE_STRIPED", None)
+    if rc_ != rb:
+        print(f"{name}: striped kernel differs from the blocked 32-bit paths on", sum(1 for x, y in zip(rc_, rb) if x != y), "reads")
+    bad = [i for i in range(len(reads)) if ra[i] != rb[i] or rc_[i] != rb[i]]
     print(f"{name}: {len(reads)} reads, {len(bad)} differ")
     for i in bad[:2]:
         x, y = ra[i], rb[i]
@@ -74,7 +82,14 @@ def main():
         reads = synth.make_reads(g, nr, rl, err=0.05, seed=seed + 100)
         n += run_case(f"synth {bp}bp {rl}bp reads -b 3000", g.gfa(), reads, extra_b=3000)
         n += run_case(f"synth {bp}bp {rl}bp reads default", g.gfa(), reads)
+    # read lengths around the points where the lane width changes (128 / 256 / 512 / 1024 columns incl. '$')
+    g = synth.make_graph(4000, 6, seed=9)
+    for rl in (126, 127, 128, 254, 255, 256, 510, 511, 512, 990, 1003, 1004, 1012, 1022, 1023):
+        reads = synth.make_reads(g, 6, rl, err=0.0, seed=rl)
+        reads = [r[:rl] for r in reads]
+        n += run_case(f"lane boundary: reads of exactly {rl} bp, full band", g.gfa(), reads, extra_b=3000)
     print("TOTAL DIFFERING", n)
+    return n
 
 
 if __name__ == "__main__":
