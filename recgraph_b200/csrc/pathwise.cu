@@ -22,6 +22,9 @@
 // acceptance rule is restated as (max score; first index with it; first index with it that is on a segment edge).
 #include <cuda_runtime.h>
 
+#include <climits>
+#include <cstdio>
+
 #include "device.h"
 #include "poa_common.cuh"
 
@@ -44,6 +47,9 @@ __device__ __forceinline__ int block_excl_max(int z, int tid, int* s_w) {
     return max(base, exc);
 }
 
+#ifdef RG_PWSTATS
+__device__ unsigned long long g_pw_cyc[4];
+#endif
 struct PwSmem {
     unsigned char* mv;  // [max_groups][Lp]
     int32_t* du;        // [Lp]
@@ -76,6 +82,10 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
     const size_t rowsz = (size_t)Pp * Lp;
     const uint32_t base_row = rev ? n - 1 : 0;
     const long long KEY_MIN = -(1ll << 62);
+    // per-column (score, path) maxima fit one 32-bit word when |score| < 2^23 for every reachable cell
+    int maxabs = 1;
+    for (int k = 0; k < 48; k++) maxabs = max(maxabs, abs(s_sc[k]));
+    const bool cb32 = (long long)maxabs * ((long long)n + Lp) < (1ll << 23);
     auto rcode = [&](int jj) -> unsigned { return rev ? read[L - 1 - jj] : read[jj - 1]; };
     // ---- base row: every path carries the accumulated read gaps (pathwise_alignment_semiglobal.rs:26-32,
     //      pathwise_alignment_recombination.rs:148-155)
@@ -100,6 +110,9 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
         const uint32_t alpha_i = g.alphas[i];
         int32_t* Si = d.S + (size_t)(i & RM) * rowsz;
         int32_t* lead_i = d.lead + (size_t)(i & RM) * Lp;
+#ifdef RG_PWSTATS
+        long long pt0 = clock64();
+#endif
         // ================= phase 0: per-column data shared by every path of the row =================
         for (int j = tid; j < L; j += PT) sm.sj[j] = (j >= 1) ? srow[rcode(j)] : 0;
         if (d.colbest) {
@@ -108,12 +121,20 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
             long long init = KEY_MIN;
             for (uint32_t q = 0; q < P; q++)
                 if (!((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u)) init = (long long)q;  // (0 << 8) | q
-            for (int j = tid; j < L; j += PT) sm.cb[j] = init;
+            if (cb32) {
+                const int init32 = init == KEY_MIN ? INT_MIN : (int)init;   // (0 << 7) | q
+                for (int j = tid; j < L; j += PT) reinterpret_cast<int*>(sm.cb)[j] = init32;
+            } else {
+                for (int j = tid; j < L; j += PT) sm.cb[j] = init;
+            }
         }
         if (d.lastcol && !rev)
             for (uint32_t q = tid; q < Pp; q += PT) d.lastcol[(size_t)i * Pp + q] = 0;
         if (tid == 0) *sm.rowbest = KEY_MIN;
         __syncthreads();
+#ifdef RG_PWSTATS
+        long long pt1 = clock64();
+#endif
         // ================= phase 1: the leader's DP of every group =================
         for (uint32_t gi = g0; gi < g1; gi++) {
             const PwGroup gr = g.grp[gi];
@@ -155,6 +176,9 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
             if (own_alpha && tid == 0) lead_i[0] = m0;
         }
         __syncthreads();
+#ifdef RG_PWSTATS
+        long long pt2 = clock64();
+#endif
         // ================= phase 2: members apply their leader's move =================
         // One warp per path, lanes over 32 consecutive columns. A run of L moves starts at the last column whose move
         // is D or U (or at column 0): its value there comes from the predecessor row, so every cell of the row is
@@ -205,38 +229,49 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
                 // value of a cell whose move is D or U (column 0: the border value); cells of an L run take the value
                 // at the run's start (a D / U cell of this tile or of an earlier one) plus the gaps since then
                 int nv = (j == 0) ? col0 : ((m == MV_D) ? spm1 + sj : sp + g_gr);
-                const unsigned below = mask & (0xffffffffu >> (31 - lane));
-                const int srcl = below ? 31 - __clz(below) : 0;
-                const int bv = __shfl_sync(FULL, nv, srcl);
-                if (isL) {
-                    const int rs = below ? tile * 32 + srcl : carry_rs;
-                    nv = (below ? bv : carry_base) + (j - rs) * g_rd;
-                }
-                {
-                    const int top = mask ? 31 - __clz(mask) : 0;
-                    const int tv = __shfl_sync(FULL, nv, top);
+                if (mask != FULL) {  // the tile has L moves (warp-uniform branch)
+                    const unsigned below = mask & (0xffffffffu >> (31 - lane));
+                    const int srcl = below ? 31 - __clz(below) : 0;
+                    const int bv = __shfl_sync(FULL, nv, srcl);
+                    if (isL) {
+                        const int rs = below ? tile * 32 + srcl : carry_rs;
+                        nv = (below ? bv : carry_base) + (j - rs) * g_rd;
+                    }
                     if (mask) {
+                        const int top = 31 - __clz(mask);
                         carry_rs = tile * 32 + top;
-                        carry_base = tv;
+                        carry_base = __shfl_sync(FULL, nv, top);
                     }
                 }
                 int nvm1 = __shfl_up_sync(FULL, nv, 1);
                 if (lane == 0) nvm1 = carry_nv;
-                unsigned code = 0;
+                // own arg-max in build_alignment's order (d, then u, else l) as the two planes of its code:
+                // D = 1, U = 2, L = 3  ->  plane 0 = not U, plane 1 = not D
+                bool pl0 = false, pl1 = false;
                 if (act && j >= 1) {
-                    // own arg-max in build_alignment's order: d, then u, else l
                     const int lq = nvm1 + g_rd;
                     const int dq = (quirk ? 0 : spm1) + sj, uq = (quirk ? 0 : sp) + g_gr;
                     const int bq = max(dq, max(uq, lq));
-                    code = (bq == dq) ? MV_D : ((bq == uq) ? MV_U : MV_L);
+                    const bool isD = bq == dq;
+                    pl1 = !isD;
+                    pl0 = isD || bq != uq;
                 }
                 if (act) Siq[j] = nv;
-                const unsigned p0 = __ballot_sync(FULL, code & 1u), p1 = __ballot_sync(FULL, code & 2u);
+                const unsigned p0 = __ballot_sync(FULL, pl0), p1 = __ballot_sync(FULL, pl1);
                 if (lane == 0 && tile < ntile) trq[tile] = make_uint2(p0, p1);
                 carry_nv = __shfl_sync(FULL, nv, 31);
                 carry_sp = __shfl_sync(FULL, sp, 31);
+                if (mask == FULL) {  // no L move in the tile: the last column is the latest run start
+                    carry_rs = tile * 32 + 31;
+                    carry_base = carry_nv;
+                }
                 // max of (score, path) over ALL slots; the highest path id wins ties (…_recombination.rs:809-830)
-                if (d.colbest && act) atomicMax(&sm.cb[j], ((long long)nv << 8) | (long long)q);
+                if (d.colbest && act) {
+                    if (cb32)
+                        atomicMax(reinterpret_cast<int*>(sm.cb) + j, (nv << 7) | (int)q);   // one ATOMS.MAX instead of a CAS loop
+                    else
+                        atomicMax(&sm.cb[j], ((long long)nv << 8) | (long long)q);
+                }
                 if (act && j == L - 1 && !rev) {
                     if (d.lastcol) d.lastcol[(size_t)i * Pp + q] = nv;
                     // first strict maximum in path order among the member paths
@@ -252,12 +287,23 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
             }
         }
         __syncthreads();
+#ifdef RG_PWSTATS
+        long long pt3 = clock64();
+#endif
         // ================= phase 3: per-row results =================
         if (d.colbest)
             for (int j = tid; j < L; j += PT) {
-                const long long key = sm.cb[j];
-                const uint32_t cb_path = (uint32_t)(key & 0xff);
-                const int cb_val = (int)(key >> 8);
+                uint32_t cb_path;
+                int cb_val;
+                if (cb32) {
+                    const int key = reinterpret_cast<int*>(sm.cb)[j];
+                    cb_path = (uint32_t)(key & 0x7f);
+                    cb_val = key >> 7;
+                } else {
+                    const long long key = sm.cb[j];
+                    cb_path = (uint32_t)(key & 0xff);
+                    cb_val = (int)(key >> 8);
+                }
                 const bool memb = (g.node_bits[(size_t)i * PW + cb_path / 32] >> (cb_path % 32)) & 1u;
                 d.colbest[(size_t)i * Lp + j] = make_int2(cb_val, (int)(cb_path | (memb ? 0x80000000u : 0u)));
             }
@@ -273,6 +319,15 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
             }
         }
         __syncthreads();
+#ifdef RG_PWSTATS
+        if (tid == 0 && blockIdx.x == 0) {
+            const long long pt4 = clock64();
+            atomicAdd(&g_pw_cyc[0], (unsigned long long)(pt1 - pt0));
+            atomicAdd(&g_pw_cyc[1], (unsigned long long)(pt2 - pt1));
+            atomicAdd(&g_pw_cyc[2], (unsigned long long)(pt3 - pt2));
+            atomicAdd(&g_pw_cyc[3], (unsigned long long)(pt4 - pt3));
+        }
+#endif
     }
 }
 
@@ -800,6 +855,15 @@ int launch_pathwise(int mode, const DevPathGraph& g, const DevPathGraph& rg_, co
         case 3: k_pathwise<3><<<blocks, PT, smem, st>>>(g, rg_, s, ws, rw, b, mode); break;
         default: k_pathwise<4><<<blocks, PT, smem, st>>>(g, rg_, s, ws, rw, b, mode); break;
     }
+#ifdef RG_PWSTATS
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[4];
+        cudaMemcpyFromSymbol(h, g_pw_cyc, sizeof h);
+        double t = (double)(h[0] + h[1] + h[2] + h[3]);
+        fprintf(stderr, "pathwise phases (CTA 0, cumulative): p0 %.1f%% p1 %.1f%% p2 %.1f%% p3 %.1f%%\n", 100 * h[0] / t, 100 * h[1] / t, 100 * h[2] / t, 100 * h[3] / t);
+    }
+#endif
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
