@@ -64,7 +64,7 @@ struct PwSmem {
 struct PwDir {  // buffers of one DP direction for the read in flight
     int32_t* S;        // ring of rows, [row & RM][path][column]
     int32_t* lead;
-    uint32_t* trace;   // [row][path][column / 32] x {plane 0, plane 1}
+    uint32_t* trace;   // [row][path]{plane 0: Lp/8 bytes, plane 1: Lp/8 bytes}, bit = column % 8
     int2* colbest;     // modes 8/9: per (row, column): {max over all slots, path | member << 31}
     int32_t* lastcol;  // forward: [row][Pp] scores of the last column
 };
@@ -180,9 +180,14 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
         long long pt2 = clock64();
 #endif
         // ================= phase 2: members apply their leader's move =================
-        // One warp per path, lanes over 32 consecutive columns. A run of L moves starts at the last column whose move
-        // is D or U (or at column 0): its value there comes from the predecessor row, so every cell of the row is
-        // independent of its left neighbour and the whole tile is computed at once.
+        // One warp per path; lane t of a tile owns CW = 8 consecutive columns (128-bit loads and stores, the chain of an
+        // L run inside the lane is a plain serial dependency). A cell whose move is D or U depends only on the
+        // predecessor row. Only a lane whose leading cells are L moves needs the value left of its first column: the
+        // last value of the nearest lane below that is not made of L moves only (found with a ballot, fetched with a
+        // shuffle) plus the gaps in between.
+        constexpr int CW = 8;
+        const int ntile8 = (L + 32 * CW - 1) / (32 * CW);
+        const uint32_t LB = Lp / 8;  // bytes per trace plane of one (row, path)
         for (uint32_t q = warp; q < P; q += NWARP) {
             int gq = -1;
             uint32_t pq = 0;
@@ -195,94 +200,118 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
             const int32_t* Spq = d.S + (size_t)(pq & RM) * rowsz + (size_t)q * Lp;
             int32_t* Siq = Si + (size_t)q * Lp;
             const unsigned char* mvq = sm.mv + (size_t)gq * Lp;
-            uint2* trq = reinterpret_cast<uint2*>(d.trace) + ((size_t)i * Pp + q) * LT;
+            unsigned char* trq = reinterpret_cast<unsigned char*>(d.trace) + ((size_t)i * Pp + q) * LB * 2;
             // reverse pass: the 'F' row is never made absolute by the reference (absolute_scores stops before it,
             // pathwise_alignment_recombination.rs:748), so its traceback sees 0 for every path but path 0
             const bool quirk = rev && pq == n - 1 && q != 0;
             const int col0 = free_border ? 0 : Spq[0] + g_gr;
-            int carry_rs = 0, carry_nv = 0, carry_sp = 0, carry_base = col0;
-            // the predecessor row is read PF tiles ahead (double-buffered): a tile is one dependent load otherwise
-            constexpr int PF = 4;
-            int spn[PF];
-#pragma unroll
-            for (int u = 0; u < PF; u++) spn[u] = (u * 32 + lane < L) ? Spq[u * 32 + lane] : 0;
-            for (int tile0 = 0; tile0 < ntile; tile0 += PF) {
-                int spv[PF];
-#pragma unroll
-                for (int u = 0; u < PF; u++) {
-                    spv[u] = spn[u];
-                    const int jn = (tile0 + PF + u) * 32 + lane;
-                    spn[u] = (jn < L) ? Spq[jn] : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < PF; u++) {
-                const int tile = tile0 + u;  // tiles past the read's end do nothing (act is false for all lanes)
-                const int j = tile * 32 + lane;
-                const bool act = j < L;
-                const int sp = spv[u];
-                int spm1 = __shfl_up_sync(FULL, sp, 1);
-                if (lane == 0) spm1 = carry_sp;
-                const unsigned m = (act && j >= 1) ? mvq[j] : (unsigned)MV_D;
-                const int sj = act ? sm.sj[j] : 0;
-                const bool isL = m == MV_L;
-                const unsigned mask = __ballot_sync(FULL, !isL);
-                // value of a cell whose move is D or U (column 0: the border value); cells of an L run take the value
-                // at the run's start (a D / U cell of this tile or of an earlier one) plus the gaps since then
-                int nv = (j == 0) ? col0 : ((m == MV_D) ? spm1 + sj : sp + g_gr);
-                if (mask != FULL) {  // the tile has L moves (warp-uniform branch)
-                    const unsigned below = mask & (0xffffffffu >> (31 - lane));
-                    const int srcl = below ? 31 - __clz(below) : 0;
-                    const int bv = __shfl_sync(FULL, nv, srcl);
-                    if (isL) {
-                        const int rs = below ? tile * 32 + srcl : carry_rs;
-                        nv = (below ? bv : carry_base) + (j - rs) * g_rd;
-                    }
-                    if (mask) {
-                        const int top = 31 - __clz(mask);
-                        carry_rs = tile * 32 + top;
-                        carry_base = __shfl_sync(FULL, nv, top);
+            int carry_last = 0;   // new value of the column left of the tile
+            int carry_sp = 0;     // predecessor-row value of the column left of the tile
+            int4 nx0 = make_int4(0, 0, 0, 0), nx1 = nx0;
+            if ((uint32_t)(lane * CW) < Lp) {
+                nx0 = *reinterpret_cast<const int4*>(Spq + lane * CW);
+                nx1 = *reinterpret_cast<const int4*>(Spq + lane * CW + 4);
+            }
+            for (int tile = 0; tile < ntile8; tile++) {
+                const int j0 = (tile * 32 + lane) * CW;
+                const int sp[CW] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
+                {   // next tile's predecessor values are in flight while this one is computed
+                    const int jn = j0 + 32 * CW;
+                    if (tile + 1 < ntile8 && (uint32_t)jn < Lp) {
+                        nx0 = *reinterpret_cast<const int4*>(Spq + jn);
+                        nx1 = *reinterpret_cast<const int4*>(Spq + jn + 4);
                     }
                 }
-                int nvm1 = __shfl_up_sync(FULL, nv, 1);
-                if (lane == 0) nvm1 = carry_nv;
+                int spm = __shfl_up_sync(FULL, sp[CW - 1], 1);
+                if (lane == 0) spm = carry_sp;
+                unsigned mvw[2] = {0x01010101u * MV_D, 0x01010101u * MV_D};
+                int sjv[CW] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (j0 < L) {
+                    const uint2 mw = *reinterpret_cast<const uint2*>(mvq + j0);
+                    mvw[0] = mw.x;
+                    mvw[1] = mw.y;
+                    const int4 s0 = *reinterpret_cast<const int4*>(sm.sj + j0), s1 = *reinterpret_cast<const int4*>(sm.sj + j0 + 4);
+                    sjv[0] = s0.x, sjv[1] = s0.y, sjv[2] = s0.z, sjv[3] = s0.w;
+                    sjv[4] = s1.x, sjv[5] = s1.y, sjv[6] = s1.z, sjv[7] = s1.w;
+                }
+                // values that do not depend on the left neighbour, L flags, position of my first non-L cell
+                int nv[CW];
+                unsigned lbits = 0;
+#pragma unroll
+                for (int k = 0; k < CW; k++) {
+                    const int j = j0 + k;
+                    const unsigned m = (mvw[k / 4] >> (8 * (k % 4))) & 0xffu;
+                    const bool isL = j >= 1 && j < L && m == MV_L;
+                    if (isL) lbits |= 1u << k;
+                    const int spl = (k == 0) ? spm : sp[k - 1];
+                    nv[k] = (j == 0) ? col0 : ((m == MV_D) ? spl + sjv[k] : sp[k] + g_gr);
+                }
+                const int first = __ffs(~lbits) - 1;            // 0..8 (8: every cell of the lane is an L move)
+                const bool transparent = first >= CW;
+                // chain inside the lane from my first non-L cell on
+#pragma unroll
+                for (int k = 1; k < CW; k++)
+                    if (((lbits >> k) & 1u) && k > first) nv[k] = nv[k - 1] + g_rd;
+                // value left of my first column
+                const unsigned fixedm = __ballot_sync(FULL, !transparent);
+                const unsigned below = fixedm & ((1u << lane) - 1u);
+                const int srcl = below ? 31 - __clz(below) : 0;
+                const int lastv = __shfl_sync(FULL, nv[CW - 1], srcl);
+                const int X = below ? lastv + (lane - 1 - srcl) * CW * g_rd : carry_last + lane * CW * g_rd;
+#pragma unroll
+                for (int k = 0; k < CW; k++)
+                    if (k < first) nv[k] = X + (k + 1) * g_rd;
                 // own arg-max in build_alignment's order (d, then u, else l) as the two planes of its code:
                 // D = 1, U = 2, L = 3  ->  plane 0 = not U, plane 1 = not D
-                bool pl0 = false, pl1 = false;
-                if (act && j >= 1) {
-                    const int lq = nvm1 + g_rd;
-                    const int dq = (quirk ? 0 : spm1) + sj, uq = (quirk ? 0 : sp) + g_gr;
-                    const int bq = max(dq, max(uq, lq));
-                    const bool isD = bq == dq;
-                    pl1 = !isD;
-                    pl0 = isD || bq != uq;
+                unsigned b0 = 0, b1 = 0;
+#pragma unroll
+                for (int k = 0; k < CW; k++) {
+                    const int j = j0 + k;
+                    if (j >= 1 && j < L) {
+                        const int spl = (k == 0) ? spm : sp[k - 1];
+                        const int lq = ((k == 0) ? X : nv[k - 1]) + g_rd;
+                        const int dq = (quirk ? 0 : spl) + sjv[k], uq = (quirk ? 0 : sp[k]) + g_gr;
+                        const int bq = max(dq, max(uq, lq));
+                        const bool isD = bq == dq;
+                        if (!isD) b1 |= 1u << k;
+                        if (isD || bq != uq) b0 |= 1u << k;
+                    }
                 }
-                if (act) Siq[j] = nv;
-                const unsigned p0 = __ballot_sync(FULL, pl0), p1 = __ballot_sync(FULL, pl1);
-                if (lane == 0 && tile < ntile) trq[tile] = make_uint2(p0, p1);
-                carry_nv = __shfl_sync(FULL, nv, 31);
-                carry_sp = __shfl_sync(FULL, sp, 31);
-                if (mask == FULL) {  // no L move in the tile: the last column is the latest run start
-                    carry_rs = tile * 32 + 31;
-                    carry_base = carry_nv;
+                if (j0 < L) {
+                    *reinterpret_cast<int4*>(Siq + j0) = make_int4(nv[0], nv[1], nv[2], nv[3]);
+                    *reinterpret_cast<int4*>(Siq + j0 + 4) = make_int4(nv[4], nv[5], nv[6], nv[7]);
+                    trq[j0 / CW] = (unsigned char)b0;
+                    trq[LB + j0 / CW] = (unsigned char)b1;
                 }
+                carry_last = __shfl_sync(FULL, nv[CW - 1], 31);
+                carry_sp = __shfl_sync(FULL, sp[CW - 1], 31);
                 // max of (score, path) over ALL slots; the highest path id wins ties (…_recombination.rs:809-830)
-                if (d.colbest && act) {
-                    if (cb32)
-                        atomicMax(reinterpret_cast<int*>(sm.cb) + j, (nv << 7) | (int)q);   // one ATOMS.MAX instead of a CAS loop
-                    else
-                        atomicMax(&sm.cb[j], ((long long)nv << 8) | (long long)q);
+                if (d.colbest) {
+#pragma unroll
+                    for (int k = 0; k < CW; k++) {
+                        const int j = j0 + k;
+                        if (j < L) {
+                            if (cb32)
+                                atomicMax(reinterpret_cast<int*>(sm.cb) + j, (nv[k] << 7) | (int)q);   // one ATOMS.MAX, no CAS loop
+                            else
+                                atomicMax(&sm.cb[j], ((long long)nv[k] << 8) | (long long)q);
+                        }
+                    }
                 }
-                if (act && j == L - 1 && !rev) {
-                    if (d.lastcol) d.lastcol[(size_t)i * Pp + q] = nv;
+                if (!rev && j0 <= L - 1 && L - 1 < j0 + CW) {
+                    int lastval = nv[0];
+#pragma unroll
+                    for (int k = 1; k < CW; k++)
+                        if (j0 + k == L - 1) lastval = nv[k];
+                    if (d.lastcol) d.lastcol[(size_t)i * Pp + q] = lastval;
                     // first strict maximum in path order among the member paths
-                    atomicMax(sm.rowbest, ((long long)nv << 8) | (long long)(255 - q));
+                    atomicMax(sm.rowbest, ((long long)lastval << 8) | (long long)(255 - q));
                     if (track_results)
                         for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
                             if (g.grp[fg].pred == i && ((g.grp_mask[(size_t)fg * PW + q / 32] >> (q % 32)) & 1u)) {
-                                sm.res[q] = nv;   // pathwise_alignment.rs:305-319
+                                sm.res[q] = lastval;   // pathwise_alignment.rs:305-319
                                 sm.end[q] = i;
                             }
-                }
                 }
             }
         }
@@ -333,8 +362,10 @@ __device__ void pw_dp(const DevPathGraph& g, const PwDir& d, const PwSmem& sm, c
 
 // own-argmax code of path q at (row, col) in one direction's trace
 __device__ __forceinline__ unsigned pw_code(const uint32_t* trace, uint32_t Lp, uint32_t PW, uint32_t row, int col, uint32_t q) {
-    const uint2 pl = reinterpret_cast<const uint2*>(trace)[((size_t)row * (PW * 32) + q) * (Lp / 32) + (uint32_t)col / 32];
-    return ((pl.x >> (col % 32)) & 1u) | (((pl.y >> (col % 32)) & 1u) << 1);
+    const uint32_t LB = Lp / 8;
+    const unsigned char* t = reinterpret_cast<const unsigned char*>(trace) + ((size_t)row * (PW * 32) + q) * LB * 2;
+    const unsigned b0 = t[(uint32_t)col / 8], b1 = t[LB + (uint32_t)col / 8];
+    return ((b0 >> (col % 8)) & 1u) | (((b1 >> (col % 8)) & 1u) << 1);
 }
 __device__ __forceinline__ uint32_t pw_pred(const DevPathGraph& g, uint32_t row, uint32_t q, uint32_t dflt) {
     uint32_t pred = dflt;
