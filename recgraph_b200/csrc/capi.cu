@@ -648,6 +648,7 @@ static int align_pathwise(rg_ctx* c, int mode) {
     if (lc == -3) return c->fail(RG_ERR_UNSUPPORTED, "read too long for the pathwise kernel's shared-memory move table");
     if (lc != 0) return c->cuda_fail("kernel configuration");
     if (bps < 1) bps = 1;
+    if (const char* e = getenv("RG_PW_BPS")) bps = std::max(1, std::min(bps, atoi(e)));  // testing: CTAs per SM
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     free_b += (c->d_pwS.cap + c->d_pwLead.cap + c->d_pwTrace.cap + c->d_rS.cap + c->d_rLead.cap + c->d_rTrace.cap + c->d_lastcol.cap) * 4 +
