@@ -30,7 +30,10 @@
 
 namespace rg {
 
-constexpr int PT = 256;    // threads per CTA
+#ifndef RG_PW_THREADS
+#define RG_PW_THREADS 512
+#endif
+constexpr int PT = RG_PW_THREADS;    // threads per CTA
 constexpr int MAXPW = 4;   // up to 128 paths (kernels are instantiated for 1..4 words of 32 paths)
 enum { MV_D = 1, MV_U = 2, MV_L = 3 };
 
@@ -428,7 +431,7 @@ __device__ __forceinline__ void rec_merge2(RecBest& a, const RecBest& o) {
 }
 
 template <int TPW>
-__global__ void __launch_bounds__(PT, 2) k_pathwise(DevPathGraph g, DevPathGraph rg_, DevScoring sc, PwWorkspace ws,
+__global__ void __launch_bounds__(PT, PT <= 256 ? 2 : 1) k_pathwise(DevPathGraph g, DevPathGraph rg_, DevScoring sc, PwWorkspace ws,
                                                   PwRecWorkspace rw, PoaBatch b, int mode) {
     extern __shared__ unsigned char s_dyn[];
     __shared__ int32_t s_sc[48];
