@@ -147,6 +147,32 @@ char* rgo_dump_pathgraph(const char* gfa_text, int is_reversed, int reverse_grap
 }
 
 // helpers pinned by the reference's own tests
+// Modes 4-7 on one read, for the self-consistency checks of the affine pathwise restatement (with o = 0 the affine
+// recurrences of modes 6 / 7 reduce to the linear ones of modes 4 / 5). Returns "score best_path cigar-or-line".
+char* rgo_pathwise_one(const char* gfa_text, const char* read, int mode, int m, int x, int o, int e) {
+    try {
+        HashGraph hg = parse_gfa_text(gfa_text);
+        PathGraph g = create_path_graph(hg, false);
+        ScoreMatrix sm = create_score_matrix_match_mis(m, x);
+        std::vector<char> seq{'$'};
+        for (const char* c = read; *c; c++) seq.push_back(*c);
+        std::ostringstream os;
+        if (mode == 6 || mode == 7) {
+            std::string line;
+            int score = 0;
+            size_t bp = mode == 6 ? pathwise_alignment_gap_exec(seq, g, sm, o, e, line, &score)
+                                  : pathwise_alignment_gap_semi_exec(seq, g, sm, o, e, line, &score);
+            os << score << " " << bp << " " << line;
+        } else {
+            GAFStruct gaf = mode == 4 ? pathwise_alignment_exec(seq, g, sm) : pathwise_alignment_semiglobal_exec(seq, g, sm);
+            os << gaf.comments;
+        }
+        return dup(os.str());
+    } catch (const std::exception& ex) {
+        return dup(std::string("PANIC ") + ex.what());
+    }
+}
+
 char* rgo_rev_and_compl(const char* seq) {
     try {
         std::vector<char> s(seq, seq + strlen(seq));

@@ -256,7 +256,19 @@ int recgraph_main(const std::vector<std::string>& argv, std::string& out, std::s
                 break;
             }
             case 6:
-            case 7: throw RefPanic("oracle: modes 6/7 (experimental affine pathwise) are not restated yet");
+            case 7: {  // main.rs:271-288: exec println!s the CIGAR line, main prints the best path
+                PathGraph graph = create_path_graph(hg, false);
+                for (size_t i = 0; i < sequences.size(); i++) {
+                    std::string line;
+                    size_t best_path = align_mode == 6
+                                           ? pathwise_alignment_gap_exec(sequences[i], graph, score_matrix, g_open, g_ext, line)
+                                           : pathwise_alignment_gap_semi_exec(sequences[i], graph, score_matrix, g_open, g_ext, line);
+                    out += line;
+                    out += "\n";
+                    out += "Best path sequence " + std::to_string(i) + ": " + std::to_string(best_path) + "\n";
+                }
+                break;
+            }
             case 8:
             case 9: {
                 PathGraph graph = create_path_graph(hg, false);

@@ -191,6 +191,12 @@ GAFStruct pathwise_alignment_exec(const std::vector<char>& seq, const PathGraph&
                                   const ScoreMatrix& sm);  // pathwise_alignment.rs:5-340
 GAFStruct pathwise_alignment_semiglobal_exec(const std::vector<char>& seq, const PathGraph& g,
                                              const ScoreMatrix& sm);  // pathwise_alignment_semiglobal.rs:6-242
+// Experimental affine pathwise modes 6 / 7: return the best path, `line` = the CIGAR line exec println!s
+// (pathwise_alignment_gap.rs:4-574, pathwise_alignment_gap_semi.rs:5-473, pathwise_alignment_output.rs:186-451).
+size_t pathwise_alignment_gap_exec(const std::vector<char>& seq, const PathGraph& g, const ScoreMatrix& sm, int o, int e,
+                                   std::string& line, int* best_score = nullptr);
+size_t pathwise_alignment_gap_semi_exec(const std::vector<char>& seq, const PathGraph& g, const ScoreMatrix& sm, int o, int e,
+                                        std::string& line, int* best_score = nullptr);
 GAFStruct pathwise_alignment_recombination_exec(int aln_mode, const std::vector<char>& seq, const PathGraph& g,
                                                 const PathGraph& rev_g, const ScoreMatrix& sm, int base_rec_cost,
                                                 float multi_rec_cost, const Displacement& displ,

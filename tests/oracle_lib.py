@@ -30,9 +30,10 @@ def load():
                              ctypes.POINTER(ctypes.c_void_p)]
     lib.rgo_main.restype = ctypes.c_int
     lib.rgo_poa_score.restype = ctypes.c_int
-    for f in ("rgo_dump_lnz", "rgo_dump_pathgraph", "rgo_rev_and_compl", "rgo_f32_display"):
+    for f in ("rgo_dump_lnz", "rgo_dump_pathgraph", "rgo_rev_and_compl", "rgo_f32_display", "rgo_pathwise_one"):
         getattr(lib, f).restype = ctypes.c_void_p
     lib.rgo_dump_lnz.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.rgo_pathwise_one.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 5
     lib.rgo_dump_pathgraph.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
     lib.rgo_rev_and_compl.argtypes = [ctypes.c_char_p]
     lib.rgo_f32_display.argtypes = [ctypes.c_float]
@@ -92,6 +93,11 @@ def dump_lnz(gfa_text, amb_mode=False):
 def dump_pathgraph(gfa_text, is_reversed=False, reverse_graph=False):
     lib = load()
     return _take(lib, lib.rgo_dump_pathgraph(gfa_text.encode(), int(is_reversed), int(reverse_graph)))
+
+
+def pathwise_one(gfa_text, read, mode, m=2, x=-4, o=-4, e=-2):
+    lib = load()
+    return _take(lib, lib.rgo_pathwise_one(gfa_text.encode(), read.encode(), mode, m, x, o, e))
 
 
 def rev_and_compl(s):

@@ -5,9 +5,13 @@ score matrix, parameters and expected value. These are the reference's only gold
 """
 import re
 
+import os
+
 import pytest
 
 from tests import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 AA = {("A", "A"): 1, ("A", "-"): -1, ("-", "A"): -1}
 AC = dict(AA)
@@ -211,3 +215,32 @@ def test_simd_variants_agree_with_scalar_on_reference_vectors():
     for variant, (lnz, nwp, preds), read, _s, _o, _e, _bta, expected, cite in POA_CASES[:4]:
         rc, score, _ = O.poa_score(10, lnz, nwp, preds, list(read), full, 0, 0, 100)
         assert rc == 0 and score == expected, cite
+
+
+def test_affine_pathwise_modes_reduce_to_linear_when_gap_open_is_zero():
+    """Modes 6 / 7 (pathwise_alignment_gap*.rs) ship no test in the reference. Self-consistency of the restatement:
+    with o = 0 and e = the linear modes' gap score, the affine recurrences give the scores of modes 4 / 5 on the
+    example; a negative o can only lower them; mode 7 reports the CIGAR of a 150-base read with 150 read-consuming ops."""
+    import re
+    gfa = open(os.path.join(ROOT, "tests", "golden", "example", "graph.gfa")).read()
+    reads, cur = [], []
+    for ln in open(os.path.join(ROOT, "tests", "golden", "example", "reads.fa")):
+        if ln.startswith(">"):
+            if cur:
+                reads.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ln.strip().upper())
+    reads.append("".join(cur))
+    for r in reads[:6]:
+        s4 = int(re.search(r"score: (-?\d+)", O.pathwise_one(gfa, r, 4)).group(1))
+        s5 = int(re.search(r"score: (-?\d+)", O.pathwise_one(gfa, r, 5)).group(1))
+        m6 = O.pathwise_one(gfa, r, 6, o=0, e=-8).split(" ")
+        m7 = O.pathwise_one(gfa, r, 7, o=0, e=-8).split(" ")
+        assert int(m6[0]) == s4 and int(m7[0]) == s5
+        a6 = O.pathwise_one(gfa, r, 6, o=-4, e=-8).split(" ")
+        a7 = O.pathwise_one(gfa, r, 7, o=-4, e=-2).split(" ")
+        assert int(a6[0]) <= s4
+        cig = a7[2].split("\t")[0]
+        ops = re.findall(r"(\d+)([MXID])", cig)
+        assert sum(int(n) for n, c in ops if c in "MXD") == len(r)  # I = graph-only steps (build_cigar, …_output.rs:471-556)
