@@ -130,7 +130,7 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int (&v)[C]) {
 #define PK_ENTER_LO (-12000)  // a row may enter the packed form when its real cells lie in base16 + [LO, HI]
 #define PK_ENTER_HI (1000)
 #define PK_GATHER_LO (-20000)  // predecessor rows gathered while packed (base16 may be up to ~4000 stale)
-#define PK_GATHER_HI (5000)
+#define PK_GATHER_HI (3000)   // + 32 rows of upward drift (30 per row) = 3960: still 32768 below the lowest padding value
 #define PK_SPREAD (14000)     // guard: leave the packed form when a real cell falls this far below the row maximum
 #define PK_REBASE (2000)      // guard: re-base when the row maximum drifted this far from base16
 #define PK_GUARD_ROWS 32      // rows between two guards; scores move by at most 60 per row (see en16)
