@@ -294,3 +294,18 @@ def test_mode2_packed_blocked32_and_striped_kernels_agree():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main() == 0
+
+
+@pytest.mark.parametrize("name", ["m0_b50", "m1", "m2_default", "m2_b50", "m2_s_true_b50", "m0_s_true_b50", "m3", "m4", "m5",
+                                  "m8", "m9"])
+def test_example_against_committed_fixtures(name):
+    """The GPU command line against the golden GAF files under tests/golden/example/expected (written by
+    tools/make_golden.py from the oracle): byte-identical stdout."""
+    import importlib.util
+    from recgraph_b200 import run_cli
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tools", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    rc, out, err = run_cli(mg.CASES[name] + EX)
+    assert rc == 0, err
+    assert out == open(os.path.join(EXAMPLE, "expected", name + ".gaf")).read()

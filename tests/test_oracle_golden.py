@@ -244,3 +244,17 @@ def test_affine_pathwise_modes_reduce_to_linear_when_gap_open_is_zero():
         cig = a7[2].split("\t")[0]
         ops = re.findall(r"(\d+)([MXID])", cig)
         assert sum(int(n) for n, c in ops if c in "MXD") == len(r)  # I = graph-only steps (build_cigar, …_output.rs:471-556)
+
+
+def test_oracle_reproduces_committed_fixtures():
+    """tests/golden/example/expected/*.gaf were written by tools/make_golden.py (oracle output on the shipped example);
+    any change of the restatement shows up here."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tools", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ex = os.path.join(ROOT, "tests", "golden", "example")
+    for name, flags in mg.CASES.items():
+        rc, out, err = O.run_cli(flags + [os.path.join(ex, "reads.fa"), os.path.join(ex, "graph.gfa")])
+        assert rc == 0, (name, err)
+        assert out == open(os.path.join(ex, "expected", name + ".gaf")).read(), name
