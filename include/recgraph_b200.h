@@ -210,6 +210,13 @@ void rg_free_reads(rg_reads* r);
 int rg_cli_main(int argc, const char** argv, char** out_text, char** err_text);
 void rg_free(void* p);
 
+/* Host-side diagnostics, no device needed: the flattened LnzGraph (graph.rs:31-123 + utils.rs:103-165: lnz, nwp, predecessor
+ * lists in list order, segment id per row, r-values) and the PathGraph or its reverse (pathwise_graph.rs:135-354: per-row
+ * alpha and path sets, per-edge path sets, distance-from-start / from-end) of a GFA text as a malloc'd text dump
+ * (free with rg_free; "ERROR ..." on malformed input). Used by the CPU tests of the host builders. */
+char* rg_debug_dump_lnz(const char* gfa_text, size_t len);
+char* rg_debug_dump_pathgraph(const char* gfa_text, size_t len, int reverse_graph);
+
 /* INT32 ALU microbenchmark used as the roofline denominator: giga-ops/s of IADD3, VIMNMX,
  * VIADDMNMX measured on the ctx's device. */
 int rg_int_peak(rg_ctx* ctx, double* iadd_gops, double* imnmx_gops, double* viaddmnmx_gops);

@@ -44,7 +44,7 @@ SYMBOLS = ["rg_init", "rg_destroy", "rg_strerror", "rg_last_error", "rg_load_gfa
            "rg_set_lnz_graph", "rg_graph_info", "rg_make_score_matrix", "rg_default_scoring", "rg_set_scoring",
            "rg_align_batch", "rg_upload_reads", "rg_align_staged", "rg_fetch_results", "rg_last_kernel_stats",
            "rg_format_gaf", "rg_read_fasta_file", "rg_read_fasta_text", "rg_free_reads", "rg_cli_main", "rg_free",
-           "rg_int_peak"]
+           "rg_int_peak", "rg_debug_dump_lnz", "rg_debug_dump_pathgraph"]
 
 _lib = None
 
@@ -78,6 +78,10 @@ def load():
     lib.rg_upload_reads.argtypes = [vp, c_i32, vp, vp]
     lib.rg_align_staged.argtypes = [vp, ctypes.c_int]
     lib.rg_fetch_results.argtypes = [vp, ctypes.POINTER(BatchResult)]
+    lib.rg_debug_dump_lnz.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    lib.rg_debug_dump_lnz.restype = vp
+    lib.rg_debug_dump_pathgraph.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+    lib.rg_debug_dump_pathgraph.restype = vp
     lib.rg_last_kernel_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_u64),
                                          ctypes.POINTER(c_u64)]
     lib.rg_format_gaf.argtypes = [vp, ctypes.c_int, ctypes.POINTER(BatchResult), c_i32, ctypes.c_char_p, c_u32,

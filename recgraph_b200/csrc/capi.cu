@@ -849,6 +849,79 @@ void rg_free_reads(rg_reads* r) {
 
 void rg_free(void* p) { free(p); }
 
+// ---- host-side diagnostics (no device needed): the flattened graph as text, in the layout of the test oracle's dumps,
+// so that the host builders (graph.rs:31-123, utils.rs:103-165, pathwise_graph.rs:135-354) can be checked on a CPU box
+static char* dup_string(const std::string& s) {
+    char* p = (char*)malloc(s.size() + 1);
+    if (!p) return nullptr;
+    memcpy(p, s.data(), s.size());
+    p[s.size()] = 0;
+    return p;
+}
+static bool flat_from_text(const char* text, size_t len, FlatGraph& f, std::string& err) {
+    GfaGraph g;
+    if (!parse_gfa(text, len, g, err)) return false;
+    return flatten_graph(g, f, err) == RG_OK;
+}
+
+char* rg_debug_dump_lnz(const char* gfa_text, size_t len) {
+    if (!gfa_text) return nullptr;
+    FlatGraph f;
+    std::string err;
+    if (!flat_from_text(gfa_text, len, f, err)) return dup_string("ERROR " + err);
+    std::string o = "lnz=";
+    for (uint32_t i = 0; i < f.n; i++) o += CODE_CHARS[f.lnz[i]];
+    o += "\nnwp=";
+    for (uint32_t i = 0; i < f.n; i++) o += f.nwp[i] ? '1' : '0';
+    o += "\n";
+    for (uint32_t i = 0; i < f.n; i++)
+        if (f.pred_off[i + 1] > f.pred_off[i]) {
+            o += "pred " + std::to_string(i) + ":";
+            for (uint32_t k = f.pred_off[i]; k < f.pred_off[i + 1]; k++) o += " " + std::to_string(f.pred_idx[k]);
+            o += "\n";
+        }
+    for (uint32_t i = 0; i + 1 < f.n; i++)
+        o += "hofp " + std::to_string(i) + ": " + (i == 0 ? std::string("-1") : std::to_string(f.row_seg_id[i])) + "\n";
+    o += "r_values=";
+    for (uint32_t i = 0; i < f.n; i++) o += (i ? "," : "") + std::to_string((long)f.r_values[i]);
+    o += "\n";
+    return dup_string(o);
+}
+
+char* rg_debug_dump_pathgraph(const char* gfa_text, size_t len, int reverse_graph) {
+    if (!gfa_text) return nullptr;
+    FlatGraph f;
+    std::string err;
+    if (!flat_from_text(gfa_text, len, f, err)) return dup_string("ERROR " + err);
+    if (!f.has_paths) return dup_string("ERROR the graph has no paths");
+    const std::vector<uint8_t>& nwp = reverse_graph ? f.rv_nwp : f.pw_nwp;
+    const std::vector<uint32_t>& poff = reverse_graph ? f.rv_pred_off : f.pw_pred_off;
+    const std::vector<uint32_t>& pidx = reverse_graph ? f.rv_pred_idx : f.pw_pred_idx;
+    const std::vector<uint32_t>& ebits = reverse_graph ? f.rv_edge_bits : f.pw_edge_bits;
+    auto bits = [&](const uint32_t* w) {
+        std::string b;
+        for (uint32_t k = 0; k < f.P; k++) b += ((w[k / 32] >> (k % 32)) & 1u) ? '1' : '0';
+        return b;
+    };
+    std::string o = "paths_number=" + std::to_string(f.P) + "\nlnz=";
+    for (uint32_t i = 0; i < f.n; i++) o += CODE_CHARS[f.lnz[i]];
+    o += "\nnwp=";
+    for (uint32_t i = 0; i < f.n; i++) o += nwp[i] ? '1' : '0';
+    o += "\n";
+    for (uint32_t i = 0; i < f.n; i++) {
+        o += "node " + std::to_string(i) + ": id=" + std::to_string(f.row_seg_id[i]) + " alpha=" + std::to_string(f.alphas[i]) +
+             " paths=" + bits(&f.node_bits[(size_t)i * f.PW]) + "\n";
+        for (uint32_t k = poff[i]; k < poff[i + 1]; k++)
+            o += "pred " + std::to_string(i) + " " + std::to_string(pidx[k]) + " " + bits(&ebits[(size_t)k * f.PW]) + "\n";
+    }
+    o += "dfs=";
+    for (uint32_t i = 0; i < f.n; i++) o += (i ? "," : "") + std::to_string(f.dfs[i]);
+    o += "\ndfe=";
+    for (uint32_t i = 0; i < f.n; i++) o += (i ? "," : "") + std::to_string(f.dfe[i]);
+    o += "\n";
+    return dup_string(o);
+}
+
 int rg_int_peak(rg_ctx* c, double* iadd, double* imnmx, double* viaddmnmx) {
     if (!c || !iadd || !imnmx || !viaddmnmx) return RG_ERR_INVALID;
     cudaSetDevice(c->device);
