@@ -849,7 +849,7 @@ void rg_free_reads(rg_reads* r) {
 
 void rg_free(void* p) { free(p); }
 
-// ---- host-side diagnostics (no device needed): the flattened graph as text, in the layout of the test oracle's dumps,
+// ---- host-side diagnostics (no device needed): the flattened graph as a text dump (layout documented in the header),
 // so that the host builders (graph.rs:31-123, utils.rs:103-165, pathwise_graph.rs:135-354) can be checked on a CPU box
 static char* dup_string(const std::string& s) {
     char* p = (char*)malloc(s.size() + 1);
