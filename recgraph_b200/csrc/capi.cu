@@ -261,6 +261,7 @@ static int upload_path_graph(rg_ctx* c) {
 static int upload_graph(rg_ctx* c) {
     FlatGraph& f = c->fg;
     cudaStream_t st = c->stream;
+    c->has_graph = false;   // stays false if the upload fails half-way
     std::vector<uint8_t> rowflags(f.n, 0);
     // RF_SINGLE_PREV: segment start whose only predecessor is the row right above it (and not the '$' row): the
     // kernels treat it like a row inside a segment, so its predecessor need not be kept in the ring either.
@@ -387,8 +388,10 @@ int rg_load_gfa_text(rg_ctx* c, const char* text, size_t len) {
     GfaGraph g;
     std::string err;
     if (!parse_gfa(text, len, g, err)) return c->fail(err.find("outside the supported") != std::string::npos ? RG_ERR_UNSUPPORTED : RG_ERR_IO, err);
-    int rc = flatten_graph(g, c->fg, err);
+    FlatGraph tmp;   // a failed load must leave the ctx's graph untouched
+    int rc = flatten_graph(g, tmp, err);
     if (rc != RG_OK) return c->fail(rc, err);
+    c->fg = std::move(tmp);
     rc = upload_graph(c);
     if (rc != RG_OK) return rc;
     return upload_path_graph(c);
@@ -409,8 +412,13 @@ int rg_set_lnz_graph(rg_ctx* c, uint32_t n, const uint8_t* lnz_codes, const uint
     if (!c || !lnz_codes || !nwp || !pred_off || !pred_idx) return RG_ERR_INVALID;
     cudaSetDevice(c->device);
     std::string err;
-    int rc = flat_from_lnz(n, lnz_codes, nwp, pred_off, pred_idx, seg_id, c->fg, err);
+    FlatGraph tmp;
+    int rc = flat_from_lnz(n, lnz_codes, nwp, pred_off, pred_idx, seg_id, tmp, err);
     if (rc != RG_OK) return c->fail(rc, err);
+    c->fg = std::move(tmp);
+    // a path graph left by an earlier rg_load_gfa_* does not describe this graph
+    c->has_path_graph = false;
+    c->path_graph_error = "graph set without paths (rg_set_lnz_graph): pathwise modes need rg_load_gfa_* or rg_set_path_graph";
     return upload_graph(c);
 }
 

@@ -567,6 +567,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                     uint32_t lf, rt;
                     band_for_row(ms, me, rv.x, L, bta, lf, rt);
                     if (lf != 0 || rt != (uint32_t)L) break;
+                    {   // the first-column seed o + e * (best_p + 1) (:88) follows the ROW INDEX of the smallest predecessor,
+                        // not the scores: after a long skip edge it can sit thousands above / below the row. Outside the
+                        // packed window the row is done by the exact 32-bit path (the dispatcher re-checks and unpacks).
+                        const int sd = o + e * (rv.y + 1) - base16;
+                        if (sd < PK_GATHER_LO || sd > PK_GATHER_HI) break;
+                    }
                     if (gat && !gather16((uint32_t)rv.z, rb >> 24)) {
                         rep16 = false;  // A / B are garbage now; the dispatcher's general path gathers from the ring itself
                         break;
@@ -666,12 +672,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
             const bool fast = (i > 0) && !nwp;
             const bool plain = left == 0 && prev_left == 0 && right <= prev_right;
 
-            bool f16 = en16 && fast && plain && right == (uint32_t)L && prev_right == (uint32_t)L;
+            // first-column seed of a packed row (see the steady loop): must fit the packed window around the base the row will use
+            const int sd16 = o + e * (best_p + 1) - (rep16 ? base16 : prev_tmax);
+            const bool seed_ok = sd16 >= PK_GATHER_LO && sd16 <= PK_GATHER_HI;
+            bool f16 = en16 && seed_ok && fast && plain && right == (uint32_t)L && prev_right == (uint32_t)L;
             // Packed segment-start row: every predecessor row (none of them row 0) and this row span the whole read, so
             // that no availability / fallback rule of gap_global_abpoa.rs:110-141 can trigger. The predecessor rows are
             // gathered from the ring straight into the packed representation; per cell the slot of the winning
             // predecessor (first in list order wins ties, :266-345) is kept as bit planes over my columns.
-            bool g16 = en16 && nwp && i > 0 && left == 0 && right == (uint32_t)L && best_p >= 1 && best_p > last_nonfull;
+            bool g16 = en16 && seed_ok && nwp && i > 0 && left == 0 && right == (uint32_t)L && best_p >= 1 && best_p > last_nonfull;
             if (g16) {
                 if (!rep16) base16 = prev_tmax;
                 if (gather16(pb, pe - pb)) {
