@@ -102,6 +102,16 @@ struct rg_ctx {
     DevBuf<int2> d_fm, d_rwbest;
     bool has_path_graph = false;
     std::string path_graph_error;
+    // score-transport kernel (pathwise_tr.cu): per-row records of both directions and its work-space
+    DevBuf<PwtRow> d_pwt_rows, d_pwt_rrows;
+    DevBuf<int32_t> d_nonmem_hi;
+    DevBuf<int32_t> d_tr_tables, d_tr_ring_lead, d_tr_ring_base, d_tr_lastcol;
+    DevBuf<uint16_t> d_tr_ring_org;
+    DevBuf<uint4> d_tr_ring_meta;
+    DevBuf<uint8_t> d_tr_mv_f, d_tr_mv_r, d_tr_own;
+    DevBuf<uint32_t> d_tr_own_pred;
+    DevBuf<int2> d_tr_cb_f, d_tr_cb_r;
+    bool pw_v1 = getenv("RG_PW_V1") != nullptr;   // testing: the per-path kernel of round 1 (pathwise.cu) for A/B runs
     DevBuf<int32_t> d_pwS, d_pwLead;
     DevBuf<uint32_t> d_pwTrace;
     // scoring
@@ -199,6 +209,64 @@ static void build_groups(const FlatGraph& f, const std::vector<uint8_t>& nwp, co
     grp_off[n] = (uint32_t)grp.size();
 }
 
+// Row records of the score-transport kernel for one direction (see device.h: PwtRow). Decides which rows transport and
+// which materialise, numbers the tables, and sizes the table ring so that no table is overwritten while a row that
+// refers to it can still be read (as a predecessor, or by the deferred last-column step of the next row).
+static void build_pwt_rows(const FlatGraph& f, const std::vector<uint32_t>& grp_off, const std::vector<PwGroup>& grp,
+                           const std::vector<uint32_t>& grp_mask, bool reverse, std::vector<PwtRow>& rows, uint32_t& TR) {
+    const uint32_t n = f.n, PW = f.PW;
+    rows.assign(n, PwtRow{});
+    const uint32_t base_row = reverse ? n - 1 : 0;
+    for (uint32_t i = 0; i < n; i++) {
+        rows[i].g0 = grp_off[i];
+        rows[i].lnz = f.lnz[i];
+    }
+    uint32_t next_id = 1, need = 2;
+    rows[base_row].tid = 0;
+    uint32_t prev = base_row;
+    // (table id, path set) the per-origin maxima of modes 8/9 currently describe
+    uint32_t mx_tid = 0;
+    std::vector<uint32_t> mx_set(&f.node_bits[(size_t)base_row * PW], &f.node_bits[(size_t)base_row * PW] + PW);
+    auto same_set = [&](const uint32_t* a, const uint32_t* b) {
+        for (uint32_t w = 0; w < PW; w++)
+            if (a[w] != b[w]) return false;
+        return true;
+    };
+    for (uint32_t t = 1; t + 1 < n; t++) {
+        const uint32_t i = reverse ? n - 1 - t : t;
+        const uint32_t g0 = grp_off[i], g1 = grp_off[i + 1];
+        const uint32_t* nb = &f.node_bits[(size_t)i * PW];
+        PwtRow& r = rows[i];
+        const bool transport = (g1 - g0 == 1) && same_set(&grp_mask[(size_t)g0 * PW], nb);
+        if (transport) {
+            r.kind |= PWT_T;
+            r.pred = grp[g0].pred;
+            r.leader = (uint16_t)grp[g0].leader;
+            r.tid = rows[r.pred].tid;
+            if (r.pred != prev) rows[r.pred].kind |= PWT_RING;
+            if (r.tid != mx_tid || !same_set(nb, mx_set.data())) {
+                r.kind |= PWT_MXREBUILD;
+                mx_tid = r.tid;
+                mx_set.assign(nb, nb + PW);
+            }
+        } else {
+            r.tid = next_id++;
+            for (uint32_t gi = g0; gi < g1; gi++) rows[grp[gi].pred].kind |= PWT_RING;
+            mx_tid = r.tid;
+            mx_set.assign(nb, nb + PW);
+        }
+        const uint32_t newest = next_id - 1;
+        for (uint32_t gi = g0; gi < g1; gi++) need = std::max(need, newest - rows[grp[gi].pred].tid + 1);
+        need = std::max(need, newest - rows[prev].tid + 1);
+        prev = i;
+    }
+    const uint32_t end_row = reverse ? 0 : n - 1;
+    if (!reverse)
+        for (uint32_t gi = grp_off[end_row]; gi < grp_off[end_row + 1]; gi++) rows[grp[gi].pred].kind |= PWT_FPRED;
+    TR = 2;
+    while (TR < need) TR <<= 1;
+}
+
 static int upload_path_graph(rg_ctx* c) {
     FlatGraph& f = c->fg;
     c->has_path_graph = false;
@@ -221,7 +289,17 @@ static int upload_path_graph(rg_ctx* c) {
     std::vector<PwGroup> rgrp;
     uint32_t rmax_groups = 1;
     build_groups(f, f.rv_nwp, f.rv_pred_off, f.rv_pred_idx, f.rv_edge_bits, true, rgrp_off, rgrp, rgrp_mask, rmax_groups);
+    std::vector<PwtRow> trows, trrows;
+    uint32_t TRf = 2, TRr = 2;
+    build_pwt_rows(f, grp_off, grp, grp_mask, false, trows, TRf);
+    build_pwt_rows(f, rgrp_off, rgrp, rgrp_mask, true, trrows, TRr);
+    std::vector<int32_t> nonmem_hi(f.n, -1);
+    for (uint32_t i = 0; i < f.n; i++)
+        for (uint32_t q = 0; q < f.P; q++)
+            if (!((f.node_bits[(size_t)i * f.PW + q / 32] >> (q % 32)) & 1u)) nonmem_hi[i] = (int32_t)q;
     cudaStream_t st = c->stream;
+    if (!(c->d_pwt_rows.upload(trows, st) && c->d_pwt_rrows.upload(trrows, st) && c->d_nonmem_hi.upload(nonmem_hi, st)))
+        return c->cuda_fail("path graph upload");
     bool ok = c->d_alphas.upload(f.alphas, st) && c->d_node_bits.upload(f.node_bits, st) && c->d_grp_off.upload(grp_off, st) &&
               c->d_grp_mask.upload(grp_mask, st) && c->d_grp.upload(grp, st) && c->d_pw_nwp.upload(f.pw_nwp, st) &&
               c->d_rgrp_off.upload(rgrp_off, st) && c->d_rgrp_mask.upload(rgrp_mask, st) && c->d_rgrp.upload(rgrp, st) &&
@@ -245,7 +323,14 @@ static int upload_path_graph(rg_ctx* c) {
     c->dpg.dfe = c->d_dfe.p;
     c->dpg.ring = ring;
     c->dpg.max_groups = max_groups;
+    c->dpg.rows = c->d_pwt_rows.p;
+    c->dpg.nonmem_hi = c->d_nonmem_hi.p;
+    c->dpg.TR = TRf;
+    c->dpg.n_groups = (uint32_t)grp.size();
     c->dpg_rev = c->dpg;
+    c->dpg_rev.rows = c->d_pwt_rrows.p;
+    c->dpg_rev.TR = TRr;
+    c->dpg_rev.n_groups = (uint32_t)rgrp.size();
     c->dpg_rev.grp_off = c->d_rgrp_off.p;
     c->dpg_rev.grp = c->d_rgrp.p;
     c->dpg_rev.grp_mask = c->d_rgrp_mask.p;
@@ -634,6 +719,9 @@ static int align_poa(rg_ctx* c, int mode) {
     return c->fail(RG_ERR_NOMEM, "trace buffers still overflow after retries");
 }
 
+static int align_pathwise_v1(rg_ctx* c, int mode);
+
+// Modes 4 / 5 / 8 / 9 through the score-transport kernel (pathwise_tr.cu).
 static int align_pathwise(rg_ctx* c, int mode) {
     if (!c->has_path_graph)
         return c->fail(c->path_graph_error.find("panics") != std::string::npos ? RG_ERR_REF_PANIC : RG_ERR_INVALID,
@@ -646,6 +734,91 @@ static int align_pathwise(rg_ctx* c, int mode) {
     const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
     if (f.P > 128) return c->fail(RG_ERR_UNSUPPORTED, "more than 128 paths are not supported on the device yet");
     if (n >= (1u << 21)) return c->fail(RG_ERR_UNSUPPORTED, "graph too large for the pathwise kernels");
+    const int cpt = pathwise_tr_cpt(c->max_len + 1);
+    if (c->pw_v1 || cpt == 0) return align_pathwise_v1(c, mode);
+    PwtWorkspace ws{};
+    ws.CPT = (uint32_t)cpt;
+    ws.LP = 256u * cpt;
+    ws.LT = ws.LP + 32;
+    ws.Pp = PW * 32;
+    ws.TRmax = std::max(c->dpg.TR, rec ? c->dpg_rev.TR : 2u);
+    ws.ringmax = std::max(c->dpg.ring, rec ? c->dpg_rev.ring : 2u);
+    ws.run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * ws.LP), 1u << 22);
+    int bps = 1;
+    int lc = pathwise_tr_blocks_per_sm(c->dpg, c->dpg_rev, ws, rec, &bps);
+    if (lc == -3) return align_pathwise_v1(c, mode);
+    if (lc != 0) return c->cuda_fail("kernel configuration");
+    if (bps < 1) bps = 1;
+    if (const char* e = getenv("RG_PW_BPS")) bps = std::max(1, std::min(bps, atoi(e)));  // testing: CTAs per SM
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    free_b += (c->d_tr_tables.cap + c->d_tr_ring_lead.cap + c->d_tr_ring_base.cap + c->d_tr_lastcol.cap + c->d_tr_own_pred.cap) * 4 +
+              c->d_tr_ring_org.cap * 2 + c->d_tr_ring_meta.cap * 16 + c->d_tr_mv_f.cap + c->d_tr_mv_r.cap + c->d_tr_own.cap +
+              (c->d_tr_cb_f.cap + c->d_tr_cb_r.cap) * 8 + (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
+    const size_t sz_tables = (size_t)ws.TRmax * ws.Pp * ws.LT, sz_ring = (size_t)ws.ringmax * ws.LP;
+    const size_t sz_mvf = (size_t)c->dpg.n_groups * (ws.LP / 4), sz_mvr = rec ? (size_t)c->dpg_rev.n_groups * (ws.LP / 4) : 0;
+    const size_t sz_own = (size_t)n * (ws.LP / 4), sz_cb = rec ? (size_t)n * ws.LP : 0, sz_last = rec ? (size_t)n * ws.Pp : 0;
+    const size_t per_slot = sz_tables * 4 + sz_ring * 10 + (size_t)ws.ringmax * 16 + sz_mvf + sz_mvr + sz_own + (size_t)n * 4 +
+                            sz_cb * 16 + sz_last * 4 + (size_t)ws.run_cap * sizeof(rg_run);
+    const size_t budget_all = (size_t)(free_b * 0.85);
+    size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(ws.run_cap, 16384), (budget_all / 8) / sizeof(rg_run));
+    out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
+    const size_t budget = budget_all - out_runs_cap * sizeof(rg_run);
+    uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * bps, (uint32_t)c->n_reads);
+    slots = (uint32_t)std::min<size_t>(slots, budget / per_slot);
+    if (slots < 1) return c->fail(RG_ERR_NOMEM, "not enough device memory for one pathwise read in flight");
+    ws.slots = slots;
+    bool ok = c->d_tr_tables.ensure(slots * sz_tables) && c->d_tr_ring_lead.ensure(slots * sz_ring) && c->d_tr_ring_base.ensure(slots * sz_ring) &&
+              c->d_tr_ring_org.ensure(slots * sz_ring) && c->d_tr_ring_meta.ensure((size_t)slots * ws.ringmax) &&
+              c->d_tr_mv_f.ensure(slots * sz_mvf) && c->d_tr_mv_r.ensure(slots * sz_mvr) && c->d_tr_own.ensure(slots * sz_own) &&
+              c->d_tr_own_pred.ensure((size_t)slots * n) && c->d_tr_cb_f.ensure(slots * sz_cb) && c->d_tr_cb_r.ensure(slots * sz_cb) &&
+              c->d_tr_lastcol.ensure(slots * sz_last) && c->d_slot_runs.ensure((size_t)slots * ws.run_cap) &&
+              c->d_out_runs.ensure(out_runs_cap) && c->d_results.ensure(c->n_reads + 1) && c->d_counters.ensure(4);
+    if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
+    ws.tables = c->d_tr_tables.p;
+    ws.ring_lead = c->d_tr_ring_lead.p;
+    ws.ring_base = c->d_tr_ring_base.p;
+    ws.ring_org = c->d_tr_ring_org.p;
+    ws.ring_meta = c->d_tr_ring_meta.p;
+    ws.mv_f = c->d_tr_mv_f.p;
+    ws.mv_r = c->d_tr_mv_r.p;
+    ws.own = c->d_tr_own.p;
+    ws.own_pred = c->d_tr_own_pred.p;
+    ws.cb_f = c->d_tr_cb_f.p;
+    ws.cb_r = c->d_tr_cb_r.p;
+    ws.lastcol = c->d_tr_lastcol.p;
+    ws.runs = c->d_slot_runs.p;
+    PoaBatch b{};
+    b.reads = c->d_reads.p;
+    b.read_off = c->d_read_off.p;
+    b.n_reads = c->n_reads;
+    b.order = c->d_order.p;
+    b.results = c->d_results.p;
+    b.out_runs = c->d_out_runs.p;
+    b.out_run_cap = out_runs_cap;
+    b.counters = c->d_counters.p;
+    cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
+    cudaEventRecord(c->ev0, c->stream);
+    int rc = launch_pathwise_tr(mode, c->dpg, c->dpg_rev, c->ds, ws, b, (int)slots, c->stream);
+    cudaEventRecord(c->ev1, c->stream);
+    if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("pathwise kernel");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->kernel_ms += ms;
+    c->launches += 1;
+    c->slots_used = slots;
+    cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("result copy");
+    c->n_runs_total = std::min<uint64_t>(c->h_counters.p[1], out_runs_cap);
+    return RG_OK;
+}
+
+// The per-path kernel of round 1 (pathwise.cu): every path of every row computed; kept for A/B tests (RG_PW_V1) and for
+// reads longer than the transport kernel's column blocks.
+static int align_pathwise_v1(rg_ctx* c, int mode) {
+    const FlatGraph& f = c->fg;
+    const uint32_t n = f.n, PW = f.PW;
+    const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
     PwWorkspace ws{};
     PwRecWorkspace rw{};
     ws.Lp = (c->max_len + 1 + 31) & ~31u;

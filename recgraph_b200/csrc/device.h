@@ -104,6 +104,29 @@ struct DevPathGraph {
     const int32_t* dfe;
     uint32_t ring;               // rows kept (pow2 > look-back)
     uint32_t max_groups;         // max groups per row
+    // ---- score-transport kernel (pathwise_tr.cu): per-row record, table ring depth, highest non-member path per row
+    const struct PwtRow* rows;   // n
+    const int32_t* nonmem_hi;    // n: highest path id that does NOT go through the row (-1: every path does)
+    uint32_t TR;                 // tables alive at once (power of two)
+    uint32_t n_groups;           // groups of all rows (size of the move trace in rows)
+};
+// Row record of the score-transport kernel. A row is a TRANSPORT row when it has exactly one group (then the group holds
+// every path of the row): all its paths apply the leader's move, so their scores relative to each other are copied from
+// the source cell and only the leader's DP plus a per-column ORIGIN index is computed. Any other row (several incoming
+// edges) MATERIALISES the scores of all its paths into a new table.
+struct PwtRow {
+    uint32_t pred;     // predecessor row of the single group (transport rows)
+    uint32_t g0;       // first group of the row (== grp_off[row])
+    uint32_t tid;      // id of the table the row's frame refers to (materialising rows: the table they create)
+    uint16_t leader;   // leader path of the single group
+    uint8_t lnz;
+    uint8_t kind;      // PWT_* bits
+};
+enum : uint8_t {
+    PWT_T = 1,          // transport row
+    PWT_RING = 2,       // some later row other than the next one reads this row's frame: keep it in the global ring
+    PWT_MXREBUILD = 4,  // modes 8/9: (table, path set) differs from the previous row's: rebuild the per-origin maxima
+    PWT_FPRED = 8       // predecessor of the end row (mode 4 results)
 };
 struct PwWorkspace {
     int32_t* S;         // slots * ring * Lp * Pp     (absolute scores, [row][col][path])
@@ -123,6 +146,29 @@ struct PwRecWorkspace {
     int2* rw;          // slots * n * Lp : reverse, column index L-1-j
     int32_t* lastcol;  // slots * n * Pp : forward scores of the last column
 };
+// Work-space of the score-transport kernel, per slot (= CTA = read in flight).
+struct PwtWorkspace {
+    int32_t* tables;    // slots * TRmax * Pp * LT      absolute scores of materialised rows, [table][path][column]
+    int32_t* ring_lead; // slots * ringmax * LP         frames of rows kept for later segment starts
+    int32_t* ring_base; // slots * ringmax * LP
+    uint16_t* ring_org; // slots * ringmax * LP
+    uint4* ring_meta;   // slots * ringmax              {leader path of the frame, table id, -, -}
+    uint8_t* mv_f;      // slots * groups_f * LP/4      leader moves, 2 bit per (group, column)
+    uint8_t* mv_r;      // slots * groups_r * LP/4      (modes 8/9)
+    uint8_t* own;       // slots * n * LP/4             own arg-max codes of the replayed path (shared by both directions)
+    uint32_t* own_pred; // slots * n                    predecessor row of the replayed path per row
+    int2* cb_f;         // slots * n * LP               modes 8/9: per (row, column) {max over all slots, path | member << 31}
+    int2* cb_r;
+    int32_t* lastcol;   // slots * n * Pp
+    rg_run* runs;       // slots * run_cap
+    uint32_t LP, LT, Pp, CPT;   // columns (= 256 * CPT), table row stride (LP + 32), padded paths, columns per thread
+    uint32_t TRmax, ringmax;
+    uint32_t run_cap, slots;
+};
+int pathwise_tr_cpt(uint32_t Lmax);   // columns per thread for reads of up to Lmax columns; 0 = too long
+int pathwise_tr_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const PwtWorkspace& ws, bool rec, int* nb);
+int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws,
+                       const PoaBatch& b, int blocks, void* stream);
 constexpr int REC_SURV = 2048;  // forward nodes of one column staged for the pair expansion
 int pathwise_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const PwWorkspace& ws, bool rec, int* nb);
 int launch_pathwise(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwWorkspace& ws,

@@ -1,0 +1,11 @@
+#!/bin/bash
+# usage: tools/gpu_retry.sh <logfile> <timeout-seconds> [--gpus N] -- '<command>'   (retries while the pod answers "busy", exit code 3)
+log=$1; shift
+to=$1; shift
+for k in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout "$to" "$@" > "$log" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3
