@@ -744,8 +744,9 @@ static int align_pathwise(rg_ctx* c, int mode) {
     ws.TRmax = std::max(c->dpg.TR, rec ? c->dpg_rev.TR : 2u);
     ws.ringmax = std::max(c->dpg.ring, rec ? c->dpg_rev.ring : 2u);
     ws.run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * ws.LP), 1u << 22);
+    ws.diag = getenv("RG_PW_DIAG") ? 1u : 0u;
     int bps = 1;
-    int lc = pathwise_tr_blocks_per_sm(c->dpg, c->dpg_rev, ws, rec, &bps);
+    int lc = pathwise_tr_blocks_per_sm(c->dpg, c->dpg_rev, c->ds, ws, rec, &bps);
     if (lc == -3) return align_pathwise_v1(c, mode);
     if (lc != 0) return c->cuda_fail("kernel configuration");
     if (bps < 1) bps = 1;

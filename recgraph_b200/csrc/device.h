@@ -164,9 +164,10 @@ struct PwtWorkspace {
     uint32_t LP, LT, Pp, CPT;   // columns (= 256 * CPT), table row stride (LP + 32), padded paths, columns per thread
     uint32_t TRmax, ringmax;
     uint32_t run_cap, slots;
+    uint32_t diag;      // RG_PW_DIAG: per-read phase timings (kilo-cycles) overwrite result fields — profiling only
 };
 int pathwise_tr_cpt(uint32_t Lmax);   // columns per thread for reads of up to Lmax columns; 0 = too long
-int pathwise_tr_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const PwtWorkspace& ws, bool rec, int* nb);
+int pathwise_tr_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws, bool rec, int* nb);
 int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws,
                        const PoaBatch& b, int blocks, void* stream);
 constexpr int REC_SURV = 2048;  // forward nodes of one column staged for the pair expansion

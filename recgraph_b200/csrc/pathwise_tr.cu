@@ -46,11 +46,11 @@ struct LastRec {   // last-column cell of a finished row, consumed one barrier l
 
 struct PwtShared {
     int32_t sc[48];
-    int totA[NWP];
-    unsigned totB[NWP];
-    int dlt[NT];
+    __align__(16) int totA[NWP];
+    __align__(16) long long totK[2][NWP];
+    int dlt[2][NT];
     int val[2][NT];
-    unsigned tot2[2][NWP];
+    __align__(16) unsigned tot2[2][NWP];
     LastRec last[2];
     int best_val, best_set;
     uint32_t best_row, best_path;
@@ -77,6 +77,28 @@ __device__ __forceinline__ int block_excl_max_i(int z, int* tot) {
     if (lane == 0) exc = NEG_INF;
     return max(base, exc);
 }
+// 64-bit keys (score << 32 | column << 16 | origin): ONE scan gives the incoming chain value and where it comes from
+__device__ __forceinline__ long long block_excl_max_k(long long z, long long* tot, long long none) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long inc = z;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc = max(inc, t);
+    }
+    if (lane == 31) tot[w] = inc;
+    __syncthreads();
+    long long base = none;
+#pragma unroll
+    for (int k = 0; k < NWP; k += 2) {
+        const longlong2 v = *reinterpret_cast<const longlong2*>(tot + k);
+        if (k < w) base = max(base, v.x);
+        if (k + 1 < w) base = max(base, v.y);
+    }
+    long long exc = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) exc = none;
+    return max(base, exc);
+}
 __device__ __forceinline__ unsigned block_excl_max_u(unsigned z, unsigned* tot) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned inc = z;
@@ -96,49 +118,36 @@ __device__ __forceinline__ unsigned block_excl_max_u(unsigned z, unsigned* tot) 
     return max(base, exc);
 }
 
-// 2-bit codes of my CPT columns -> bytes [t * CPT / 4, (t + 1) * CPT / 4) of a row of LP / 4 bytes
+// Two bit planes of my CPT columns (a = low plane, b = high plane) -> bytes [t * CPT / 4, (t + 1) * CPT / 4) of a row of
+// LP / 4 bytes. Leader moves: a = L move, b = D move (else U). Own codes of the replayed path: a = D, b = U (else L).
 template <int CPT>
-__device__ __forceinline__ void store_codes(uint8_t* rowp, int t, const unsigned (&code)[CPT]) {
-    constexpr int NWD = (CPT + 15) / 16;
-    unsigned w[NWD];
-#pragma unroll
-    for (int q = 0; q < NWD; q++) w[q] = 0;
-#pragma unroll
-    for (int k = 0; k < CPT; k++) w[k / 16] |= code[k] << (2 * (k % 16));
+__device__ __forceinline__ void store_planes2(uint8_t* rowp, int t, unsigned a, unsigned b) {
     uint8_t* p = rowp + (size_t)t * (CPT / 4);
     if constexpr (CPT == 4)
-        *p = (uint8_t)w[0];
+        *p = (uint8_t)(a | (b << 4));
     else if constexpr (CPT == 8)
-        *reinterpret_cast<uint16_t*>(p) = (uint16_t)w[0];
+        *reinterpret_cast<uint16_t*>(p) = (uint16_t)(a | (b << 8));
     else if constexpr (CPT == 16)
-        *reinterpret_cast<uint32_t*>(p) = w[0];
-    else if constexpr (CPT == 32)
-        *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
-    else {
-#pragma unroll
-        for (int q = 0; q < NWD; q++) reinterpret_cast<uint32_t*>(p)[q] = w[q];
-    }
+        *reinterpret_cast<uint32_t*>(p) = a | (b << 16);
+    else
+        *reinterpret_cast<uint2*>(p) = make_uint2(a, b);
 }
 template <int CPT>
-__device__ __forceinline__ void load_codes(const uint8_t* rowp, int t, unsigned (&code)[CPT]) {
-    constexpr int NWD = (CPT + 15) / 16;
-    unsigned w[NWD];
+__device__ __forceinline__ void load_planes2(const uint8_t* rowp, int t, unsigned& a, unsigned& b) {
     const uint8_t* p = rowp + (size_t)t * (CPT / 4);
-    if constexpr (CPT == 4)
-        w[0] = *p;
-    else if constexpr (CPT == 8)
-        w[0] = *reinterpret_cast<const uint16_t*>(p);
-    else if constexpr (CPT == 16)
-        w[0] = *reinterpret_cast<const uint32_t*>(p);
-    else if constexpr (CPT == 32) {
-        const uint2 v = *reinterpret_cast<const uint2*>(p);
-        w[0] = v.x, w[1] = v.y;
+    if constexpr (CPT == 4) {
+        const unsigned v = *p;
+        a = v & 15u, b = v >> 4;
+    } else if constexpr (CPT == 8) {
+        const unsigned v = *reinterpret_cast<const uint16_t*>(p);
+        a = v & 255u, b = v >> 8;
+    } else if constexpr (CPT == 16) {
+        const unsigned v = *reinterpret_cast<const uint32_t*>(p);
+        a = v & 0xffffu, b = v >> 16;
     } else {
-#pragma unroll
-        for (int q = 0; q < NWD; q++) w[q] = reinterpret_cast<const uint32_t*>(p)[q];
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        a = v.x, b = v.y;
     }
-#pragma unroll
-    for (int k = 0; k < CPT; k++) code[k] = (w[k / 16] >> (2 * (k % 16))) & 3u;
 }
 
 // The leader's linear-gap DP over my columns (pathwise_alignment_semiglobal.rs:38-60): A = leader scores of the
@@ -216,10 +225,48 @@ struct PwtCtx {
     int32_t* s_res;
     uint32_t* s_end;
     uint32_t LP, LT, Pp, TRmax;
+    long long* mcyc;   // diagnostics: cycles spent in materialising rows (thread 0)
+};
+
+// Substitution scores of my columns against graph base `lnz`. SIMPLE (match / mismatch tables of score_matrix.rs:35-66): a
+// bit test on per-base equality masks built once per read; otherwise a shared-memory table look-up.
+template <int CPT, bool SIMPLE>
+struct SubScores {
+    unsigned eqm[4];                 // SIMPLE: bit k = my column k holds base b
+    unsigned rcw[(CPT + 3) / 4];     // read codes of my columns, one byte each
+    int s_match, s_mis;
+    __device__ __forceinline__ void init(const uint8_t* read, int L, int j0, bool rev, const int32_t* sc) {
+#pragma unroll
+        for (int q = 0; q < (CPT + 3) / 4; q++) rcw[q] = 0;
+        eqm[0] = eqm[1] = eqm[2] = eqm[3] = 0;
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int j = j0 + k;
+            // column jj aligns read[jj-1] in the forward pass, read[L-1-jj] in the reverse pass
+            const unsigned code = (j >= 1 && j < L) ? (rev ? read[L - 1 - j] : read[j - 1]) : 4u;
+            rcw[k / 4] |= code << (8 * (k % 4));
+#pragma unroll
+            for (unsigned bse = 0; bse < 4; bse++) eqm[bse] |= (code == bse ? 1u : 0u) << k;
+        }
+        s_match = sc[0];
+        s_mis = sc[1];
+    }
+    __device__ __forceinline__ void get(int lnz, const int32_t* sc, int (&sv)[CPT]) const {
+        if constexpr (SIMPLE) {
+            const unsigned em = lnz == 0 ? eqm[0] : (lnz == 1 ? eqm[1] : (lnz == 2 ? eqm[2] : (lnz == 3 ? eqm[3] : 0u)));
+            const int dm = s_match - s_mis;
+#pragma unroll
+            for (int k = 0; k < CPT; k++) sv[k] = s_mis + (int)((em >> k) & 1u) * dm;
+        } else {
+            const int32_t* srow = sc + lnz * 8;
+#pragma unroll
+            for (int k = 0; k < CPT; k++) sv[k] = srow[(rcw[k / 4] >> (8 * (k % 4))) & 0xffu];
+        }
+    }
 };
 
 // One DP pass over all rows of one direction.
-template <int CPT>
+template <int CPT, bool SIMPLE>
 __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBufs& d, PwtShared& sh, const uint8_t* read,
                          int L, bool rev, bool free_border, bool track_best, bool track_results, bool want_last, int gap) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -229,29 +276,14 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
     const int j0 = tid * CPT;
     const size_t tstride = (size_t)Pp * LT;
     const uint32_t base_row = rev ? n - 1 : 0;
-    constexpr unsigned ALL = (CPT >= 32) ? 0xffffffffu : ((1u << (CPT % 32)) - 1u);
-    static_assert(CPT <= 32 || CPT == 48, "CPT");
+    const long long KNONE = (long long)NEG_INF << 32;
+    SubScores<CPT, SIMPLE> ss;
+    ss.init(read, L, j0, rev, sh.sc);
 
-    // read codes of my columns in this direction's coordinates (column jj aligns read[jj-1] forward, read[L-1-jj] reverse)
-    unsigned rcw[(CPT + 3) / 4];
-#pragma unroll
-    for (int q = 0; q < (CPT + 3) / 4; q++) rcw[q] = 0;
-#pragma unroll
-    for (int k = 0; k < CPT; k++) {
-        const int j = j0 + k;
-        const unsigned code = (j >= 1 && j < L) ? (rev ? read[L - 1 - j] : read[j - 1]) : 4u;
-        rcw[k / 4] |= code << (8 * (k % 4));
-    }
-    auto subs = [&](int lnz, int (&sv)[CPT]) {
-        const int32_t* srow = sh.sc + lnz * 8;
-#pragma unroll
-        for (int k = 0; k < CPT; k++) sv[k] = srow[(rcw[k / 4] >> (8 * (k % 4))) & 0xffu];
-    };
-
-    // ---- frame of the previously processed row, in registers
-    int pl[CPT], pb[CPT];
+    // ---- frame of the previously processed row, in registers: leader score, base - leader score, origin
+    int pl[CPT], pd[CPT];
     unsigned po[CPT];
-    int plm1, pbm1;
+    int plm1, pdm1;
     unsigned pom1;
     uint32_t lam, tidp, prev_row;
 
@@ -266,11 +298,11 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             pl[k] = (j0 + k) * gap;
-            pb[k] = 0;
+            pd[k] = -(j0 + k) * gap;
             po[k] = (unsigned)(j0 + k);
         }
         plm1 = (j0 - 1) * gap;
-        pbm1 = 0;
+        pdm1 = -(j0 - 1) * gap;
         pom1 = (unsigned)(j0 - 1);
         lam = g.alphas[base_row];
         tidp = 0;
@@ -292,7 +324,8 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 #pragma unroll
         for (int k = 0; k < CPT; k += 4) {
             *reinterpret_cast<int4*>(cx.ring_lead + o + k) = make_int4(pl[k], pl[k + 1], pl[k + 2], pl[k + 3]);
-            *reinterpret_cast<int4*>(cx.ring_base + o + k) = make_int4(pb[k], pb[k + 1], pb[k + 2], pb[k + 3]);
+            *reinterpret_cast<int4*>(cx.ring_base + o + k) =
+                make_int4(pl[k] + pd[k], pl[k + 1] + pd[k + 1], pl[k + 2] + pd[k + 2], pl[k + 3] + pd[k + 3]);
             *reinterpret_cast<uint2*>(cx.ring_org + o + k) = make_uint2(po[k] | (po[k + 1] << 16), po[k + 2] | (po[k + 3] << 16));
         }
         if (tid == 0) cx.ring_meta[row & RM] = make_uint4(lam, tidp, 0u, 0u);
@@ -356,12 +389,15 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
     };
 
     int par = 0;
-    PwtRow rnext = g.rows[rev ? n - 2 : 1];
+    uint4 rnext = reinterpret_cast<const uint4*>(g.rows)[rev ? n - 2 : 1];
     for (uint32_t t = 1; t + 1 < n; t++) {
         const uint32_t i = rev ? n - 1 - t : t;
-        const PwtRow r = rnext;
-        if (t + 2 < n) rnext = g.rows[rev ? i - 1 : i + 1];
+        PwtRow r;
+        r.pred = rnext.x, r.g0 = rnext.y, r.tid = rnext.z;
+        r.leader = (uint16_t)(rnext.w & 0xffffu), r.lnz = (uint8_t)((rnext.w >> 16) & 0xffu), r.kind = (uint8_t)(rnext.w >> 24);
+        if (t + 2 < n) rnext = reinterpret_cast<const uint4*>(g.rows)[rev ? i - 1 : i + 1];
         const int32_t nmh = d.cb ? g.nonmem_hi[i] : -1;
+        const long long tm0 = (cx.mcyc && !(r.kind & PWT_T)) ? clock64() : 0;
         if (r.kind & PWT_T) {
             // ================= transport row =================
             if (r.pred != prev_row) {
@@ -372,12 +408,12 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                     const int4 bb = *reinterpret_cast<const int4*>(cx.ring_base + o + k);
                     const uint2 oo = *reinterpret_cast<const uint2*>(cx.ring_org + o + k);
                     pl[k] = a.x, pl[k + 1] = a.y, pl[k + 2] = a.z, pl[k + 3] = a.w;
-                    pb[k] = bb.x, pb[k + 1] = bb.y, pb[k + 2] = bb.z, pb[k + 3] = bb.w;
+                    pd[k] = bb.x - a.x, pd[k + 1] = bb.y - a.y, pd[k + 2] = bb.z - a.z, pd[k + 3] = bb.w - a.w;
                     po[k] = oo.x & 0xffffu, po[k + 1] = oo.x >> 16, po[k + 2] = oo.y & 0xffffu, po[k + 3] = oo.y >> 16;
                 }
                 if (tid > 0) {
                     plm1 = cx.ring_lead[o - 1];
-                    pbm1 = cx.ring_base[o - 1];
+                    pdm1 = cx.ring_base[o - 1] - plm1;
                     pom1 = cx.ring_org[o - 1];
                 }
                 const uint4 mt = cx.ring_meta[r.pred & RM];
@@ -389,8 +425,16 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                 // the leader of this row is not the path the frame's leader scores belong to: S[p][j][a] = base + T[a][org]
                 const int32_t* Ta = Tp + (size_t)r.leader * LT;
 #pragma unroll
-                for (int k = 0; k < CPT; k++) pl[k] = pb[k] + Ta[po[k]];
-                if (tid > 0) plm1 = pbm1 + Ta[pom1];
+                for (int k = 0; k < CPT; k++) {
+                    const int tv = Ta[po[k]];
+                    pl[k] += pd[k] + tv;
+                    pd[k] = -tv;
+                }
+                if (tid > 0) {
+                    const int tv = Ta[pom1];
+                    plm1 += pdm1 + tv;
+                    pdm1 = -tv;
+                }
                 lam = r.leader;
             }
             if (d.cb && (r.kind & PWT_MXREBUILD)) {
@@ -420,65 +464,92 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                     cx.s_mx[ZC] = make_int2(0, hq);
                 }
             }
-            int sv[CPT], nl[CPT];
-            subs(r.lnz, sv);
-            unsigned dbits, lbits;
-            int lead_left;
-            const int m0 = free_border ? 0 : pl[0] + gap;
-            leader_dp<CPT>(pl, plm1, sv, gap, m0, j0, sh.totA, nl, dbits, lbits, lead_left);
-            last_issue(par ^ 1);   // the previous row's last-column record is visible now (barrier inside leader_dp)
-            // origin / base of the cells that are not L moves; L cells copy from the left
-            unsigned no[CPT];
-            int dl[CPT];
-            unsigned curno = 0;
-            int curdl = 0;
+            // ---- phase A: candidates, the chain inside my columns as if nothing came in from the left, and for every cell
+            // the (origin, base - leader) it copies: from the diagonal / vertical source, or from its left neighbour on an L move
+            int nl[CPT];
+            unsigned dbits = 0;
+            {
+                int sv[CPT];
+                ss.get(r.lnz, sh.sc, sv);
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    const int dd = ((k == 0) ? plm1 : pl[k - 1]) + sv[k];
+                    const int uu = pl[k] + gap;
+                    nl[k] = max(dd, uu);
+                    if (dd >= uu) dbits |= 1u << k;   // equality tests in the order d, u, l (…_semiglobal.rs:46-57)
+                }
+            }
+            if (tid == 0) {
+                nl[0] = free_border ? 0 : pl[0] + gap;
+                dbits &= ~1u;
+            }
+            unsigned lbits = 0;
+            unsigned old_o = pom1, cur_o = 0, src_o = 0;
+            int old_d = pdm1, cur_d = 0, src_d = 0, srcc = 0;
 #pragma unroll
             for (int k = 0; k < CPT; k++) {
-                if (!((lbits >> k) & 1u)) {
+                const unsigned o_k = po[k];
+                const int d_k = pd[k];
+                const bool isL = (k > 0) && (nl[k - 1] + gap > nl[k]);
+                unsigned no;
+                int nd;
+                if (isL) {
+                    nl[k] = nl[k - 1] + gap;
+                    no = cur_o;
+                    nd = cur_d;
+                    lbits |= 1u << k;
+                } else {
                     const bool isD = (dbits >> k) & 1u;
-                    unsigned so = isD ? ((k == 0) ? pom1 : po[k - 1]) : po[k];
-                    int sb = isD ? ((k == 0) ? pbm1 : pb[k - 1]) + sv[k] : pb[k] + gap;
+                    no = isD ? old_o : o_k;
+                    nd = isD ? old_d : d_k;
                     if (k == 0 && tid == 0 && free_border) {
-                        so = ZC;
-                        sb = 0;
+                        no = ZC;
+                        nd = 0;
                     }
-                    curno = so;
-                    curdl = sb - nl[k];
+                    srcc = k;
+                    src_o = no;
+                    src_d = nd;
                 }
-                no[k] = curno;
-                dl[k] = curdl;
+                po[k] = no;
+                pd[k] = nd;
+                cur_o = no;
+                cur_d = nd;
+                old_o = o_k;
+                old_d = d_k;
             }
-            const unsigned nonl = ~lbits & ALL;
-            const int first = nonl ? __ffs(nonl) - 1 : CPT;
-            const unsigned key2 = nonl ? (((unsigned)(j0 + 31 - __clz(nonl)) << 16) | curno) : 0u;
-            sh.dlt[tid] = curdl;
-            const unsigned exc2 = block_excl_max_u(key2, sh.totB);
-            const unsigned org_in = exc2 & 0xffffu;
-            const int dl_in = sh.dlt[(exc2 >> 16) / CPT];
-            unsigned code[CPT];
+            // ---- one scan: (normalised chain value, column, origin) of the best source left of my columns; ties go to the
+            // right-most source, which is exactly the cell where the reference's strict `l > max(d, u)` test stops an L run
+            const long long key = ((long long)(nl[CPT - 1] - (j0 + CPT - 1) * gap) << 32) |
+                                  (long long)(((unsigned)(j0 + srcc) << 16) | src_o);
+            sh.dlt[par][tid] = src_d;
+            const long long exc = block_excl_max_k(key, sh.totK[par], KNONE);
+            last_issue(par ^ 1);   // the previous row's last-column record is visible now
+            const int lc_in = (tid == 0) ? NEG_INF : (int)(exc >> 32) + j0 * gap;   // lead[j0 - 1] + gap
+            const unsigned org_in = (unsigned)exc & 0xffffu;
+            const int dl_in = sh.dlt[par][(((unsigned)exc >> 16) & 0xffffu) / CPT];
+            // ---- phase B: the incoming chain overrides a prefix of my cells (it loses `gap` per column like every chain)
 #pragma unroll
             for (int k = 0; k < CPT; k++) {
-                if (k < first) {
-                    no[k] = org_in;
-                    dl[k] = dl_in;
+                const int inc = lc_in + k * gap;
+                if (inc > nl[k]) {
+                    nl[k] = inc;
+                    po[k] = org_in;
+                    pd[k] = dl_in;
+                    lbits |= 1u << k;
                 }
-                code[k] = ((lbits >> k) & 1u) ? (unsigned)MV_L : (((dbits >> k) & 1u) ? (unsigned)MV_D : (unsigned)MV_U);
             }
-            store_codes<CPT>(d.mv + (size_t)r.g0 * (LP / 4), tid, code);
+            store_planes2<CPT>(d.mv + (size_t)r.g0 * (LP / 4), tid, lbits, dbits);
 #pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                pl[k] = nl[k];
-                pb[k] = nl[k] + dl[k];
-                po[k] = no[k];
-            }
-            plm1 = lead_left;
+            for (int k = 0; k < CPT; k++) pl[k] = nl[k];
+            plm1 = lc_in - gap;
             pom1 = org_in;
-            pbm1 = lead_left + dl_in;
+            pdm1 = dl_in;
         } else {
             // ================= materialising row: several incoming edges =================
             const uint32_t g0 = r.g0, g1 = g.grp_off[i + 1];
             int32_t* Tn = cx.tables + (size_t)(r.tid & TM) * tstride;
             bool first_sync = true;
+            __syncthreads();   // the previous row's ring copy (frame + meta, written in its tail) must be visible to every thread
             for (uint32_t gi = g0; gi < g1; gi++) {
                 const PwGroup gr = g.grp[gi];
                 const uint32_t a = gr.leader;
@@ -513,19 +584,17 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                 }
                 const int Am1 = tid ? cx.s_A[j0 - 1] : NEG_INF;
                 int sv[CPT], nl[CPT];
-                subs(r.lnz, sv);
+                ss.get(r.lnz, sh.sc, sv);
                 unsigned dbits, lbits;
                 int lead_left;
                 const int m0 = free_border ? 0 : A[0] + gap;
                 leader_dp<CPT>(A, Am1, sv, gap, m0, j0, sh.totA, nl, dbits, lbits, lead_left);
-                unsigned code[CPT];
 #pragma unroll
                 for (int k = 0; k < CPT; k++) {
-                    code[k] = ((lbits >> k) & 1u) ? (unsigned)MV_L : (((dbits >> k) & 1u) ? (unsigned)MV_D : (unsigned)MV_U);
-                    cx.s_mv[j0 + k] = (uint8_t)code[k];
+                    cx.s_mv[j0 + k] = (uint8_t)(((lbits >> k) & 1u) ? (unsigned)MV_L : (((dbits >> k) & 1u) ? (unsigned)MV_D : (unsigned)MV_U));
                     cx.s_A[j0 + k] = sv[k];   // the member pass reads the substitution scores from here
                 }
-                store_codes<CPT>(d.mv + (size_t)gi * (LP / 4), tid, code);
+                store_planes2<CPT>(d.mv + (size_t)gi * (LP / 4), tid, lbits, dbits);
                 __syncthreads();
                 // ---- members apply the leader's move: one warp per path, lane owns 8 consecutive columns of a 256-column
                 // tile. A cell whose move is D or U depends only on the predecessor row; an L run inside the lane is a serial
@@ -606,11 +675,11 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                 }
 #pragma unroll
                 for (int k = 0; k < CPT; k++) {
-                    pb[k] = 0;
+                    pd[k] = -pl[k];
                     po[k] = (unsigned)(j0 + k);
                 }
                 if (tid > 0) plm1 = Tl[-1];
-                pbm1 = 0;
+                pdm1 = -plm1;
                 pom1 = (unsigned)(j0 - 1);
             }
             if (d.cb) {
@@ -646,7 +715,7 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int2 mx = cx.s_mx[po[k + h]];
-                    int val = pb[k + h] + mx.x, path = mx.y;
+                    int val = pl[k + h] + pd[k + h] + mx.x, path = mx.y;
                     bool memb = true;
                     // slots of paths that do not go through the row hold 0 (as in the reference); highest path id wins ties
                     if (nmh >= 0 && (0 > val || (0 == val && nmh > path))) {
@@ -659,14 +728,15 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                 *reinterpret_cast<int4*>(out + k) = make_int4(e[0].x, e[0].y, e[1].x, e[1].y);
             }
         }
+        if (cx.mcyc && !(r.kind & PWT_T)) *cx.mcyc += clock64() - tm0;
         if (r.kind & PWT_RING) ring_store(i);
         if (want_last && j0 <= L - 1 && L - 1 < j0 + CPT) {
             LastRec lr;
-            lr.base = pb[0];
+            lr.base = pl[0] + pd[0];
             lr.org = po[0];
 #pragma unroll
             for (int k = 1; k < CPT; k++)
-                if (j0 + k == L - 1) lr.base = pb[k], lr.org = po[k];
+                if (j0 + k == L - 1) lr.base = pl[k] + pd[k], lr.org = po[k];
             lr.row = i;
             lr.tid = tidp;
             sh.last[par] = lr;
@@ -684,27 +754,22 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 // Scores of ONE path replayed from the stored leader moves, rows up to `limit` (inclusive) in processing order; writes the
 // path's own arg-max code (build_alignment's order: d, then u, else l — pathwise_alignment_output.rs:80-109) per cell and
 // the path's predecessor per row.
-template <int CPT>
+template <int CPT, bool SIMPLE>
 __device__ void pwt_replay(const DevPathGraph& g, const PwtCtx& cx, const uint8_t* mv, uint8_t* own, uint32_t* own_pred,
                            PwtShared& sh, const uint8_t* read, int L, bool rev, bool free_border, uint32_t q, uint32_t limit, int gap) {
     const int tid = threadIdx.x;
     const uint32_t n = g.n, PW = g.PW, LP = cx.LP;
     const int j0 = tid * CPT;
     constexpr unsigned ALL = (CPT >= 32) ? 0xffffffffu : ((1u << (CPT % 32)) - 1u);
-    unsigned rcw[(CPT + 3) / 4];
+    SubScores<CPT, SIMPLE> ss;
+    ss.init(read, L, j0, rev, sh.sc);
+    unsigned inread = 0;   // columns 1 .. L-1 among mine
 #pragma unroll
-    for (int w = 0; w < (CPT + 3) / 4; w++) rcw[w] = 0;
-#pragma unroll
-    for (int k = 0; k < CPT; k++) {
-        const int j = j0 + k;
-        const unsigned code = (j >= 1 && j < L) ? (rev ? read[L - 1 - j] : read[j - 1]) : 4u;
-        rcw[k / 4] |= code << (8 * (k % 4));
-    }
+    for (int k = 0; k < CPT; k++)
+        if (j0 + k >= 1 && j0 + k < L) inread |= 1u << k;
     int prev[CPT], prevm1 = (j0 - 1) * gap;
 #pragma unroll
     for (int k = 0; k < CPT; k++) prev[k] = (j0 + k) * gap;
-    const uint32_t base_row = rev ? n - 1 : 0;
-    uint32_t last_row = base_row;
     int par = 0;
     for (uint32_t t = 1; t + 1 < n; t++) {
         const uint32_t i = rev ? n - 1 - t : t;
@@ -717,28 +782,23 @@ __device__ void pwt_replay(const DevPathGraph& g, const PwtCtx& cx, const uint8_
                 if ((g.grp_mask[(size_t)gg * PW + q / 32] >> (q % 32)) & 1u) gi = gg;
             pred = g.grp[gi].pred;
         }
-        (void)last_row;
-        unsigned code[CPT];
-        load_codes<CPT>(mv + (size_t)gi * (LP / 4), tid, code);
-        const int32_t* srow = sh.sc + r.lnz * 8;
+        unsigned lbits, dbits;
+        load_planes2<CPT>(mv + (size_t)gi * (LP / 4), tid, lbits, dbits);
+        if (tid == 0) lbits &= ~1u;
         // reverse pass: the 'F' row is never made absolute by the reference (absolute_scores stops before it,
         // pathwise_alignment_recombination.rs:748), so its traceback sees 0 for every path but path 0
         const bool quirk = rev && pred == n - 1 && q != 0;
         int sv[CPT], cur[CPT];
-        unsigned lbits = 0;
+        ss.get(r.lnz, sh.sc, sv);
         int lastnorm = 0;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            sv[k] = srow[(rcw[k / 4] >> (8 * (k % 4))) & 0xffu];
-            const int j = j0 + k;
-            const bool isL = j >= 1 && code[k] == MV_L;
-            if (isL) {
-                lbits |= 1u << k;
+            if ((lbits >> k) & 1u) {
                 cur[k] = (k == 0) ? 0 : cur[k - 1] + gap;
             } else {
-                cur[k] = (j == 0) ? (free_border ? 0 : prev[0] + gap)
-                                  : ((code[k] == MV_D) ? ((k == 0) ? prevm1 : prev[k - 1]) + sv[k] : prev[k] + gap);
-                lastnorm = cur[k] - j * gap;
+                cur[k] = ((dbits >> k) & 1u) ? ((k == 0) ? prevm1 : prev[k - 1]) + sv[k] : prev[k] + gap;
+                if (k == 0 && tid == 0) cur[0] = free_border ? 0 : prev[0] + gap;
+                lastnorm = cur[k] - (j0 + k) * gap;
             }
         }
         const unsigned nonl = ~lbits & ALL;
@@ -748,41 +808,47 @@ __device__ void pwt_replay(const DevPathGraph& g, const PwtCtx& cx, const uint8_
         const unsigned exc = block_excl_max_u(key, sh.tot2[par]);
         const int vin = (tid == 0) ? 0 : sh.val[par][(exc - 1) / CPT];
         const int cur_left = vin + (j0 - 1) * gap;   // S[i][j0-1][q]
-        unsigned oc[CPT];
 #pragma unroll
-        for (int k = 0; k < CPT; k++) {
+        for (int k = 0; k < CPT; k++)
             if (k < first) cur[k] = vin + (j0 + k) * gap;
-        }
+        unsigned od = 0, ou = 0;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            const int j = j0 + k;
             const int spl = (k == 0) ? prevm1 : prev[k - 1];
             const int lq = ((k == 0) ? cur_left : cur[k - 1]) + gap;
             const int dq = (quirk ? 0 : spl) + sv[k], uq = (quirk ? 0 : prev[k]) + gap;
             const int bq = max(dq, max(uq, lq));
-            oc[k] = (j >= 1 && j < L) ? ((bq == dq) ? (unsigned)MV_D : ((bq == uq) ? (unsigned)MV_U : (unsigned)MV_L)) : 0u;
+            if (bq == dq)
+                od |= 1u << k;
+            else if (bq == uq)
+                ou |= 1u << k;
         }
-        store_codes<CPT>(own + (size_t)i * (LP / 4), tid, oc);
+        store_planes2<CPT>(own + (size_t)i * (LP / 4), tid, od & inread, ou & inread);
         if (tid == 0) own_pred[i] = pred;
         prevm1 = cur_left;
 #pragma unroll
         for (int k = 0; k < CPT; k++) prev[k] = cur[k];
-        last_row = i;
         par ^= 1;
     }
     __syncthreads();
 }
 
+// own arg-max of the replayed path at (row, col): MV_D / MV_U / MV_L
+template <int CPT>
 __device__ __forceinline__ unsigned own_code(const uint8_t* own, uint32_t LP, uint32_t row, int col) {
-    return (own[(size_t)row * (LP / 4) + (uint32_t)col / 4] >> (2 * (col % 4))) & 3u;
+    unsigned a, b;
+    load_planes2<CPT>(own + (size_t)row * (LP / 4), col / CPT, a, b);
+    const int k = col % CPT;
+    return ((a >> k) & 1u) ? (unsigned)MV_D : (((b >> k) & 1u) ? (unsigned)MV_U : (unsigned)MV_L);
 }
 
 // Forward-direction walk shared by build_alignment (pathwise_alignment_output.rs:7-184), the no_rec builders
 // (recombination_output.rs:239-361,633-782) and the forward half of the rec builders (:100-163,472-557).
+template <int CPT>
 __device__ void pwt_walk_fwd(const DevPathGraph& g, const uint8_t* own, const uint32_t* own_pred, uint32_t LP, const uint8_t* read,
                              uint32_t& ii, int& j, bool pad_global, RunEmitter& em) {
     while (ii > 0 && j > 0) {
-        const unsigned code = own_code(own, LP, ii, j);
+        const unsigned code = own_code<CPT>(own, LP, ii, j);
         if (code == MV_D) {
             em.step(g.lnz[ii] != read[j - 1] ? RG_OP_d : RG_OP_D, ii, 0);
             ii = own_pred[ii];
@@ -830,7 +896,7 @@ __device__ __forceinline__ void rec_merge2(RecBest& a, const RecBest& o) {
     }
 }
 
-template <int CPT>
+template <int CPT, bool SIMPLE>
 __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
     k_pathwise_tr(DevPathGraph g, DevPathGraph rg_, DevScoring sc, PwtWorkspace ws, PoaBatch b, int mode) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -915,9 +981,15 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
             cx.s_end[q] = 0;
         }
         __syncthreads();
-        pwt_pass<CPT>(g, cx, fwd, sh, read, L, false, !global_mode, mode == RG_MODE_PATHWISE_SEMIGLOBAL,
-                      mode == RG_MODE_PATHWISE_GLOBAL, mode != RG_MODE_PATHWISE_GLOBAL || true, gap);
-        if (rec_mode) pwt_pass<CPT>(rg_, cx, rvd, sh, read, L, true, !global_mode, false, false, false, gap);
+        long long mcyc = 0;
+        cx.mcyc = ws.diag ? &mcyc : nullptr;
+        const long long tc0 = clock64();
+        pwt_pass<CPT, SIMPLE>(g, cx, fwd, sh, read, L, false, !global_mode, mode == RG_MODE_PATHWISE_SEMIGLOBAL,
+                      mode == RG_MODE_PATHWISE_GLOBAL, true, gap);
+        const long long tc1 = clock64();
+        if (rec_mode) pwt_pass<CPT, SIMPLE>(rg_, cx, rvd, sh, read, L, true, !global_mode, false, false, false, gap);
+        const long long tc2 = clock64();
+        long long tc3 = tc2;
 
         if (!rec_mode) {
             // ================= modes 4 / 5: end cell, replay of the chosen path, traceback (thread 0), publish =================
@@ -936,7 +1008,7 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
                 score = sh.best_val;
             }
             __syncthreads();
-            pwt_replay<CPT>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, !global_mode, best_path, ending, gap);
+            pwt_replay<CPT, SIMPLE>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, !global_mode, best_path, ending, gap);
             if (tid == 0) {
                 res.score = score;
                 res.best_path = best_path;
@@ -946,7 +1018,7 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
                 em.init(runs, ws.run_cap);
                 uint32_t ii = ending;
                 int j = L - 1;
-                pwt_walk_fwd(g, own, own_pred, LP, read, ii, j, global_mode, em);
+                pwt_walk_fwd<CPT>(g, own, own_pred, LP, read, ii, j, global_mode, em);
                 em.flush(0);
                 res.start_row = ii;
                 if (em.overflow) res.status |= RG_READ_TRACE_OVERFLOW;
@@ -959,6 +1031,11 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
                 for (uint32_t k = 0; k < nr; k++) b.out_runs[ro + k] = runs[k];
                 res.run_off = ro;
                 res.n_runs = nr;
+                if (ws.diag) {   // kilo-cycles: forward pass, materialising rows, replay + walk
+                    res.fen = (uint32_t)((tc1 - tc0) >> 10);
+                    res.rsn = (uint32_t)(mcyc >> 10);
+                    res.rev_end_row = (uint32_t)((clock64() - tc2) >> 10);
+                }
                 b.results[ridx] = res;
             }
             __syncthreads();
@@ -1141,6 +1218,7 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
             }
             __syncthreads();
         }
+        tc3 = clock64();
         // 4. outcome (every thread derives it: the replays below are CTA-wide)
         const float basef = (float)base_score;
         // sequential acceptance rule restated: a candidate is taken if it beats the incumbent, or ties it while
@@ -1177,7 +1255,7 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
                 ekey = block_max_ll(ekey, sh);
                 ending = (ekey == LLONG_MIN) ? 0u : 0xffffffffu - (uint32_t)(ekey & 0xffffffffll);
             }
-            pwt_replay<CPT>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, !global_mode, base_path, ending, gap);
+            pwt_replay<CPT, SIMPLE>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, !global_mode, base_path, ending, gap);
             if (tid == 0) {
                 res.best_path = res.rev_best_path = base_path;
                 res.end_row = ending;
@@ -1186,7 +1264,7 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
                 res.score_f32 = (float)base_score;
                 uint32_t ii = ending;
                 int j = L - 1;
-                pwt_walk_fwd(g, own, own_pred, LP, read, ii, j, mode == RG_MODE_REC_GLOBAL, em);
+                pwt_walk_fwd<CPT>(g, own, own_pred, LP, read, ii, j, mode == RG_MODE_REC_GLOBAL, em);
                 em.flush(0);
                 res.start_row = ii;
                 res.n_runs = em.n;
@@ -1195,7 +1273,7 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
             const uint32_t rcol = (uint32_t)(key >> 42), fen = (uint32_t)((key >> 21) & 0x1fffffu), rsn = (uint32_t)(key & 0x1fffffu);
             const uint32_t fp = (uint32_t)fwd.cb[(size_t)fen * LP + rcol].y & 0x7fffffffu;
             const uint32_t rp = (uint32_t)rvd.cb[(size_t)rsn * LP + (L - 1 - rcol)].y & 0x7fffffffu;
-            pwt_replay<CPT>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, !global_mode, fp, fen, gap);
+            pwt_replay<CPT, SIMPLE>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, !global_mode, fp, fen, gap);
             uint32_t ii = fen;
             if (tid == 0) {
                 res.status |= RG_READ_RECOMBINATION;
@@ -1208,13 +1286,13 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
                 res.displacement = abs(g.dfs[fen] - g.dfs[rsn]) + abs(g.dfe[fen] - g.dfe[rsn]);
                 // forward half, traceback order (recombination_output.rs:100-163 / 472-557)
                 int j = (int)rcol;
-                pwt_walk_fwd(g, own, own_pred, LP, read, ii, j, mode == RG_MODE_REC_GLOBAL, em);
+                pwt_walk_fwd<CPT>(g, own, own_pred, LP, read, ii, j, mode == RG_MODE_REC_GLOBAL, em);
                 em.flush(0);
                 res.start_row = ii;
                 res.n_runs = em.n;
             }
             __syncthreads();   // the walk is done with the own-code buffer before the reverse replay rewrites it
-            pwt_replay<CPT>(rg_, cx, rvd.mv, own, own_pred, sh, read, L, true, !global_mode, rp, rsn, gap);
+            pwt_replay<CPT, SIMPLE>(rg_, cx, rvd.mv, own, own_pred, sh, read, L, true, !global_mode, rp, rsn, gap);
             if (tid == 0) {
                 // reverse half, forward order (:38-98 / 389-470): rows ascend
                 em.ascending = true;
@@ -1222,7 +1300,7 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
                 int cj = (int)rcol;
                 uint32_t rev_end = ri;
                 while (ri > 0 && ri < n - 1 && cj < L - 1) {
-                    const unsigned code = own_code(own, LP, ri, L - 1 - cj);
+                    const unsigned code = own_code<CPT>(own, LP, ri, L - 1 - cj);
                     rev_end = ri;
                     if (code == MV_D) {
                         em.step(g.lnz[ri] != read[cj] ? RG_OP_d : RG_OP_D, ri, 0);  // r_seq[j] = seq[j+1]
@@ -1263,6 +1341,13 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
             for (uint32_t k = 0; k < nr; k++) b.out_runs[ro + k] = runs[k];
             res.run_off = ro;
             if (nr == 0) res.n_runs = res.n_runs_rev = 0;
+            if (ws.diag) {   // kilo-cycles: forward pass, reverse pass, pair reduction, replay + walk; materialising rows
+                res.fen = (uint32_t)((tc1 - tc0) >> 10);
+                res.rsn = (uint32_t)((tc2 - tc1) >> 10);
+                res.rec_col = (uint32_t)((tc3 - tc2) >> 10);
+                res.rev_end_row = (uint32_t)((clock64() - tc3) >> 10);
+                res.displacement = (int32_t)(mcyc >> 10);
+            }
             b.results[ridx] = res;
         }
         __syncthreads();
@@ -1273,12 +1358,18 @@ size_t pwt_smem_bytes(const PwtWorkspace& ws, bool rec) {
     return (size_t)ws.LP * 11 + (size_t)ws.Pp * 8 + (rec ? (size_t)ws.LT * 8 : 0) + 16;
 }
 
-const void* pwt_kernel(uint32_t cpt) {
+bool pwt_simple(const DevScoring& s) {   // match/mismatch table of score_matrix.rs:35-66
+    for (int a = 0; a < 5; a++)
+        for (int b = 0; b < 5; b++)
+            if (s.sc[a][b] != ((a == b && a < 4) ? s.sc[0][0] : s.sc[0][1])) return false;
+    return true;
+}
+const void* pwt_kernel(uint32_t cpt, bool simple) {
     switch (cpt) {
-        case 4: return (const void*)k_pathwise_tr<4>;
-        case 8: return (const void*)k_pathwise_tr<8>;
-        case 16: return (const void*)k_pathwise_tr<16>;
-        case 32: return (const void*)k_pathwise_tr<32>;
+        case 4: return simple ? (const void*)k_pathwise_tr<4, true> : (const void*)k_pathwise_tr<4, false>;
+        case 8: return simple ? (const void*)k_pathwise_tr<8, true> : (const void*)k_pathwise_tr<8, false>;
+        case 16: return simple ? (const void*)k_pathwise_tr<16, true> : (const void*)k_pathwise_tr<16, false>;
+        case 32: return simple ? (const void*)k_pathwise_tr<32, true> : (const void*)k_pathwise_tr<32, false>;
         default: return nullptr;
     }
 }
@@ -1296,21 +1387,22 @@ int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_,
     cudaStream_t st = (cudaStream_t)stream;
     const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
     const size_t smem = pwt_smem_bytes(ws, rec);
-    const void* k = pwt_kernel(ws.CPT);
+    const void* k = pwt_kernel(ws.CPT, pwt_simple(s));
     if (smem > 200 * 1024 || !k) return -3;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    switch (ws.CPT) {
-        case 4: k_pathwise_tr<4><<<blocks, NT, smem, st>>>(g, rg_, s, ws, b, mode); break;
-        case 8: k_pathwise_tr<8><<<blocks, NT, smem, st>>>(g, rg_, s, ws, b, mode); break;
-        case 16: k_pathwise_tr<16><<<blocks, NT, smem, st>>>(g, rg_, s, ws, b, mode); break;
-        default: k_pathwise_tr<32><<<blocks, NT, smem, st>>>(g, rg_, s, ws, b, mode); break;
-    }
+    DevPathGraph ga = g, gb = rg_;
+    DevScoring sa = s;
+    PwtWorkspace wa = ws;
+    PoaBatch ba = b;
+    int ma = mode;
+    void* args[] = {&ga, &gb, &sa, &wa, &ba, &ma};
+    if (cudaLaunchKernel(k, dim3(blocks), dim3(NT), args, smem, st) != cudaSuccess) return -1;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int pathwise_tr_blocks_per_sm(const DevPathGraph&, const DevPathGraph&, const PwtWorkspace& ws, bool rec, int* nb) {
+int pathwise_tr_blocks_per_sm(const DevPathGraph&, const DevPathGraph&, const DevScoring& s, const PwtWorkspace& ws, bool rec, int* nb) {
     const size_t smem = pwt_smem_bytes(ws, rec);
-    const void* k = pwt_kernel(ws.CPT);
+    const void* k = pwt_kernel(ws.CPT, pwt_simple(s));
     if (smem > 200 * 1024 || !k) return -3;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, NT, smem) == cudaSuccess ? 0 : -1;
