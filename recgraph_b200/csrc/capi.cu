@@ -220,6 +220,9 @@ static void build_pwt_rows(const FlatGraph& f, const std::vector<uint32_t>& grp_
     for (uint32_t i = 0; i < n; i++) {
         rows[i].g0 = grp_off[i];
         rows[i].lnz = f.lnz[i];
+        rows[i].nmh = 255;
+        for (uint32_t q = 0; q < f.P; q++)
+            if (!((f.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u)) rows[i].nmh = (uint8_t)q;
     }
     uint32_t next_id = 1, need = 2;
     rows[base_row].tid = 0;
@@ -241,7 +244,7 @@ static void build_pwt_rows(const FlatGraph& f, const std::vector<uint32_t>& grp_
         if (transport) {
             r.kind |= PWT_T;
             r.pred = grp[g0].pred;
-            r.leader = (uint16_t)grp[g0].leader;
+            r.leader = (uint8_t)grp[g0].leader;
             r.tid = rows[r.pred].tid;
             if (r.pred != prev) rows[r.pred].kind |= PWT_RING;
             if (r.tid != mx_tid || !same_set(nb, mx_set.data())) {
@@ -746,7 +749,7 @@ static int align_pathwise(rg_ctx* c, int mode) {
     ws.run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * ws.LP), 1u << 22);
     ws.diag = getenv("RG_PW_DIAG") ? 1u : 0u;
     int bps = 1;
-    int lc = pathwise_tr_blocks_per_sm(c->dpg, c->dpg_rev, c->ds, ws, rec, &bps);
+    int lc = pathwise_tr_blocks_per_sm(c->dpg, c->dpg_rev, c->ds, ws, mode != RG_MODE_PATHWISE_GLOBAL, &bps);
     if (lc == -3) return align_pathwise_v1(c, mode);
     if (lc != 0) return c->cuda_fail("kernel configuration");
     if (bps < 1) bps = 1;

@@ -118,7 +118,8 @@ struct PwtRow {
     uint32_t pred;     // predecessor row of the single group (transport rows)
     uint32_t g0;       // first group of the row (== grp_off[row])
     uint32_t tid;      // id of the table the row's frame refers to (materialising rows: the table they create)
-    uint16_t leader;   // leader path of the single group
+    uint8_t leader;    // leader path of the single group (P <= 128)
+    uint8_t nmh;       // highest path id that does NOT go through the row, 255: every path does
     uint8_t lnz;
     uint8_t kind;      // PWT_* bits
 };

@@ -265,10 +265,42 @@ struct SubScores {
     }
 };
 
+// Per-origin maxima over the member paths of row i of table T: s_mx[c] = {max_q T[q][c], highest q with it | lowest q << 16}
+// (modes 8/9 take the highest path id on ties, …_recombination.rs:809-830; the best end of modes 5/9 the lowest).
+template <int CPT>
+__device__ __forceinline__ void build_mx(const DevPathGraph& g, const PwtCtx& cx, const int32_t* T, uint32_t i, int j0, unsigned ZC) {
+    int bv[CPT];
+    unsigned bq[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) bv[k] = INT_MIN, bq[k] = 0;
+    unsigned lo = 0xffffu, hi = 0;
+    for (uint32_t q = 0; q < g.P; q++) {
+        if (!((g.node_bits[(size_t)i * g.PW + q / 32] >> (q % 32)) & 1u)) continue;
+        if (lo == 0xffffu) lo = q;
+        hi = q;
+        const int32_t* Tq = T + (size_t)q * cx.LT + j0;
+#pragma unroll
+        for (int k = 0; k < CPT; k += 4) {
+            const int4 v = *reinterpret_cast<const int4*>(Tq + k);
+            const int vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (vv[e] > bv[k + e])
+                    bv[k + e] = vv[e], bq[k + e] = q | (q << 16);
+                else if (vv[e] == bv[k + e])
+                    bq[k + e] = (bq[k + e] & 0xffff0000u) | q;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; k++) cx.s_mx[j0 + k] = make_int2(bv[k], (int)bq[k]);
+    if (threadIdx.x == 0) cx.s_mx[ZC] = make_int2(0, (int)(hi | (lo << 16)));
+}
+
 // One DP pass over all rows of one direction.
 template <int CPT, bool SIMPLE>
 __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBufs& d, PwtShared& sh, const uint8_t* read,
-                         int L, bool rev, bool free_border, bool track_best, bool track_results, bool want_last, int gap) {
+                         int L, bool rev, bool free_border, bool track_best, bool track_results, bool fpred_rows, int gap) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = g.n, P = g.P, PW = g.PW, RM = g.ring - 1, TM = g.TR - 1;
     const uint32_t LP = cx.LP, LT = cx.LT, Pp = cx.Pp;
@@ -277,6 +309,7 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
     const size_t tstride = (size_t)Pp * LT;
     const uint32_t base_row = rev ? n - 1 : 0;
     const long long KNONE = (long long)NEG_INF << 32;
+    const bool need_mx = track_best || d.cb != nullptr;
     SubScores<CPT, SIMPLE> ss;
     ss.init(read, L, j0, rev, sh.sc);
 
@@ -307,17 +340,21 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
         lam = g.alphas[base_row];
         tidp = 0;
         prev_row = base_row;
-        if (d.cb) {
+        if (need_mx) {   // s_mx entry: {max over the member paths, highest path with it | lowest path with it << 16}
 #pragma unroll
             for (int k = 0; k < CPT; k++) cx.s_mx[j0 + k] = make_int2((j0 + k) * gap, (int)P - 1);
             if (tid == 0) cx.s_mx[ZC] = make_int2(0, (int)P - 1);
         }
-        if (d.lastcol)
-            for (uint32_t q = tid; q < Pp; q += NT) d.lastcol[(size_t)base_row * Pp + q] = (q < P) ? (L - 1) * gap : 0;
-        if (tid == 0) {
-            sh.last[0].row = 0xffffffffu;
-            sh.last[1].row = 0xffffffffu;
-        }
+    }
+    // running best end cell (mode 5: …_semiglobal.rs:244-277; mode 9 baseline: …_recombination.rs:790-799, which also
+    // scans row 0): kept by the thread that owns column L-1
+    const bool own_last = j0 <= L - 1 && L - 1 < j0 + CPT;
+    bool bset = false;
+    int bval = 0;
+    uint32_t brow = 0, bpath = 0;
+    if (track_best && d.cb) {
+        bset = true;
+        bval = (L - 1) * gap;
     }
     auto ring_store = [&](uint32_t row) {
         const size_t o = (size_t)(row & RM) * LP + j0;
@@ -333,70 +370,16 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
     if (g.rows[base_row].kind & PWT_RING) ring_store(base_row);
     __syncthreads();
 
-    // the last warp turns the last-column cell of a finished row into per-path scores (one barrier after the row)
-    int lv[4];
-    unsigned lrow = 0xffffffffu;
-    auto last_issue = [&](int par) {
-        lrow = 0xffffffffu;
-        if (!want_last || warp != NWP - 1) return;
-        const LastRec lr = sh.last[par];
-        lrow = lr.row;
-        if (lrow == 0xffffffffu) return;
-        const int32_t* T = cx.tables + (size_t)(lr.tid & TM) * tstride;
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            const uint32_t q = lane + 32 * w;
-            lv[w] = 0;
-            if (w < (int)PW && q < P && ((g.node_bits[(size_t)lrow * PW + w] >> lane) & 1u)) lv[w] = lr.base + T[(size_t)q * LT + lr.org];
-        }
-    };
-    auto last_finish = [&]() {
-        if (lrow == 0xffffffffu) return;
-        long long key = -(1ll << 62);
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            const uint32_t q = lane + 32 * w;
-            if (w < (int)PW && q < Pp) {
-                const bool memb = q < P && ((g.node_bits[(size_t)lrow * PW + w] >> lane) & 1u);
-                if (d.lastcol) d.lastcol[(size_t)lrow * Pp + q] = memb ? lv[w] : 0;
-                if (memb) {
-                    // first strict maximum in path order among the member paths (…_semiglobal.rs:256-265)
-                    key = max(key, ((long long)lv[w] << 8) | (long long)(255 - q));
-                    if (track_results && (g.rows[lrow].kind & PWT_FPRED))
-                        for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
-                            if (g.grp[fg].pred == lrow && ((g.grp_mask[(size_t)fg * PW + w] >> lane) & 1u)) {
-                                cx.s_res[q] = lv[w];   // pathwise_alignment.rs:305-319
-                                cx.s_end[q] = lrow;
-                            }
-                }
-            }
-        }
-        if (track_best) {
-#pragma unroll
-            for (int dl = 16; dl >= 1; dl >>= 1) key = max(key, __shfl_xor_sync(FULL, key, dl));
-            if (lane == 0 && key != -(1ll << 62)) {
-                // …_semiglobal.rs:269-273: a row replaces the incumbent only if strictly better
-                const int row_best = (int)(key >> 8);
-                if (!sh.best_set || row_best > sh.best_val) {
-                    sh.best_set = 1;
-                    sh.best_val = row_best;
-                    sh.best_row = lrow;
-                    sh.best_path = 255u - (uint32_t)(key & 0xff);
-                }
-            }
-        }
-        lrow = 0xffffffffu;
-    };
-
     int par = 0;
     uint4 rnext = reinterpret_cast<const uint4*>(g.rows)[rev ? n - 2 : 1];
     for (uint32_t t = 1; t + 1 < n; t++) {
         const uint32_t i = rev ? n - 1 - t : t;
         PwtRow r;
         r.pred = rnext.x, r.g0 = rnext.y, r.tid = rnext.z;
-        r.leader = (uint16_t)(rnext.w & 0xffffu), r.lnz = (uint8_t)((rnext.w >> 16) & 0xffu), r.kind = (uint8_t)(rnext.w >> 24);
+        r.leader = (uint8_t)(rnext.w & 0xffu), r.nmh = (uint8_t)((rnext.w >> 8) & 0xffu), r.lnz = (uint8_t)((rnext.w >> 16) & 0xffu),
+        r.kind = (uint8_t)(rnext.w >> 24);
         if (t + 2 < n) rnext = reinterpret_cast<const uint4*>(g.rows)[rev ? i - 1 : i + 1];
-        const int32_t nmh = d.cb ? g.nonmem_hi[i] : -1;
+        const int32_t nmh = r.nmh == 255 ? -1 : (int32_t)r.nmh;
         const long long tm0 = (cx.mcyc && !(r.kind & PWT_T)) ? clock64() : 0;
         if (r.kind & PWT_T) {
             // ================= transport row =================
@@ -437,32 +420,10 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                 }
                 lam = r.leader;
             }
-            if (d.cb && (r.kind & PWT_MXREBUILD)) {
+            if (need_mx && (r.kind & PWT_MXREBUILD)) {
                 // per-origin maxima over the paths of THIS row (its path set differs from the table's creator's)
                 __syncthreads();   // the previous row may still be reading s_mx
-                int bv[CPT], bq[CPT];
-#pragma unroll
-                for (int k = 0; k < CPT; k++) bv[k] = INT_MIN, bq[k] = 0;
-                for (uint32_t q = 0; q < P; q++) {
-                    if (!((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u)) continue;
-                    const int32_t* Tq = Tp + (size_t)q * LT + j0;
-#pragma unroll
-                    for (int k = 0; k < CPT; k += 4) {
-                        const int4 v = *reinterpret_cast<const int4*>(Tq + k);
-                        const int vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
-                            if (vv[e] >= bv[k + e]) bv[k + e] = vv[e], bq[k + e] = (int)q;   // highest path id wins ties
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < CPT; k++) cx.s_mx[j0 + k] = make_int2(bv[k], bq[k]);
-                if (tid == 0) {
-                    int hq = 0;
-                    for (uint32_t q = 0; q < P; q++)
-                        if ((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u) hq = (int)q;
-                    cx.s_mx[ZC] = make_int2(0, hq);
-                }
+                build_mx<CPT>(g, cx, Tp, i, j0, ZC);
             }
             // ---- phase A: candidates, the chain inside my columns as if nothing came in from the left, and for every cell
             // the (origin, base - leader) it copies: from the diagonal / vertical source, or from its left neighbour on an L move
@@ -523,7 +484,6 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                                   (long long)(((unsigned)(j0 + srcc) << 16) | src_o);
             sh.dlt[par][tid] = src_d;
             const long long exc = block_excl_max_k(key, sh.totK[par], KNONE);
-            last_issue(par ^ 1);   // the previous row's last-column record is visible now
             const int lc_in = (tid == 0) ? NEG_INF : (int)(exc >> 32) + j0 * gap;   // lead[j0 - 1] + gap
             const unsigned org_in = (unsigned)exc & 0xffffu;
             const int dl_in = sh.dlt[par][(((unsigned)exc >> 16) & 0xffffu) / CPT];
@@ -548,7 +508,6 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
             // ================= materialising row: several incoming edges =================
             const uint32_t g0 = r.g0, g1 = g.grp_off[i + 1];
             int32_t* Tn = cx.tables + (size_t)(r.tid & TM) * tstride;
-            bool first_sync = true;
             __syncthreads();   // the previous row's ring copy (frame + meta, written in its tail) must be visible to every thread
             for (uint32_t gi = g0; gi < g1; gi++) {
                 const PwGroup gr = g.grp[gi];
@@ -578,10 +537,6 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                     }
                 }
                 __syncthreads();
-                if (first_sync) {
-                    last_issue(par ^ 1);
-                    first_sync = false;
-                }
                 const int Am1 = tid ? cx.s_A[j0 - 1] : NEG_INF;
                 int sv[CPT], nl[CPT];
                 ss.get(r.lnz, sh.sc, sv);
@@ -682,27 +637,8 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                 pdm1 = -plm1;
                 pom1 = (unsigned)(j0 - 1);
             }
-            if (d.cb) {
-                int bv[CPT], bq[CPT];
-#pragma unroll
-                for (int k = 0; k < CPT; k++) bv[k] = INT_MIN, bq[k] = 0;
-                int hq = 0;
-                for (uint32_t q = 0; q < P; q++) {
-                    if (!((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u)) continue;
-                    hq = (int)q;
-                    const int32_t* Tq = Tn + (size_t)q * LT + j0;
-#pragma unroll
-                    for (int k = 0; k < CPT; k += 4) {
-                        const int4 v = *reinterpret_cast<const int4*>(Tq + k);
-                        const int vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
-                            if (vv[e] >= bv[k + e]) bv[k + e] = vv[e], bq[k + e] = (int)q;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < CPT; k++) cx.s_mx[j0 + k] = make_int2(bv[k], bq[k]);
-                if (tid == 0) cx.s_mx[ZC] = make_int2(0, hq);
+            if (need_mx) {
+                build_mx<CPT>(g, cx, Tn, i, j0, ZC);
                 __syncthreads();
             }
         }
@@ -715,7 +651,7 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int2 mx = cx.s_mx[po[k + h]];
-                    int val = pl[k + h] + pd[k + h] + mx.x, path = mx.y;
+                    int val = pl[k + h] + pd[k + h] + mx.x, path = mx.y & 0xffff;
                     bool memb = true;
                     // slots of paths that do not go through the row hold 0 (as in the reference); highest path id wins ties
                     if (nmh >= 0 && (0 > val || (0 == val && nmh > path))) {
@@ -730,24 +666,60 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
         }
         if (cx.mcyc && !(r.kind & PWT_T)) *cx.mcyc += clock64() - tm0;
         if (r.kind & PWT_RING) ring_store(i);
-        if (want_last && j0 <= L - 1 && L - 1 < j0 + CPT) {
-            LastRec lr;
-            lr.base = pl[0] + pd[0];
-            lr.org = po[0];
+        if ((track_best || (fpred_rows && (r.kind & PWT_FPRED))) && own_last) {
+            int lbase = pl[0] + pd[0];
+            unsigned lorg = po[0];
 #pragma unroll
             for (int k = 1; k < CPT; k++)
-                if (j0 + k == L - 1) lr.base = pl[k] + pd[k], lr.org = po[k];
-            lr.row = i;
-            lr.tid = tidp;
-            sh.last[par] = lr;
+                if (j0 + k == L - 1) lbase = pl[k] + pd[k], lorg = po[k];
+            if (track_best) {
+                // best member path of the row = base + per-origin maximum; first strict maximum in path order (lowest id);
+                // a row replaces the incumbent only if strictly better (…_semiglobal.rs:256-273)
+                const int2 mx = cx.s_mx[lorg];
+                const int v = lbase + mx.x;
+                if (!bset || v > bval) {
+                    bset = true;
+                    bval = v;
+                    brow = i;
+                    bpath = (uint32_t)mx.y >> 16;
+                }
+            }
+            if (fpred_rows && (r.kind & PWT_FPRED)) {
+                LastRec lr;
+                lr.base = lbase, lr.org = lorg, lr.row = i, lr.tid = tidp;
+                sh.last[0] = lr;
+            }
         }
-        last_finish();
+        if (fpred_rows && (r.kind & PWT_FPRED)) {
+            // predecessor of the end row: per-path scores of its last column (mode 4 results, pathwise_alignment.rs:305-319;
+            // mode 8 baseline, …_recombination.rs:777-788). Rare rows: two extra barriers.
+            __syncthreads();
+            if (warp == 0) {
+                const LastRec lr = sh.last[0];
+                const int32_t* T = cx.tables + (size_t)(lr.tid & TM) * tstride;
+                for (uint32_t q = lane; q < Pp; q += 32) {
+                    const bool memb = q < P && ((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u);
+                    const int v = memb ? lr.base + T[(size_t)q * LT + lr.org] : 0;
+                    if (d.lastcol) d.lastcol[(size_t)i * Pp + q] = v;
+                    if (memb && track_results)
+                        for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
+                            if (g.grp[fg].pred == i && ((g.grp_mask[(size_t)fg * PW + q / 32] >> (q % 32)) & 1u)) {
+                                cx.s_res[q] = v;
+                                cx.s_end[q] = i;
+                            }
+                }
+            }
+            __syncthreads();
+        }
         prev_row = i;
         par ^= 1;
     }
-    __syncthreads();
-    last_issue(par ^ 1);
-    last_finish();
+    if (track_best && own_last) {
+        sh.best_set = bset ? 1 : 0;
+        sh.best_val = bval;
+        sh.best_row = brow;
+        sh.best_path = bpath;
+    }
     __syncthreads();
 }
 
@@ -756,7 +728,8 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 // the path's predecessor per row.
 template <int CPT, bool SIMPLE>
 __device__ void pwt_replay(const DevPathGraph& g, const PwtCtx& cx, const uint8_t* mv, uint8_t* own, uint32_t* own_pred,
-                           PwtShared& sh, const uint8_t* read, int L, bool rev, bool free_border, uint32_t q, uint32_t limit, int gap) {
+                           PwtShared& sh, const uint8_t* read, int L, bool rev, bool free_border, uint32_t q, uint32_t limit, int gap,
+                           bool find_end = false) {
     const int tid = threadIdx.x;
     const uint32_t n = g.n, PW = g.PW, LP = cx.LP;
     const int j0 = tid * CPT;
@@ -770,6 +743,10 @@ __device__ void pwt_replay(const DevPathGraph& g, const PwtCtx& cx, const uint8_
     int prev[CPT], prevm1 = (j0 - 1) * gap;
 #pragma unroll
     for (int k = 0; k < CPT; k++) prev[k] = (j0 + k) * gap;
+    const bool own_last = j0 <= L - 1 && L - 1 < j0 + CPT;
+    bool eset = false;
+    int eval = 0;
+    uint32_t erow = 0;
     int par = 0;
     for (uint32_t t = 1; t + 1 < n; t++) {
         const uint32_t i = rev ? n - 1 - t : t;
@@ -825,10 +802,26 @@ __device__ void pwt_replay(const DevPathGraph& g, const PwtCtx& cx, const uint8_
         }
         store_planes2<CPT>(own + (size_t)i * (LP / 4), tid, od & inread, ou & inread);
         if (tid == 0) own_pred[i] = pred;
+        if (find_end && own_last) {
+            // ending_node (…_recombination.rs:885-897): first strict maximum of the path's last-column scores
+            int v = cur[0];
+#pragma unroll
+            for (int k = 1; k < CPT; k++)
+                if (j0 + k == L - 1) v = cur[k];
+            if (!eset || v > eval) {
+                eset = true;
+                eval = v;
+                erow = i;
+            }
+        }
         prevm1 = cur_left;
 #pragma unroll
         for (int k = 0; k < CPT; k++) prev[k] = cur[k];
         par ^= 1;
+    }
+    if (find_end && own_last) {
+        sh.best_row = erow;
+        sh.best_val = eval;
     }
     __syncthreads();
 }
@@ -984,8 +977,8 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
         long long mcyc = 0;
         cx.mcyc = ws.diag ? &mcyc : nullptr;
         const long long tc0 = clock64();
-        pwt_pass<CPT, SIMPLE>(g, cx, fwd, sh, read, L, false, !global_mode, mode == RG_MODE_PATHWISE_SEMIGLOBAL,
-                      mode == RG_MODE_PATHWISE_GLOBAL, true, gap);
+        pwt_pass<CPT, SIMPLE>(g, cx, fwd, sh, read, L, false, !global_mode, !global_mode, mode == RG_MODE_PATHWISE_GLOBAL,
+                              global_mode, gap);
         const long long tc1 = clock64();
         if (rec_mode) pwt_pass<CPT, SIMPLE>(rg_, cx, rvd, sh, read, L, true, !global_mode, false, false, false, gap);
         const long long tc2 = clock64();
@@ -1062,22 +1055,14 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
                         }
                 }
             }
-            sh.best_val = mx;
-            sh.best_path = bp;
-        }
-        if (mode == RG_MODE_REC_SEMIGLOBAL) {
-            // first strict maximum in (row, path) order over the member slots of rows 0..n-2 (…_recombination.rs:790-799)
-            long long key = LLONG_MIN;
-            for (uint32_t i = tid; i + 1 < n; i += NT)
-                for (uint32_t q = 0; q < P; q++)
-                    if ((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u)
-                        key = max(key, ((long long)fwd.lastcol[(size_t)i * Pp + q] << 32) | (long long)(0xffffffffu - (i * Pp + q)));
-            key = block_max_ll(key, sh);
-            if (tid == 0) {
-                sh.best_val = (int)(key >> 32);
-                sh.best_path = (0xffffffffu - (uint32_t)(key & 0xffffffffll)) % Pp;
+            if (mode == RG_MODE_REC_GLOBAL) {
+                sh.best_val = mx;
+                sh.best_path = bp;
             }
         }
+        __syncthreads();
+        // mode 9: the forward pass already tracked the first strict maximum in (row, path) order over the member slots of rows
+        // 0..n-2 (…_recombination.rs:790-799) in sh.best_val / sh.best_path
         if (tid == 0) {
             sh.rb_v = (float)sh.best_val;
             sh.rb_k1 = ~0ull;
@@ -1246,21 +1231,22 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
             if (mode == RG_MODE_REC_GLOBAL) {
                 for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
                     if ((g.grp_mask[(size_t)fg * PW + base_path / 32] >> (base_path % 32)) & 1u) ending = g.grp[fg].pred;
-            } else {
-                // ending_node (…_recombination.rs:885-897): first strict maximum over the rows of the path
-                long long ekey = LLONG_MIN;
-                for (uint32_t i = 1 + tid; i + 1 < n; i += NT)
-                    if ((g.node_bits[(size_t)i * PW + base_path / 32] >> (base_path % 32)) & 1u)
-                        ekey = max(ekey, ((long long)fwd.lastcol[(size_t)i * Pp + base_path] << 32) | (long long)(0xffffffffu - i));
-                ekey = block_max_ll(ekey, sh);
-                ending = (ekey == LLONG_MIN) ? 0u : 0xffffffffu - (uint32_t)(ekey & 0xffffffffll);
             }
-            pwt_replay<CPT, SIMPLE>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, !global_mode, base_path, ending, gap);
+            int end_score = 0;
+            if (mode == RG_MODE_REC_GLOBAL) {
+                pwt_replay<CPT, SIMPLE>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, false, base_path, ending, gap);
+                end_score = fwd.lastcol[(size_t)ending * Pp + base_path];
+            } else {
+                // ending_node (…_recombination.rs:885-897) needs the path's last-column score on every row: the replay finds it
+                pwt_replay<CPT, SIMPLE>(g, cx, fwd.mv, own, own_pred, sh, read, L, false, true, base_path, n - 2, gap, true);
+                ending = sh.best_row;
+                end_score = sh.best_val;
+            }
             if (tid == 0) {
                 res.best_path = res.rev_best_path = base_path;
                 res.end_row = ending;
                 res.end_col = (uint32_t)(L - 1);
-                res.score = fwd.lastcol[(size_t)ending * Pp + base_path];
+                res.score = end_score;
                 res.score_f32 = (float)base_score;
                 uint32_t ii = ending;
                 int j = L - 1;
@@ -1354,8 +1340,8 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
     }
 }
 
-size_t pwt_smem_bytes(const PwtWorkspace& ws, bool rec) {
-    return (size_t)ws.LP * 11 + (size_t)ws.Pp * 8 + (rec ? (size_t)ws.LT * 8 : 0) + 16;
+size_t pwt_smem_bytes(const PwtWorkspace& ws, bool mx) {
+    return (size_t)ws.LP * 11 + (size_t)ws.Pp * 8 + (mx ? (size_t)ws.LT * 8 : 0) + 16;
 }
 
 bool pwt_simple(const DevScoring& s) {   // match/mismatch table of score_matrix.rs:35-66
@@ -1385,8 +1371,7 @@ int pathwise_tr_cpt(uint32_t Lmax) {
 int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws,
                        const PoaBatch& b, int blocks, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
-    const size_t smem = pwt_smem_bytes(ws, rec);
+    const size_t smem = pwt_smem_bytes(ws, mode != RG_MODE_PATHWISE_GLOBAL);   // every mode but 4 keeps the per-origin maxima
     const void* k = pwt_kernel(ws.CPT, pwt_simple(s));
     if (smem > 200 * 1024 || !k) return -3;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -1400,8 +1385,8 @@ int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_,
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int pathwise_tr_blocks_per_sm(const DevPathGraph&, const DevPathGraph&, const DevScoring& s, const PwtWorkspace& ws, bool rec, int* nb) {
-    const size_t smem = pwt_smem_bytes(ws, rec);
+int pathwise_tr_blocks_per_sm(const DevPathGraph&, const DevPathGraph&, const DevScoring& s, const PwtWorkspace& ws, bool mx, int* nb) {
+    const size_t smem = pwt_smem_bytes(ws, mx);
     const void* k = pwt_kernel(ws.CPT, pwt_simple(s));
     if (smem > 200 * 1024 || !k) return -3;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
