@@ -105,7 +105,7 @@ struct rg_ctx {
     // score-transport kernel (pathwise_tr.cu): per-row records of both directions and its work-space
     DevBuf<PwtRow> d_pwt_rows, d_pwt_rrows;
     DevBuf<int32_t> d_nonmem_hi;
-    DevBuf<int32_t> d_tr_tables, d_tr_ring_lead, d_tr_ring_base, d_tr_lastcol;
+    DevBuf<int32_t> d_tr_tables, d_tr_ring_lead, d_tr_lastcol;
     DevBuf<uint16_t> d_tr_ring_org;
     DevBuf<uint4> d_tr_ring_meta;
     DevBuf<uint8_t> d_tr_mv_f, d_tr_mv_r, d_tr_own;
@@ -756,13 +756,13 @@ static int align_pathwise(rg_ctx* c, int mode) {
     if (const char* e = getenv("RG_PW_BPS")) bps = std::max(1, std::min(bps, atoi(e)));  // testing: CTAs per SM
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    free_b += (c->d_tr_tables.cap + c->d_tr_ring_lead.cap + c->d_tr_ring_base.cap + c->d_tr_lastcol.cap + c->d_tr_own_pred.cap) * 4 +
+    free_b += (c->d_tr_tables.cap + c->d_tr_ring_lead.cap + c->d_tr_lastcol.cap + c->d_tr_own_pred.cap) * 4 +
               c->d_tr_ring_org.cap * 2 + c->d_tr_ring_meta.cap * 16 + c->d_tr_mv_f.cap + c->d_tr_mv_r.cap + c->d_tr_own.cap +
               (c->d_tr_cb_f.cap + c->d_tr_cb_r.cap) * 8 + (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
     const size_t sz_tables = (size_t)ws.TRmax * ws.Pp * ws.LT, sz_ring = (size_t)ws.ringmax * ws.LP;
     const size_t sz_mvf = (size_t)c->dpg.n_groups * (ws.LP / 4), sz_mvr = rec ? (size_t)c->dpg_rev.n_groups * (ws.LP / 4) : 0;
     const size_t sz_own = (size_t)n * (ws.LP / 4), sz_cb = rec ? (size_t)n * ws.LP : 0, sz_last = rec ? (size_t)n * ws.Pp : 0;
-    const size_t per_slot = sz_tables * 4 + sz_ring * 10 + (size_t)ws.ringmax * 16 + sz_mvf + sz_mvr + sz_own + (size_t)n * 4 +
+    const size_t per_slot = sz_tables * 4 + sz_ring * 6 + (size_t)ws.ringmax * 16 + sz_mvf + sz_mvr + sz_own + (size_t)n * 4 +
                             sz_cb * 16 + sz_last * 4 + (size_t)ws.run_cap * sizeof(rg_run);
     const size_t budget_all = (size_t)(free_b * 0.85);
     size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(ws.run_cap, 16384), (budget_all / 8) / sizeof(rg_run));
@@ -772,7 +772,7 @@ static int align_pathwise(rg_ctx* c, int mode) {
     slots = (uint32_t)std::min<size_t>(slots, budget / per_slot);
     if (slots < 1) return c->fail(RG_ERR_NOMEM, "not enough device memory for one pathwise read in flight");
     ws.slots = slots;
-    bool ok = c->d_tr_tables.ensure(slots * sz_tables) && c->d_tr_ring_lead.ensure(slots * sz_ring) && c->d_tr_ring_base.ensure(slots * sz_ring) &&
+    bool ok = c->d_tr_tables.ensure(slots * sz_tables) && c->d_tr_ring_lead.ensure(slots * sz_ring) &&
               c->d_tr_ring_org.ensure(slots * sz_ring) && c->d_tr_ring_meta.ensure((size_t)slots * ws.ringmax) &&
               c->d_tr_mv_f.ensure(slots * sz_mvf) && c->d_tr_mv_r.ensure(slots * sz_mvr) && c->d_tr_own.ensure(slots * sz_own) &&
               c->d_tr_own_pred.ensure((size_t)slots * n) && c->d_tr_cb_f.ensure(slots * sz_cb) && c->d_tr_cb_r.ensure(slots * sz_cb) &&
@@ -781,7 +781,6 @@ static int align_pathwise(rg_ctx* c, int mode) {
     if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
     ws.tables = c->d_tr_tables.p;
     ws.ring_lead = c->d_tr_ring_lead.p;
-    ws.ring_base = c->d_tr_ring_base.p;
     ws.ring_org = c->d_tr_ring_org.p;
     ws.ring_meta = c->d_tr_ring_meta.p;
     ws.mv_f = c->d_tr_mv_f.p;

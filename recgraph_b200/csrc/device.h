@@ -151,7 +151,6 @@ struct PwRecWorkspace {
 struct PwtWorkspace {
     int32_t* tables;    // slots * TRmax * Pp * LT      absolute scores of materialised rows, [table][path][column]
     int32_t* ring_lead; // slots * ringmax * LP         frames of rows kept for later segment starts
-    int32_t* ring_base; // slots * ringmax * LP
     uint16_t* ring_org; // slots * ringmax * LP
     uint4* ring_meta;   // slots * ringmax              {leader path of the frame, table id, -, -}
     uint8_t* mv_f;      // slots * groups_f * LP/4      leader moves, 2 bit per (group, column)

@@ -25,8 +25,10 @@
 // codes are written as 2 bits per cell and thread 0 walks them.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 
 #include "device.h"
 #include "poa_common.cuh"
@@ -48,6 +50,9 @@ struct PwtShared {
     int32_t sc[48];
     __align__(16) int totA[NWP];
     __align__(16) long long totK[2][NWP];
+    __align__(16) int totA2[2][NWP];
+    int zref[2];
+    int zconv;
     int dlt[2][NT];
     int val[2][NT];
     __align__(16) unsigned tot2[2][NWP];
@@ -75,6 +80,18 @@ __device__ __forceinline__ int block_excl_max_i(int z, int* tot) {
         if (k < w) base = max(base, tot[k]);
     int exc = __shfl_up_sync(FULL, inc, 1);
     if (lane == 0) exc = NEG_INF;
+    return max(base, exc);
+}
+// 32-bit non-negative keys; the warp totals are combined with one load + one warp reduction
+__device__ __forceinline__ int block_excl_max_r(int z, int* tot) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int inc = warp_incl_max(z, lane);
+    if (lane == 31) tot[w] = inc;
+    __syncthreads();
+    const int mine = (lane < w) ? tot[lane & (NWP - 1)] : -1;
+    const int base = __reduce_max_sync(FULL, mine);
+    int exc = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) exc = -1;
     return max(base, exc);
 }
 // 64-bit keys (score << 32 | column << 16 | origin): ONE scan gives the incoming chain value and where it comes from
@@ -213,7 +230,6 @@ struct PwtDirBufs {
 struct PwtCtx {
     int32_t* tables;
     int32_t* ring_lead;
-    int32_t* ring_base;
     uint16_t* ring_org;
     uint4* ring_meta;
     // dynamic shared arrays
@@ -265,10 +281,13 @@ struct SubScores {
     }
 };
 
-// Per-origin maxima over the member paths of row i of table T: s_mx[c] = {max_q T[q][c], highest q with it | lowest q << 16}
+// Per-origin maxima over the member paths of row i of table T, RELATIVE to the frame's leader path lam:
+//   s_mx[c] = {max_q T[q][c] - T[lam][c], highest q with the maximum | lowest q with it << 16}
+// so that the best score over the row's paths at a cell with leader score v and origin c is v + s_mx[c].x
 // (modes 8/9 take the highest path id on ties, …_recombination.rs:809-830; the best end of modes 5/9 the lowest).
 template <int CPT>
-__device__ __forceinline__ void build_mx(const DevPathGraph& g, const PwtCtx& cx, const int32_t* T, uint32_t i, int j0, unsigned ZC) {
+__device__ __forceinline__ void build_mx(const DevPathGraph& g, const PwtCtx& cx, const int32_t* T, uint32_t i, uint32_t lam, int j0,
+                                         unsigned ZC) {
     int bv[CPT];
     unsigned bq[CPT];
 #pragma unroll
@@ -292,13 +311,25 @@ __device__ __forceinline__ void build_mx(const DevPathGraph& g, const PwtCtx& cx
             }
         }
     }
+    const int32_t* Tl = T + (size_t)lam * cx.LT + j0;
 #pragma unroll
-    for (int k = 0; k < CPT; k++) cx.s_mx[j0 + k] = make_int2(bv[k], (int)bq[k]);
+    for (int k = 0; k < CPT; k += 4) {
+        const int4 v = *reinterpret_cast<const int4*>(Tl + k);
+        cx.s_mx[j0 + k] = make_int2(bv[k] - v.x, (int)bq[k]);
+        cx.s_mx[j0 + k + 1] = make_int2(bv[k + 1] - v.y, (int)bq[k + 1]);
+        cx.s_mx[j0 + k + 2] = make_int2(bv[k + 2] - v.z, (int)bq[k + 2]);
+        cx.s_mx[j0 + k + 3] = make_int2(bv[k + 3] - v.w, (int)bq[k + 3]);
+    }
     if (threadIdx.x == 0) cx.s_mx[ZC] = make_int2(0, (int)(hi | (lo << 16)));
 }
 
 // One DP pass over all rows of one direction.
-template <int CPT, bool SIMPLE>
+// A row's FRAME is (leader scores `lead`, origins `org`) + (lam = the path the leader scores belong to, tid = table):
+//        S[i][j][q] = lead[j] + T_tid[q][org[j]] - T_tid[lam][org[j]]          for every path q of the row.
+// K32: the CTA-wide scan of a transport row runs on 32-bit keys (score relative to the previous row's first column, biased,
+// 23 bits | thread 8 bits) — the host enables it when 3 * max|score| * (LP + 2) < 2^22, which bounds every key (a cell of
+// row i differs from the row's first column by at most one substitution / gap score per read character).
+template <int CPT, bool SIMPLE, bool K32>
 __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBufs& d, PwtShared& sh, const uint8_t* read,
                          int L, bool rev, bool free_border, bool track_best, bool track_results, bool fpred_rows, int gap) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -309,16 +340,20 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
     const size_t tstride = (size_t)Pp * LT;
     const uint32_t base_row = rev ? n - 1 : 0;
     const long long KNONE = (long long)NEG_INF << 32;
+    constexpr int KBIAS = 1 << 22;
+    constexpr unsigned ALL = (CPT >= 32) ? 0xffffffffu : ((1u << (CPT % 32)) - 1u);
     const bool need_mx = track_best || d.cb != nullptr;
     SubScores<CPT, SIMPLE> ss;
     ss.init(read, L, j0, rev, sh.sc);
 
-    // ---- frame of the previously processed row, in registers: leader score, base - leader score, origin
-    int pl[CPT], pd[CPT];
+    // ---- frame of the previously processed row, in registers
+    int pl[CPT];
     unsigned po[CPT];
-    int plm1, pdm1;
+    int plm1;
     unsigned pom1;
     uint32_t lam, tidp, prev_row;
+    uint32_t mx_lam = 0;   // leader path the per-origin maxima in shared memory are relative to
+    int zref = 0;          // K32: leader score of the previous row's first column
 
     // ---- base row: every path carries the accumulated read gaps (pathwise_alignment_semiglobal.rs:26-32,
     //      pathwise_alignment_recombination.rs:148-155); it creates table 0
@@ -331,19 +366,18 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             pl[k] = (j0 + k) * gap;
-            pd[k] = -(j0 + k) * gap;
             po[k] = (unsigned)(j0 + k);
         }
         plm1 = (j0 - 1) * gap;
-        pdm1 = -(j0 - 1) * gap;
         pom1 = (unsigned)(j0 - 1);
         lam = g.alphas[base_row];
         tidp = 0;
         prev_row = base_row;
-        if (need_mx) {   // s_mx entry: {max over the member paths, highest path with it | lowest path with it << 16}
+        if (need_mx) {   // every path has the same scores on the base row
 #pragma unroll
-            for (int k = 0; k < CPT; k++) cx.s_mx[j0 + k] = make_int2((j0 + k) * gap, (int)P - 1);
+            for (int k = 0; k < CPT; k++) cx.s_mx[j0 + k] = make_int2(0, (int)P - 1);
             if (tid == 0) cx.s_mx[ZC] = make_int2(0, (int)P - 1);
+            mx_lam = lam;
         }
     }
     // running best end cell (mode 5: …_semiglobal.rs:244-277; mode 9 baseline: …_recombination.rs:790-799, which also
@@ -361,8 +395,6 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 #pragma unroll
         for (int k = 0; k < CPT; k += 4) {
             *reinterpret_cast<int4*>(cx.ring_lead + o + k) = make_int4(pl[k], pl[k + 1], pl[k + 2], pl[k + 3]);
-            *reinterpret_cast<int4*>(cx.ring_base + o + k) =
-                make_int4(pl[k] + pd[k], pl[k + 1] + pd[k + 1], pl[k + 2] + pd[k + 2], pl[k + 3] + pd[k + 3]);
             *reinterpret_cast<uint2*>(cx.ring_org + o + k) = make_uint2(po[k] | (po[k + 1] << 16), po[k + 2] | (po[k + 3] << 16));
         }
         if (tid == 0) cx.ring_meta[row & RM] = make_uint4(lam, tidp, 0u, 0u);
@@ -388,45 +420,51 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 #pragma unroll
                 for (int k = 0; k < CPT; k += 4) {
                     const int4 a = *reinterpret_cast<const int4*>(cx.ring_lead + o + k);
-                    const int4 bb = *reinterpret_cast<const int4*>(cx.ring_base + o + k);
                     const uint2 oo = *reinterpret_cast<const uint2*>(cx.ring_org + o + k);
                     pl[k] = a.x, pl[k + 1] = a.y, pl[k + 2] = a.z, pl[k + 3] = a.w;
-                    pd[k] = bb.x - a.x, pd[k + 1] = bb.y - a.y, pd[k + 2] = bb.z - a.z, pd[k + 3] = bb.w - a.w;
                     po[k] = oo.x & 0xffffu, po[k + 1] = oo.x >> 16, po[k + 2] = oo.y & 0xffffu, po[k + 3] = oo.y >> 16;
                 }
                 if (tid > 0) {
                     plm1 = cx.ring_lead[o - 1];
-                    pdm1 = cx.ring_base[o - 1] - plm1;
                     pom1 = cx.ring_org[o - 1];
                 }
                 const uint4 mt = cx.ring_meta[r.pred & RM];
                 lam = mt.x;
                 tidp = mt.y;
+                if (K32) zref = cx.ring_lead[(size_t)(r.pred & RM) * LP];
             }
             const int32_t* Tp = cx.tables + (size_t)(tidp & TM) * tstride;
             if ((uint32_t)r.leader != lam) {
-                // the leader of this row is not the path the frame's leader scores belong to: S[p][j][a] = base + T[a][org]
+                // the leader of this row is not the path the frame's leader scores belong to:
+                // S[p][j][a] = lead[j] + T[a][org[j]] - T[lam][org[j]]
                 const int32_t* Ta = Tp + (size_t)r.leader * LT;
+                const int32_t* Tl = Tp + (size_t)lam * LT;
 #pragma unroll
-                for (int k = 0; k < CPT; k++) {
-                    const int tv = Ta[po[k]];
-                    pl[k] += pd[k] + tv;
-                    pd[k] = -tv;
-                }
-                if (tid > 0) {
-                    const int tv = Ta[pom1];
-                    plm1 += pdm1 + tv;
-                    pdm1 = -tv;
+                for (int k = 0; k < CPT; k++) pl[k] += Ta[po[k]] - Tl[po[k]];
+                if (tid > 0) plm1 += Ta[pom1] - Tl[pom1];
+                if (K32) {   // every thread must use the same reference: thread 0 publishes its converted first column
+                    if (tid == 0) sh.zconv = pl[0];
+                    __syncthreads();
+                    zref = sh.zconv;
                 }
                 lam = r.leader;
             }
-            if (need_mx && (r.kind & PWT_MXREBUILD)) {
-                // per-origin maxima over the paths of THIS row (its path set differs from the table's creator's)
+            if (need_mx && ((r.kind & PWT_MXREBUILD) || mx_lam != lam)) {
                 __syncthreads();   // the previous row may still be reading s_mx
-                build_mx<CPT>(g, cx, Tp, i, j0, ZC);
+                if (r.kind & PWT_MXREBUILD) {
+                    // per-origin maxima over the paths of THIS row (its path set or table differs from the previous row's)
+                    build_mx<CPT>(g, cx, Tp, i, lam, j0, ZC);
+                } else {
+                    // same table and path set, other leader path: re-express the maxima relative to it
+                    const int32_t* Tl = Tp + (size_t)lam * LT + j0;
+                    const int32_t* Tm = Tp + (size_t)mx_lam * LT + j0;
+#pragma unroll
+                    for (int k = 0; k < CPT; k++) cx.s_mx[j0 + k].x += Tm[k] - Tl[k];
+                }
+                mx_lam = lam;
             }
-            // ---- phase A: candidates, the chain inside my columns as if nothing came in from the left, and for every cell
-            // the (origin, base - leader) it copies: from the diagonal / vertical source, or from its left neighbour on an L move
+            // ---- phase A: candidates and the chain inside my columns as if nothing came in from the left; every cell
+            // copies its origin from the diagonal / vertical source, or from its left neighbour on an L move
             int nl[CPT];
             unsigned dbits = 0;
             {
@@ -445,65 +483,60 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                 dbits &= ~1u;
             }
             unsigned lbits = 0;
-            unsigned old_o = pom1, cur_o = 0, src_o = 0;
-            int old_d = pdm1, cur_d = 0, src_d = 0, srcc = 0;
+            {
+                unsigned old_o = pom1, cur_o = 0;
 #pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                const unsigned o_k = po[k];
-                const int d_k = pd[k];
-                const bool isL = (k > 0) && (nl[k - 1] + gap > nl[k]);
-                unsigned no;
-                int nd;
-                if (isL) {
-                    nl[k] = nl[k - 1] + gap;
-                    no = cur_o;
-                    nd = cur_d;
-                    lbits |= 1u << k;
-                } else {
-                    const bool isD = (dbits >> k) & 1u;
-                    no = isD ? old_o : o_k;
-                    nd = isD ? old_d : d_k;
-                    if (k == 0 && tid == 0 && free_border) {
-                        no = ZC;
-                        nd = 0;
+                for (int k = 0; k < CPT; k++) {
+                    const unsigned o_k = po[k];
+                    unsigned no = ((dbits >> k) & 1u) ? old_o : o_k;
+                    if (k == 0 && tid == 0 && free_border) no = ZC;
+                    if (k > 0) {
+                        const int c = nl[k - 1] + gap;
+                        if (c > nl[k]) {
+                            no = cur_o;
+                            lbits |= 1u << k;
+                        }
+                        nl[k] = max(c, nl[k]);
                     }
-                    srcc = k;
-                    src_o = no;
-                    src_d = nd;
+                    po[k] = no;
+                    cur_o = no;
+                    old_o = o_k;
                 }
-                po[k] = no;
-                pd[k] = nd;
-                cur_o = no;
-                cur_d = nd;
-                old_o = o_k;
-                old_d = d_k;
             }
-            // ---- one scan: (normalised chain value, column, origin) of the best source left of my columns; ties go to the
-            // right-most source, which is exactly the cell where the reference's strict `l > max(d, u)` test stops an L run
-            const long long key = ((long long)(nl[CPT - 1] - (j0 + CPT - 1) * gap) << 32) |
-                                  (long long)(((unsigned)(j0 + srcc) << 16) | src_o);
-            sh.dlt[par][tid] = src_d;
-            const long long exc = block_excl_max_k(key, sh.totK[par], KNONE);
-            const int lc_in = (tid == 0) ? NEG_INF : (int)(exc >> 32) + j0 * gap;   // lead[j0 - 1] + gap
-            const unsigned org_in = (unsigned)exc & 0xffffu;
-            const int dl_in = sh.dlt[par][(((unsigned)exc >> 16) & 0xffffu) / CPT];
+            // ---- one scan: the best source left of my columns (normalised chain value; ties go to the right-most source,
+            // which is exactly the cell where the reference's strict `l > max(d, u)` test stops an L run) and its origin.
+            // All cells after a thread's last source copy that source's origin, so the origin to publish is po[CPT-1].
+            int lc_in;
+            unsigned org_in;
+            if constexpr (K32) {
+                if (tid == 0) sh.zref[par] = nl[0];
+                const int zrel = nl[CPT - 1] - (j0 + CPT - 1) * gap - zref;
+                sh.dlt[par][tid] = (int)po[CPT - 1];
+                const int exc = block_excl_max_r((((zrel + KBIAS) << 8) | tid), sh.totA2[par]);
+                lc_in = (tid == 0) ? NEG_INF : (exc >> 8) - KBIAS + zref + j0 * gap;   // lead[j0 - 1] + gap
+                org_in = (unsigned)sh.dlt[par][exc & 255];
+                zref = sh.zref[par];
+            } else {
+                const unsigned nonl = ~lbits & ALL;
+                const long long key = ((long long)(nl[CPT - 1] - (j0 + CPT - 1) * gap) << 32) |
+                                      (long long)(((unsigned)(j0 + 31 - __clz(nonl)) << 16) | po[CPT - 1]);
+                const long long exc = block_excl_max_k(key, sh.totK[par], KNONE);
+                lc_in = (tid == 0) ? NEG_INF : (int)(exc >> 32) + j0 * gap;
+                org_in = (unsigned)exc & 0xffffu;
+            }
             // ---- phase B: the incoming chain overrides a prefix of my cells (it loses `gap` per column like every chain)
 #pragma unroll
             for (int k = 0; k < CPT; k++) {
-                const int inc = lc_in + k * gap;
-                if (inc > nl[k]) {
-                    nl[k] = inc;
+                const int nv = max(nl[k], lc_in + k * gap);
+                if (nv != nl[k]) {
                     po[k] = org_in;
-                    pd[k] = dl_in;
                     lbits |= 1u << k;
                 }
+                pl[k] = nv;
             }
             store_planes2<CPT>(d.mv + (size_t)r.g0 * (LP / 4), tid, lbits, dbits);
-#pragma unroll
-            for (int k = 0; k < CPT; k++) pl[k] = nl[k];
             plm1 = lc_in - gap;
             pom1 = org_in;
-            pdm1 = dl_in;
         } else {
             // ================= materialising row: several incoming edges =================
             const uint32_t g0 = r.g0, g1 = g.grp_off[i + 1];
@@ -519,19 +552,21 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                     const size_t o = (size_t)(gr.pred & RM) * LP + j0;
                     const uint4 mt = cx.ring_meta[gr.pred & RM];
                     ftid = mt.y;
-                    const int32_t* Ta = cx.tables + (size_t)(ftid & TM) * tstride + (size_t)a * LT;
+                    const int32_t* Tf = cx.tables + (size_t)(ftid & TM) * tstride;
+                    const int32_t* Ta = Tf + (size_t)a * LT;
+                    const int32_t* Tl = Tf + (size_t)mt.x * LT;
 #pragma unroll
                     for (int k = 0; k < CPT; k += 4) {
                         const int4 fl = *reinterpret_cast<const int4*>(cx.ring_lead + o + k);
-                        const int4 fb = *reinterpret_cast<const int4*>(cx.ring_base + o + k);
                         const uint2 oo = *reinterpret_cast<const uint2*>(cx.ring_org + o + k);
-                        const int fls[4] = {fl.x, fl.y, fl.z, fl.w}, fbs[4] = {fb.x, fb.y, fb.z, fb.w};
+                        const int fls[4] = {fl.x, fl.y, fl.z, fl.w};
                         const unsigned fos[4] = {oo.x & 0xffffu, oo.x >> 16, oo.y & 0xffffu, oo.y >> 16};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            A[k + e] = (a == mt.x) ? fls[e] : fbs[e] + Ta[fos[e]];
+                            const int fb = fls[e] - Tl[fos[e]];   // base: S[p][j][q] = base + T[q][org]
+                            A[k + e] = fb + Ta[fos[e]];
                             cx.s_A[j0 + k + e] = A[k + e];
-                            cx.s_wb[j0 + k + e] = fbs[e];
+                            cx.s_wb[j0 + k + e] = fb;
                             cx.s_org[j0 + k + e] = (uint16_t)fos[e];
                         }
                     }
@@ -618,7 +653,7 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                 }
                 __syncthreads();
             }
-            // ---- the row's new frame: base 0, origin = own column, leader scores of the row's alpha path
+            // ---- the row's new frame: origin = own column, leader scores of the row's alpha path
             lam = g.alphas[i];
             tidp = r.tid;
             {
@@ -629,16 +664,14 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                     pl[k] = v.x, pl[k + 1] = v.y, pl[k + 2] = v.z, pl[k + 3] = v.w;
                 }
 #pragma unroll
-                for (int k = 0; k < CPT; k++) {
-                    pd[k] = -pl[k];
-                    po[k] = (unsigned)(j0 + k);
-                }
+                for (int k = 0; k < CPT; k++) po[k] = (unsigned)(j0 + k);
                 if (tid > 0) plm1 = Tl[-1];
-                pdm1 = -plm1;
                 pom1 = (unsigned)(j0 - 1);
+                if (K32) zref = Tn[(size_t)lam * LT];
             }
             if (need_mx) {
-                build_mx<CPT>(g, cx, Tn, i, j0, ZC);
+                build_mx<CPT>(g, cx, Tn, i, lam, j0, ZC);
+                mx_lam = lam;
                 __syncthreads();
             }
         }
@@ -651,7 +684,7 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int2 mx = cx.s_mx[po[k + h]];
-                    int val = pl[k + h] + pd[k + h] + mx.x, path = mx.y & 0xffff;
+                    int val = pl[k + h] + mx.x, path = mx.y & 0xffff;
                     bool memb = true;
                     // slots of paths that do not go through the row hold 0 (as in the reference); highest path id wins ties
                     if (nmh >= 0 && (0 > val || (0 == val && nmh > path))) {
@@ -667,16 +700,16 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
         if (cx.mcyc && !(r.kind & PWT_T)) *cx.mcyc += clock64() - tm0;
         if (r.kind & PWT_RING) ring_store(i);
         if ((track_best || (fpred_rows && (r.kind & PWT_FPRED))) && own_last) {
-            int lbase = pl[0] + pd[0];
+            int llead = pl[0];
             unsigned lorg = po[0];
 #pragma unroll
             for (int k = 1; k < CPT; k++)
-                if (j0 + k == L - 1) lbase = pl[k] + pd[k], lorg = po[k];
+                if (j0 + k == L - 1) llead = pl[k], lorg = po[k];
             if (track_best) {
-                // best member path of the row = base + per-origin maximum; first strict maximum in path order (lowest id);
-                // a row replaces the incumbent only if strictly better (…_semiglobal.rs:256-273)
+                // best member path of the row = leader score + per-origin maximum; first strict maximum in path order (lowest
+                // id); a row replaces the incumbent only if strictly better (…_semiglobal.rs:256-273)
                 const int2 mx = cx.s_mx[lorg];
-                const int v = lbase + mx.x;
+                const int v = llead + mx.x;
                 if (!bset || v > bval) {
                     bset = true;
                     bval = v;
@@ -686,7 +719,7 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
             }
             if (fpred_rows && (r.kind & PWT_FPRED)) {
                 LastRec lr;
-                lr.base = lbase, lr.org = lorg, lr.row = i, lr.tid = tidp;
+                lr.base = llead, lr.org = lorg, lr.row = lam, lr.tid = tidp;
                 sh.last[0] = lr;
             }
         }
@@ -695,11 +728,12 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
             // mode 8 baseline, …_recombination.rs:777-788). Rare rows: two extra barriers.
             __syncthreads();
             if (warp == 0) {
-                const LastRec lr = sh.last[0];
+                const LastRec lr = sh.last[0];   // .row holds the frame's leader path here
                 const int32_t* T = cx.tables + (size_t)(lr.tid & TM) * tstride;
+                const int lbase = lr.base - T[(size_t)lr.row * LT + lr.org];
                 for (uint32_t q = lane; q < Pp; q += 32) {
                     const bool memb = q < P && ((g.node_bits[(size_t)i * PW + q / 32] >> (q % 32)) & 1u);
-                    const int v = memb ? lr.base + T[(size_t)q * LT + lr.org] : 0;
+                    const int v = memb ? lbase + T[(size_t)q * LT + lr.org] : 0;
                     if (d.lastcol) d.lastcol[(size_t)i * Pp + q] = v;
                     if (memb && track_results)
                         for (uint32_t fg = g.grp_off[n - 1]; fg < g.grp_off[n]; fg++)
@@ -889,8 +923,8 @@ __device__ __forceinline__ void rec_merge2(RecBest& a, const RecBest& o) {
     }
 }
 
-template <int CPT, bool SIMPLE>
-__global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
+template <int CPT, bool SIMPLE, bool K32>
+__global__ void __launch_bounds__(NT, (CPT <= 8) ? 4 : ((CPT <= 16) ? 2 : 1))
     k_pathwise_tr(DevPathGraph g, DevPathGraph rg_, DevScoring sc, PwtWorkspace ws, PoaBatch b, int mode) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ PwtShared sh;
@@ -904,7 +938,6 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
     cx.LP = LP, cx.LT = LT, cx.Pp = Pp, cx.TRmax = ws.TRmax;
     cx.tables = ws.tables + (size_t)slot * ws.TRmax * Pp * LT;
     cx.ring_lead = ws.ring_lead + (size_t)slot * ws.ringmax * LP;
-    cx.ring_base = ws.ring_base + (size_t)slot * ws.ringmax * LP;
     cx.ring_org = ws.ring_org + (size_t)slot * ws.ringmax * LP;
     cx.ring_meta = ws.ring_meta + (size_t)slot * ws.ringmax;
     {
@@ -977,10 +1010,10 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 3 : ((CPT <= 16) ? 2 : 1))
         long long mcyc = 0;
         cx.mcyc = ws.diag ? &mcyc : nullptr;
         const long long tc0 = clock64();
-        pwt_pass<CPT, SIMPLE>(g, cx, fwd, sh, read, L, false, !global_mode, !global_mode, mode == RG_MODE_PATHWISE_GLOBAL,
+        pwt_pass<CPT, SIMPLE, K32>(g, cx, fwd, sh, read, L, false, !global_mode, !global_mode, mode == RG_MODE_PATHWISE_GLOBAL,
                               global_mode, gap);
         const long long tc1 = clock64();
-        if (rec_mode) pwt_pass<CPT, SIMPLE>(rg_, cx, rvd, sh, read, L, true, !global_mode, false, false, false, gap);
+        if (rec_mode) pwt_pass<CPT, SIMPLE, K32>(rg_, cx, rvd, sh, read, L, true, !global_mode, false, false, false, gap);
         const long long tc2 = clock64();
         long long tc3 = tc2;
 
@@ -1350,12 +1383,25 @@ bool pwt_simple(const DevScoring& s) {   // match/mismatch table of score_matrix
             if (s.sc[a][b] != ((a == b && a < 4) ? s.sc[0][0] : s.sc[0][1])) return false;
     return true;
 }
-const void* pwt_kernel(uint32_t cpt, bool simple) {
+// 32-bit scan keys are exact when every score difference inside a row fits 22 bits (see pwt_pass)
+bool pwt_k32(const DevScoring& s, uint32_t LP) {
+    long long mx = 1;
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) mx = std::max<long long>(mx, std::llabs((long long)s.sc[a][b]));
+    return 3 * mx * ((long long)LP + 2) < (1ll << 22);
+}
+template <int CPT>
+const void* pwt_kernel_c(bool simple, bool k32) {
+    if (simple) return k32 ? (const void*)k_pathwise_tr<CPT, true, true> : (const void*)k_pathwise_tr<CPT, true, false>;
+    return k32 ? (const void*)k_pathwise_tr<CPT, false, true> : (const void*)k_pathwise_tr<CPT, false, false>;
+}
+const void* pwt_kernel(uint32_t cpt, const DevScoring& s, uint32_t LP) {
+    const bool simple = pwt_simple(s), k32 = pwt_k32(s, LP) && !getenv("RG_PW_K64");
     switch (cpt) {
-        case 4: return simple ? (const void*)k_pathwise_tr<4, true> : (const void*)k_pathwise_tr<4, false>;
-        case 8: return simple ? (const void*)k_pathwise_tr<8, true> : (const void*)k_pathwise_tr<8, false>;
-        case 16: return simple ? (const void*)k_pathwise_tr<16, true> : (const void*)k_pathwise_tr<16, false>;
-        case 32: return simple ? (const void*)k_pathwise_tr<32, true> : (const void*)k_pathwise_tr<32, false>;
+        case 4: return pwt_kernel_c<4>(simple, k32);
+        case 8: return pwt_kernel_c<8>(simple, k32);
+        case 16: return pwt_kernel_c<16>(simple, k32);
+        case 32: return pwt_kernel_c<32>(simple, k32);
         default: return nullptr;
     }
 }
@@ -1372,7 +1418,7 @@ int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_,
                        const PoaBatch& b, int blocks, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = pwt_smem_bytes(ws, mode != RG_MODE_PATHWISE_GLOBAL);   // every mode but 4 keeps the per-origin maxima
-    const void* k = pwt_kernel(ws.CPT, pwt_simple(s));
+    const void* k = pwt_kernel(ws.CPT, s, ws.LP);
     if (smem > 200 * 1024 || !k) return -3;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     DevPathGraph ga = g, gb = rg_;
@@ -1387,7 +1433,7 @@ int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_,
 
 int pathwise_tr_blocks_per_sm(const DevPathGraph&, const DevPathGraph&, const DevScoring& s, const PwtWorkspace& ws, bool mx, int* nb) {
     const size_t smem = pwt_smem_bytes(ws, mx);
-    const void* k = pwt_kernel(ws.CPT, pwt_simple(s));
+    const void* k = pwt_kernel(ws.CPT, s, ws.LP);
     if (smem > 200 * 1024 || !k) return -3;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, NT, smem) == cudaSuccess ? 0 : -1;
