@@ -105,7 +105,7 @@ struct rg_ctx {
     // score-transport kernel (pathwise_tr.cu): per-row records of both directions and its work-space
     DevBuf<PwtRow> d_pwt_rows, d_pwt_rrows;
     DevBuf<int32_t> d_nonmem_hi;
-    DevBuf<int32_t> d_tr_tables, d_tr_ring_lead, d_tr_lastcol;
+    DevBuf<int32_t> d_tr_tables, d_tr_ring_lead, d_tr_lastcol, d_tr_colmax;
     DevBuf<uint16_t> d_tr_ring_org;
     DevBuf<uint4> d_tr_ring_meta;
     DevBuf<uint8_t> d_tr_mv_f, d_tr_mv_r, d_tr_own;
@@ -776,7 +776,7 @@ static int align_pathwise(rg_ctx* c, int mode) {
               c->d_tr_ring_org.ensure(slots * sz_ring) && c->d_tr_ring_meta.ensure((size_t)slots * ws.ringmax) &&
               c->d_tr_mv_f.ensure(slots * sz_mvf) && c->d_tr_mv_r.ensure(slots * sz_mvr) && c->d_tr_own.ensure(slots * sz_own) &&
               c->d_tr_own_pred.ensure((size_t)slots * n) && c->d_tr_cb_f.ensure(slots * sz_cb) && c->d_tr_cb_r.ensure(slots * sz_cb) &&
-              c->d_tr_lastcol.ensure(slots * sz_last) && c->d_slot_runs.ensure((size_t)slots * ws.run_cap) &&
+              c->d_tr_lastcol.ensure(slots * sz_last) && c->d_tr_colmax.ensure((size_t)slots * 2 * ws.LP) && c->d_slot_runs.ensure((size_t)slots * ws.run_cap) &&
               c->d_out_runs.ensure(out_runs_cap) && c->d_results.ensure(c->n_reads + 1) && c->d_counters.ensure(4);
     if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
     ws.tables = c->d_tr_tables.p;
@@ -790,6 +790,7 @@ static int align_pathwise(rg_ctx* c, int mode) {
     ws.cb_f = c->d_tr_cb_f.p;
     ws.cb_r = c->d_tr_cb_r.p;
     ws.lastcol = c->d_tr_lastcol.p;
+    ws.colmax = c->d_tr_colmax.p;
     ws.runs = c->d_slot_runs.p;
     PoaBatch b{};
     b.reads = c->d_reads.p;

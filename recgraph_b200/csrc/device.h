@@ -160,6 +160,7 @@ struct PwtWorkspace {
     int2* cb_f;         // slots * n * LP               modes 8/9: per (row, column) {max over all slots, path | member << 31}
     int2* cb_r;
     int32_t* lastcol;   // slots * n * Pp
+    int32_t* colmax;    // slots * 2 * LP           modes 8/9: column maxima of cb_f / cb_r
     rg_run* runs;       // slots * run_cap
     uint32_t LP, LT, Pp, CPT;   // columns (= 256 * CPT), table row stride (LP + 32), padded paths, columns per thread
     uint32_t TRmax, ringmax;

@@ -225,6 +225,7 @@ struct PwtDirBufs {
     uint8_t* mv;     // leader moves of this direction: [group][LP / 4]
     int2* cb;        // modes 8/9 per-(row, column) maxima, or nullptr
     int32_t* lastcol;// forward pass of modes 8/9: [row][Pp], or nullptr
+    int32_t* colmax; // modes 8/9: [LP] column maxima of the member entries of cb, or nullptr
 };
 
 struct PwtCtx {
@@ -334,6 +335,9 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                          int L, bool rev, bool free_border, bool track_best, bool track_results, bool fpred_rows, int gap) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = g.n, P = g.P, PW = g.PW, RM = g.ring - 1, TM = g.TR - 1;
+    int cmax[CPT];   // modes 8/9: per column, the maximum over the rows of the member entries written to d.cb
+#pragma unroll
+    for (int k = 0; k < CPT; k++) cmax[k] = NEG_INF;
     const uint32_t LP = cx.LP, LT = cx.LT, Pp = cx.Pp;
     const unsigned ZC = LP;                       // the all-zero column every table has
     const int j0 = tid * CPT;
@@ -693,6 +697,7 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
                         memb = false;
                     }
                     e[h] = make_int2(val, (int)((unsigned)path | (memb ? 0x80000000u : 0u)));
+                    if (memb) cmax[k + h] = max(cmax[k + h], val);
                 }
                 *reinterpret_cast<int4*>(out + k) = make_int4(e[0].x, e[0].y, e[1].x, e[1].y);
             }
@@ -753,6 +758,10 @@ __device__ void pwt_pass(const DevPathGraph& g, const PwtCtx& cx, const PwtDirBu
         sh.best_val = bval;
         sh.best_row = brow;
         sh.best_path = bpath;
+    }
+    if (d.colmax) {
+#pragma unroll
+        for (int k = 0; k < CPT; k++) d.colmax[j0 + k] = cmax[k];
     }
     __syncthreads();
 }
@@ -956,7 +965,7 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 4 : ((CPT <= 16) ? 2 : 1))
         off += (size_t)LP;
         cx.s_mx = reinterpret_cast<int2*>(s_dyn + off);   // modes 8/9 only: [LT]
     }
-    uint32_t* s_surv = reinterpret_cast<uint32_t*>(cx.s_wb);   // best_alignment reuses the DP staging arrays (LP >= 1024 words)
+    uint32_t* s_surv = reinterpret_cast<uint32_t*>(cx.s_mx);   // best_alignment: survivors in the per-origin maxima's space (2 * LT words)
     PwtDirBufs fwd, rvd;
     fwd.mv = ws.mv_f + (size_t)slot * g.n_groups * (LP / 4);
     fwd.cb = rec_mode ? ws.cb_f + (size_t)slot * n * LP : nullptr;
@@ -964,6 +973,8 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 4 : ((CPT <= 16) ? 2 : 1))
     rvd.mv = rec_mode ? ws.mv_r + (size_t)slot * rg_.n_groups * (LP / 4) : nullptr;
     rvd.cb = rec_mode ? ws.cb_r + (size_t)slot * n * LP : nullptr;
     rvd.lastcol = nullptr;
+    fwd.colmax = rec_mode ? ws.colmax + (size_t)slot * 2 * LP : nullptr;
+    rvd.colmax = rec_mode ? ws.colmax + (size_t)slot * 2 * LP + LP : nullptr;
     uint8_t* own = ws.own + (size_t)slot * n * (LP / 4);
     uint32_t* own_pred = ws.own_pred + (size_t)slot * n;
     rg_run* runs = ws.runs + (size_t)slot * ws.run_cap;
@@ -1118,23 +1129,37 @@ __global__ void __launch_bounds__(NT, (CPT <= 8) ? 4 : ((CPT <= 16) ? 2 : 1))
         mine.v = (float)base_score;
         mine.k1 = ~0ull;
         mine.k2 = ~0ull;
-        const uint32_t surv_cap = min((uint32_t)REC_SURV, LP);
-        for (int j = oob; j < L - oob; j++) {
-            const int jj = L - 1 - j;  // column of w in the reverse pass's coordinates
-            int wmax = NEG_INF;
-            for (uint32_t ri = 1 + tid; ri + 1 < n; ri += NT) {
-                const int2 e = rvd.cb[(size_t)ri * LP + jj];
-                if (e.y < 0) wmax = max(wmax, e.x);
+        const uint32_t surv_cap = min((uint32_t)REC_SURV, 2 * LT);
+        // Column bounds: no pair of column j can score above (max_i m[i][j] + max_ri w[ri][j]) - R when the displacement
+        // multiplier is not negative. The maxima were collected by the two passes; columns whose bound is below the running
+        // maximum are skipped without touching their entries, and the column with the best bound goes first so that the
+        // running maximum is close to final from the start. (The acceptance rule is order-free, see step 4.)
+        int32_t* s_cmf = cx.s_wb;   // staging arrays of the DP are free now
+        int32_t* s_cmr = cx.s_A;
+        for (uint32_t j = tid; j < LP; j += NT) {
+            s_cmf[j] = fwd.colmax[j];
+            s_cmr[j] = rvd.colmax[j];
+        }
+        __syncthreads();
+        int first_col = -1;
+        if (prune) {
+            long long bk = LLONG_MIN;
+            for (int j = oob + tid; j < L - oob; j += NT) {
+                const int a = s_cmf[j], bb = s_cmr[L - 1 - j];
+                if (a > NEG_INF / 2 && bb > NEG_INF / 2) bk = max(bk, ((long long)(a + bb) << 32) | (long long)(0xffffffffu - (uint32_t)j));
             }
-            wmax = __reduce_max_sync(FULL, wmax);
-            if (lane == 0) sh.red_i[warp] = wmax;
+            bk = block_max_ll(bk, sh);
+            if (bk != LLONG_MIN) first_col = (int)(0xffffffffu - (uint32_t)(bk & 0xffffffffll));
+        }
+        for (int jt = (first_col >= 0 ? oob - 1 : oob); jt < L - oob; jt++) {
+            const int j = (jt < oob) ? first_col : jt;
+            const int jj = L - 1 - j;  // column of w in the reverse pass's coordinates
+            const int wmax = s_cmr[jj];
+            const float cur = sh.rb_v;
+            if (wmax <= NEG_INF / 2 || s_cmf[j] <= NEG_INF / 2) continue;
+            if (prune && __fsub_rn((float)(s_cmf[j] + wmax), Rf) < cur) continue;
             if (tid == 0) sh.nsurv = 0;
             __syncthreads();
-            wmax = sh.red_i[0];
-            for (int k = 1; k < NWP; k++) wmax = max(wmax, sh.red_i[k]);
-            const float cur = sh.rb_v;
-            __syncthreads();
-            if (wmax <= NEG_INF / 2) continue;
             // survivors: forward nodes whose best case can still reach the running maximum
             for (uint32_t i = 1 + tid; i + 1 < n; i += NT) {
                 const int2 e = fwd.cb[(size_t)i * LP + j];
