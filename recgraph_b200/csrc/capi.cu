@@ -111,6 +111,7 @@ struct rg_ctx {
     DevBuf<uint8_t> d_tr_mv_f, d_tr_mv_r, d_tr_own;
     DevBuf<uint32_t> d_tr_own_pred;
     DevBuf<int2> d_tr_cb_f, d_tr_cb_r;
+    DevBuf<int32_t> d_gapT;
     bool pw_v1 = getenv("RG_PW_V1") != nullptr;   // testing: the per-path kernel of round 1 (pathwise.cu) for A/B runs
     DevBuf<int32_t> d_pwS, d_pwLead;
     DevBuf<uint32_t> d_pwTrace;
@@ -894,6 +895,60 @@ static int align_pathwise_v1(rg_ctx* c, int mode) {
     return RG_OK;
 }
 
+// Modes 6 / 7: affine-gap pathwise alignment (experimental in the reference), pathwise_gap.cu.
+static int align_pathwise_gap(rg_ctx* c, int mode) {
+    if (!c->has_path_graph)
+        return c->fail(c->path_graph_error.find("panics") != std::string::npos ? RG_ERR_REF_PANIC : RG_ERR_INVALID,
+                       c->path_graph_error.empty() ? "no path graph" : c->path_graph_error);
+    const FlatGraph& f = c->fg;
+    const uint32_t n = f.n;
+    if (f.P > 128) return c->fail(RG_ERR_UNSUPPORTED, "more than 128 paths are not supported on the device yet");
+    PwGapWorkspace ws{};
+    ws.Lp = c->max_len + 1;
+    ws.Pp = f.PW * 32;
+    ws.run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * ws.Lp), 1u << 22);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    free_b += c->d_gapT.cap * 4 + (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
+    const size_t per_slot = (size_t)3 * n * ws.Lp * ws.Pp * 4 + (size_t)ws.run_cap * sizeof(rg_run);
+    const size_t budget_all = (size_t)(free_b * 0.85);
+    size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(ws.run_cap, 16384), (budget_all / 8) / sizeof(rg_run));
+    out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
+    const size_t budget = budget_all - out_runs_cap * sizeof(rg_run);
+    uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * 4, (uint32_t)c->n_reads);
+    slots = (uint32_t)std::min<size_t>(slots, budget / per_slot);
+    if (slots < 1) return c->fail(RG_ERR_NOMEM, "not enough device memory for the three n x L x P tensors of one read (modes 6 / 7 keep the reference's footprint)");
+    ws.slots = slots;
+    if (!(c->d_gapT.ensure((size_t)slots * 3 * n * ws.Lp * ws.Pp) && c->d_slot_runs.ensure((size_t)slots * ws.run_cap) &&
+          c->d_out_runs.ensure(out_runs_cap) && c->d_results.ensure(c->n_reads + 1) && c->d_counters.ensure(4)))
+        return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
+    ws.T = c->d_gapT.p;
+    ws.runs = c->d_slot_runs.p;
+    PoaBatch b{};
+    b.reads = c->d_reads.p;
+    b.read_off = c->d_read_off.p;
+    b.n_reads = c->n_reads;
+    b.order = c->d_order.p;
+    b.results = c->d_results.p;
+    b.out_runs = c->d_out_runs.p;
+    b.out_run_cap = out_runs_cap;
+    b.counters = c->d_counters.p;
+    cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
+    cudaEventRecord(c->ev0, c->stream);
+    int rc = launch_pathwise_gap(mode, c->dpg, c->ds, ws, b, (int)slots, c->stream);
+    cudaEventRecord(c->ev1, c->stream);
+    if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("pathwise (affine) kernel");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->kernel_ms += ms;
+    c->launches += 1;
+    c->slots_used = slots;
+    cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("result copy");
+    c->n_runs_total = std::min<uint64_t>(c->h_counters.p[1], out_runs_cap);
+    return RG_OK;
+}
+
 int rg_align_staged(rg_ctx* c, int mode) {
     if (!c) return RG_ERR_INVALID;
     if (!c->has_graph) return c->fail(RG_ERR_INVALID, "no graph loaded");
@@ -919,6 +974,8 @@ int rg_align_staged(rg_ctx* c, int mode) {
         case RG_MODE_PATHWISE_SEMIGLOBAL:
         case RG_MODE_REC_GLOBAL:
         case RG_MODE_REC_SEMIGLOBAL: rc = align_pathwise(c, mode); break;
+        case RG_MODE_PATHWISE_GAP_GLOBAL:
+        case RG_MODE_PATHWISE_GAP_SEMIGLOBAL: rc = align_pathwise_gap(c, mode); break;
         default: return c->fail(RG_ERR_UNSUPPORTED, "alignment mode not implemented on the device yet");
     }
     if (rc != RG_OK) return rc;

@@ -171,6 +171,14 @@ int pathwise_tr_cpt(uint32_t Lmax);   // columns per thread for reads of up to L
 int pathwise_tr_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws, bool rec, int* nb);
 int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws,
                        const PoaBatch& b, int blocks, void* stream);
+// Modes 6 / 7 (pathwise_gap.cu): the reference's three delta-encoded tensors per read in flight.
+struct PwGapWorkspace {
+    int32_t* T;      // slots * 3 * n * Lp * Pp   (dpm, x, y)
+    rg_run* runs;    // slots * run_cap
+    uint32_t Lp, Pp, run_cap, slots;
+};
+int launch_pathwise_gap(int mode, const DevPathGraph& g, const DevScoring& s, const PwGapWorkspace& ws, const PoaBatch& b, int blocks,
+                        void* stream);
 constexpr int REC_SURV = 2048;  // forward nodes of one column staged for the pair expansion
 int pathwise_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const PwWorkspace& ws, bool rec, int* nb);
 int launch_pathwise(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwWorkspace& ws,

@@ -195,6 +195,7 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
     struct Batch {
         std::vector<std::string> warn, record;
         std::vector<int32_t> score;
+        std::vector<uint32_t> best_path;
     };
     std::vector<char> buf(1 << 16);
     int fail_code = 0;
@@ -214,7 +215,9 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
         bt.warn.resize(n);
         bt.record.resize(n);
         bt.score.resize(n);
+        bt.best_path.resize(n);
         for (int32_t k = 0; k < n; k++) {
+            bt.best_path[k] = res.reads[k].best_path;
             const int32_t i = idx.empty() ? k : idx[k];
             if (res.reads[k].status & RG_READ_REF_PANIC) {
                 fail_code = panic("reference panic while aligning read " + std::to_string(i + 1) + " (see DESIGN.md, reference quirks)");
@@ -278,6 +281,12 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
         size_t number = mode <= 3 ? (size_t)i + 1 : (size_t)i;
         // warning lines are println!'d to stdout by the reference even with -o; only the record goes to the file
         out += fwd.warn[i];
+        if (mode == 6 || mode == 7) {
+            // main.rs:271-288: exec println!s the CIGAR line, main the best path; no GAF record, -o is not used
+            out += fwd.record[i];
+            out += "Best path sequence " + std::to_string(i) + ": " + std::to_string(fwd.best_path[i]) + "\n";
+            continue;
+        }
         const std::string* rec = &fwd.record[i];
         if (rev_of[i] >= 0) {
             const int32_t k = rev_of[i];

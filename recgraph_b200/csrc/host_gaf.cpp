@@ -405,6 +405,29 @@ void format_gaf(const FlatGraph& g, int mode, const rg_read_result& r, const rg_
             gaf_line(out, name, read_len, 0, read_len - 1, '+', fp.handles, plen, ps, pe, 0, comments);
             break;
         }
+        case RG_MODE_PATHWISE_GAP_GLOBAL:
+        case RG_MODE_PATHWISE_GAP_SEMIGLOBAL: {
+            // pathwise_alignment_gap.rs:563-573 / pathwise_alignment_gap_semi.rs:434-445: the CIGAR line exec println!s
+            // (main.rs:277,286 then prints "Best path sequence ..."; the CLI adds that line). Runs arrive in traceback order;
+            // mode 6 drops the LAST element of the reversed list, i.e. the first traceback step (…_output.rs:304-305).
+            CigarBuilder cb;
+            for (uint32_t k = r.n_runs; k-- > 0;) {
+                uint32_t cnt = run_count(runs[k]);
+                if (mode == RG_MODE_PATHWISE_GAP_GLOBAL && k == 0 && cnt > 0) cnt--;
+                if (cnt) cb.add(cigar_sym(run_op(runs[k])), cnt);
+            }
+            cb.flush();
+            out += cb.s;
+            if (mode == RG_MODE_PATHWISE_GAP_SEMIGLOBAL) {
+                out += "\t(";
+                append_u64(out, r.start_row);
+                out += ' ';
+                append_u64(out, r.rev_end_row);
+                out += ')';
+            }
+            out += '\n';
+            break;
+        }
         default: break;
     }
 }
