@@ -1,0 +1,890 @@
+"""SECOND, INDEPENDENT restatement of the reference's pathwise / recombination path — TEST INFRASTRUCTURE ONLY.
+
+Written in plain Python from the Rust sources alone (never from oracle/*.cpp), so that the C++ oracle — the checker of
+the CUDA path — is itself checked by a second reading of the reference for the parts the reference's own tests do not pin
+(tests/test_pyref_vs_oracle.py diffs the two on the example and on hundreds of random small graphs):
+
+  pathwise_graph.rs:135-354                      create_path_graph, create_reverse_path_graph, displacement
+  pathwise_alignment.rs:5-340                    mode 4 exec
+  pathwise_alignment_semiglobal.rs:6-277         mode 5 exec, best_ending_node
+  pathwise_alignment_output.rs:7-184,471-556     build_alignment, build_cigar
+  pathwise_alignment_recombination.rs:9-897      exec, rev_align, align, absolute_scores, best_alignment, ending_node
+  recombination_output.rs:12-782                 the four gaf_output_* builders
+  utils.rs:221-323, gaf_output.rs:70-94          get_path_len_start_end, get_rec_path_len_start_end, GAFStruct::to_string
+  score_matrix.rs:35-51, sequences.rs:5-45, main.rs:253-312
+
+`rev_align` is `align` mirrored in i and j (checked mechanically: sed 's/i + 1/i - 1/; s/j + 1/j - 1/' on lines 129-435
+diffs clean against 436-745 apart from the border cases), so one cell routine parameterised by direction serves both.
+HashMap iteration orders of the reference (predecessors of a node) are fixed to ascending predecessor index.
+f32 arithmetic uses numpy.float32 so that every operation rounds as in Rust.
+"""
+import numpy as np
+
+F32 = np.float32
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def read_gfa(text):
+    """GFA1 S / L / P lines with integer segment names (gfa crate, GFA<usize, ()>)."""
+    segs, paths = {}, []
+    for ln in text.splitlines():
+        f = ln.split("\t")
+        if f[0] == "S":
+            segs[int(f[1])] = f[2]
+        elif f[0] == "P":
+            paths.append([int(s[:-1]) for s in f[2].split(",")])
+    return segs, paths
+
+
+def read_fasta(text):
+    """sequences.rs:5-45"""
+    names, seqs, cur = [], [], []
+    for line in text.splitlines():
+        if not line.startswith(">") and line != "":
+            cur += ["N" if c == "-" else c.upper() for c in line]
+        elif line.startswith(">"):
+            names.append(line[1:])
+            if cur:
+                seqs.append(["$"] + cur)
+            cur = []
+    if cur:
+        seqs.append(["$"] + cur)
+    assert len(seqs) == len(names), "wrong fasta file format"
+    return seqs, names
+
+
+def score_matrix_match_mis(m, x):
+    """score_matrix.rs:35-51"""
+    sm = {}
+    for i in "ACGTN-":
+        for j in "ACGTN-":
+            if i == j:
+                sm[(i, j)] = m
+            elif i == "-" or j == "-":
+                sm[(i, j)] = x * 2
+            else:
+                sm[(i, j)] = x
+    sm[("N", "N")] = x
+    del sm[("-", "-")]
+    return sm
+
+
+# ------------------------------------------------------------------------------------------------ graph
+class PathGraph:
+    pass
+
+
+def create_path_graph(segs, paths):
+    """pathwise_graph.rs:135-248 (is_reversed = false)"""
+    g = PathGraph()
+    lnz = ["$"]
+    ids = [0]
+    pos = {}
+    for sid in sorted(segs):
+        start = len(lnz)
+        for ch in segs[sid]:
+            lnz.append(ch)
+            ids.append(sid)
+        pos[sid] = (start, len(lnz) - 1)
+    lnz.append("F")
+    ids.append(0)
+    n, P = len(lnz), len(paths)
+    nwp = [False] * n
+    pred = {}  # node -> {pred -> set(paths)}
+    alphas = [P + 1] * n
+    pn = [set() for _ in range(n)]
+    pn[0] = set(range(P))
+    alphas[0] = 0
+    alphas[n - 1] = 0
+    for pid, path in enumerate(paths):
+        for k, sid in enumerate(path):
+            hs, he = pos[sid]
+            for idx in range(hs, he + 1):
+                pn[idx].add(pid)
+                if alphas[idx] == P + 1:
+                    alphas[idx] = pid
+            nwp[hs] = True
+            if k == 0:
+                pred.setdefault(hs, {}).setdefault(0, set()).add(pid)
+            else:
+                pe = pos[path[k - 1]][1]
+                pred.setdefault(hs, {}).setdefault(pe, set()).add(pid)
+                if k == len(path) - 1:
+                    pred.setdefault(n - 1, {}).setdefault(he, set()).add(pid)
+    nwp[n - 1] = True
+    pn[n - 1] = set(range(P))
+    g.lnz, g.nwp, g.pred, g.pn, g.alphas, g.P, g.ids = lnz, nwp, pred, pn, alphas, P, ids
+    return g
+
+
+def create_reverse_path_graph(fg):
+    """pathwise_graph.rs:250-282"""
+    g = PathGraph()
+    n = len(fg.lnz)
+    nwp = [False] * n
+    pred = {}
+    for node, ps in fg.pred.items():
+        for p, paths in ps.items():
+            nwp[p] = True
+            for q in paths:
+                pred.setdefault(p, {}).setdefault(node, set()).add(q)
+    g.lnz, g.nwp, g.pred, g.pn, g.alphas, g.P, g.ids = fg.lnz, nwp, pred, fg.pn, fg.alphas, fg.P, fg.ids
+    return g
+
+
+def preds_and_paths(g, node):
+    """PredHash::get_preds_and_paths; the reference unwrap()s a missing entry."""
+    return sorted(g.pred[node].items())
+
+
+def distance_from_start(rg):
+    """pathwise_graph.rs:306-329 (called with the REVERSE graph)"""
+    n = len(rg.lnz)
+    r = [-1] * n
+    r[0] = 0
+    for p, _ in preds_and_paths(rg, 0):
+        r[p] = 1
+    for i in range(1, n - 1):
+        if r[i] == -1 or r[i] > r[i - 1] + 1:
+            r[i] = r[i - 1] + 1
+        if rg.nwp[i]:
+            for p, _ in preds_and_paths(rg, i):
+                if r[p] == -1 or r[p] > r[i] + 1:
+                    r[p] = r[i] + 1
+    return r
+
+
+def distance_from_end(g):
+    """pathwise_graph.rs:330-354"""
+    n = len(g.lnz)
+    r = [-1] * n
+    r[n - 1] = 0
+    for p, _ in preds_and_paths(g, n - 1):
+        r[p] = 1
+    for i in range(n - 2, 0, -1):
+        if r[i] == -1 or r[i] > r[i + 1] + 1:
+            r[i] = r[i + 1] + 1
+        if g.nwp[i]:
+            for p, _ in preds_and_paths(g, i):
+                if r[p] == -1 or r[p] > r[i] + 1:
+                    r[p] = r[i] + 1
+    return r
+
+
+class Displacement:
+    """pathwise_graph.rs:284-305 without materialising the n x n matrix"""
+
+    def __init__(self, g, rg):
+        self.dfe = distance_from_end(g)
+        self.dfs = distance_from_start(rg)
+
+    def at(self, i, j):
+        if i == j:
+            return 0
+        return abs(self.dfs[i] - self.dfs[j]) + abs(self.dfe[i] - self.dfe[j])
+
+
+# ------------------------------------------------------------------------------------------------ the delta-encoded DP
+def _dp(seq, g, sm, rev, free_border, border_is_dp):
+    """pathwise_alignment.rs:19-304 / pathwise_alignment_semiglobal.rs:19-225 (rev = False) and
+    pathwise_alignment_recombination.rs:146-431 (rev = True). free_border: the border column is all zeros."""
+    lnz, nwp, pn, alphas, P = g.lnz, g.nwp, g.pn, g.alphas, g.P
+    n, L = len(lnz), len(seq)
+    dpm = [[[0] * P for _ in range(L)] for _ in range(n)]
+    di = 1 if rev else -1
+
+    def border(i, j):  # (_, 0) forward / j == last_char_pos reverse
+        ip = i + di
+        if not nwp[i]:
+            common = pn[i] & pn[ip]
+            if alphas[ip] in common:
+                for path in sorted(common):
+                    if path == alphas[i]:
+                        dpm[i][j][path] = dpm[ip][j][path] + sm[(lnz[i], "-")]
+                    else:
+                        dpm[i][j][path] = dpm[ip][j][path]
+            else:
+                dpm[i][j][alphas[i]] = dpm[ip][j][alphas[i]] + dpm[ip][j][alphas[ip]] + sm[(lnz[i], "-")]
+                for path in sorted(common):
+                    if path != alphas[i]:
+                        dpm[i][j][path] = dpm[ip][j][path] - dpm[ip][j][alphas[i]]
+        else:
+            alphas_deltas = {}
+            for p, p_paths in preds_and_paths(g, i):
+                common = pn[i] & p_paths
+                paths = sorted(common)
+                if alphas[p] in common:
+                    alphas_deltas[alphas[p]] = paths
+                    dpm[i][j][alphas[p]] = dpm[p][j][alphas[p]] + sm[(lnz[i], "-")]
+                    for path in paths:
+                        if path != alphas[p]:
+                            dpm[i][j][path] = dpm[p][j][path]
+                else:
+                    ta = alphas[i] if alphas[i] in common else paths[0]
+                    alphas_deltas[ta] = paths
+                    dpm[i][j][ta] = dpm[p][j][alphas[p]] + dpm[p][j][ta] + sm[(lnz[i], "-")]
+                    for path in paths:
+                        if path != ta:
+                            dpm[i][j][path] = dpm[p][j][path] - dpm[p][j][ta]
+            for a in sorted(alphas_deltas):
+                if a != alphas[i]:
+                    dpm[i][j][a] -= dpm[i][j][alphas[i]]
+                    for path in alphas_deltas[a]:
+                        if path != a:
+                            dpm[i][j][path] += dpm[i][j][a]
+
+    def general(i, j):
+        ip, jp = i + di, j + di
+        sub, gi_, gj_ = sm[(lnz[i], seq[j])], sm[(lnz[i], "-")], sm[(seq[j], "-")]
+        if not nwp[i]:
+            common = pn[i] & pn[ip]
+            ai, ap = alphas[i], alphas[ip]
+            if ap in common:
+                u = dpm[ip][j][ap] + gi_
+                d = dpm[ip][jp][ap] + sub
+                l = dpm[i][jp][ai] + gj_
+                best = max(d, u, l)
+                dpm[i][j][ai] = best
+                for path in common:
+                    if path != ai:
+                        if best == d:
+                            dpm[i][j][path] = dpm[ip][jp][path]
+                        elif best == u:
+                            dpm[i][j][path] = dpm[ip][j][path]
+                        else:
+                            dpm[i][j][path] = dpm[i][jp][path]
+            else:
+                u = dpm[ip][j][ap] + dpm[ip][j][ai] + gi_
+                d = dpm[ip][jp][ap] + dpm[ip][jp][ai] + sub
+                l = dpm[i][jp][ai] + gj_
+                best = max(d, u, l)
+                dpm[i][j][ai] = best
+                for path in common:
+                    if path != ai:
+                        if best == d:
+                            dpm[i][j][path] = dpm[ip][jp][path] - dpm[ip][jp][ai]
+                        elif best == u:
+                            dpm[i][j][path] = dpm[ip][j][path] - dpm[ip][j][ai]
+                        else:
+                            dpm[i][j][path] = dpm[i][jp][path]
+        else:
+            alphas_deltas = {}
+            ai = alphas[i]
+            for p, p_paths in preds_and_paths(g, i):
+                common = pn[i] & p_paths
+                paths = sorted(common)
+                ap = alphas[p]
+                if ap in common:
+                    alphas_deltas[ap] = paths
+                    u = dpm[p][j][ap] + gi_
+                    d = dpm[p][jp][ap] + sub
+                    if ai == ap:
+                        l = dpm[i][jp][ap] + gj_
+                    else:
+                        l = dpm[i][jp][ap] + dpm[i][jp][ai] + gj_
+                    best = max(d, u, l)
+                    dpm[i][j][ap] = best
+                    for path in paths:
+                        if path != ap:
+                            if best == d:
+                                dpm[i][j][path] = dpm[p][jp][path]
+                            elif best == u:
+                                dpm[i][j][path] = dpm[p][j][path]
+                            elif ap == ai:
+                                dpm[i][j][path] = dpm[i][jp][path]
+                            else:
+                                dpm[i][j][path] = dpm[i][jp][path] - dpm[i][jp][ap]
+                else:
+                    ta = ai if ai in common else paths[0]
+                    alphas_deltas[ta] = paths
+                    u = dpm[p][j][ap] + dpm[p][j][ta] + gi_
+                    d = dpm[p][jp][ap] + dpm[p][jp][ta] + sub
+                    if ai == ta:
+                        l = dpm[i][jp][ta] + gj_
+                    else:
+                        l = dpm[i][jp][ta] + dpm[i][jp][ai] + gj_
+                    best = max(d, u, l)
+                    dpm[i][j][ta] = best
+                    for path in paths:
+                        if path != ta:
+                            if best == d:
+                                dpm[i][j][path] = dpm[p][jp][path] - dpm[p][jp][ta]
+                            elif best == u:
+                                dpm[i][j][path] = dpm[p][j][path] - dpm[p][j][ta]
+                            elif ta == ai:
+                                dpm[i][j][path] = dpm[i][jp][path]
+                            else:
+                                dpm[i][j][path] = dpm[i][jp][path] - dpm[i][jp][ta]
+            for a in sorted(alphas_deltas):
+                if a != ai:
+                    dpm[i][j][a] -= dpm[i][j][ai]
+                    for path in alphas_deltas[a]:
+                        if path != a:
+                            dpm[i][j][path] += dpm[i][j][a]
+
+    if not rev:
+        for i in range(0, n - 1):
+            for j in range(0, L):
+                if i == 0 and j == 0:
+                    pass
+                elif j == 0:
+                    if not free_border:
+                        border(i, j)
+                elif i == 0:
+                    a0 = alphas[0]
+                    dpm[i][j][a0] = dpm[i][j - 1][a0] + sm[(seq[j], "-")]
+                    for k in range(a0 + 1, P):
+                        dpm[i][j][k] = dpm[i][j - 1][k]
+                else:
+                    general(i, j)
+    else:
+        last_i, last_j = n - 1, L - 1
+        for i in range(last_i, 0, -1):
+            for j in range(last_j, 0, -1):
+                if i == last_i and j == last_j:
+                    pass
+                elif i == last_i:
+                    a = alphas[i]
+                    dpm[i][j][a] = dpm[i][j + 1][a] + sm[(seq[j], "-")]
+                    for k in range(a + 1, P):
+                        dpm[i][j][k] = dpm[i][j + 1][k]
+                elif j == last_j:
+                    if not free_border:
+                        border(i, j)
+                else:
+                    general(i, j)
+    return dpm
+
+
+# ------------------------------------------------------------------------------------------------ output helpers
+def build_cigar(cigar):
+    """pathwise_alignment_output.rs:471-556"""
+    out = ""
+    d = u = l = mm = 0
+    for ch in cigar:
+        if ch == "D":
+            if u:
+                out += f"{u}I"
+                u = 0
+            if l:
+                out += f"{l}D"
+                l = 0
+            if mm:
+                out += f"{mm}X"
+                mm = 0
+            d += 1
+        elif ch == "U":
+            if d:
+                out += f"{d}M"
+                d = 0
+            if l:
+                out += f"{l}D"
+                l = 0
+            if mm:
+                out += f"{mm}X"
+                mm = 0
+            u += 1
+        elif ch == "d":
+            if d:
+                out += f"{d}M"
+                d = 0
+            if l:
+                out += f"{l}D"
+                l = 0
+            if u:
+                out += f"{u}I"
+                u = 0
+            mm += 1
+        else:
+            if d:
+                out += f"{d}M"
+                d = 0
+            if u:
+                out += f"{u}I"
+                u = 0
+            if mm:
+                out += f"{mm}X"
+                mm = 0
+            l += 1
+    if d:
+        out += f"{d}M"
+    if u:
+        out += f"{u}I"
+    if l:
+        out += f"{l}D"
+    if mm:
+        out += f"{mm}X"
+    return out
+
+
+def dedup(v):
+    out = []
+    for x in v:
+        if not out or out[-1] != x:
+            out.append(x)
+    return out
+
+
+def get_path_len_start_end(ids, start, end, path_len):
+    """utils.rs:221-254"""
+    path_start = 0
+    if start > 0:
+        first = ids[start]
+        counter = start - 1
+        while counter > 0 and ids[counter] == first:
+            counter -= 1
+            path_start += 1
+    path_end = path_start + path_len - 1 if path_len > 0 else 0
+    end_offset = 0
+    if end > 0:
+        last = ids[end]
+        counter = end + 1
+        while counter < len(ids) - 1 and ids[counter] == last:
+            counter += 1
+            end_offset += 1
+    return path_end + end_offset + 1, path_start, path_end
+
+
+def get_rec_path_len_start_end(ids, fen, rsn, start, end, forw_len, rev_len):
+    """utils.rs:256-323"""
+    def back(row):
+        c = 0
+        if row > 0:
+            first = ids[row]
+            counter = row - 1
+            while counter > 0 and ids[counter] == first:
+                counter -= 1
+                c += 1
+        return c
+
+    def fwd(row):
+        c = 0
+        if row > 0:
+            last = ids[row]
+            counter = row + 1
+            while counter < len(ids) - 1 and ids[counter] == last:
+                counter += 1
+                c += 1
+        return c
+
+    path_start = back(start)
+    forw_path_end = path_start + forw_len - 1 if forw_len > 0 else 0
+    forw_path_len = forw_path_end + fwd(fen) + 1
+    rev_path_start = back(rsn)
+    rev_path_end = rev_path_start + rev_len - 1 if rev_len > 0 else 0
+    path_end = forw_path_len + rev_path_end
+    rev_path_len = rev_path_end + fwd(end) + 1
+    return forw_path_len + rev_path_len, path_start, path_end
+
+
+def get_node_offset(ids, node):
+    """pathwise_alignment_recombination.rs:9-22"""
+    h = ids[node]
+    if h == 0:
+        return 0
+    counter, off = node, 0
+    while ids[counter - 1] == h:
+        counter -= 1
+        off += 1
+    return off
+
+
+def gaf_string(name, qlen, qs, qe, strand, path, plen, ps, pe, residues, abl, mq, comments):
+    """gaf_output.rs:70-94"""
+    return "\t".join([name, str(qlen), str(qs), str(qe), strand, ">" + ">".join(str(x) for x in path), str(plen), str(ps),
+                      str(pe), str(residues), abl, mq, comments])
+
+
+def f32_display(v):
+    """Rust `{}` of an f32: shortest decimal that round-trips, never scientific, integers without a fraction."""
+    s = np.format_float_positional(F32(v), unique=True, trim="-")
+    return s
+
+
+# ------------------------------------------------------------------------------------------------ modes 4 / 5
+def build_alignment(dpm, g, seq, sm, best_path, ending_node, global_align, name):
+    """pathwise_alignment_output.rs:7-184"""
+    lnz, alphas, nwp, ids = g.lnz, g.alphas, g.nwp, g.ids
+    cigar, hia, pseq = [], [], []
+    path_length = 0
+    i, j = ending_node, len(dpm[ending_node]) - 1
+
+    def absv(ii, jj):
+        if alphas[ii] == best_path:
+            return dpm[ii][jj][best_path]
+        return dpm[ii][jj][best_path] + dpm[ii][jj][alphas[ii]]
+
+    score = absv(i, j)
+    while i > 0 and j > 0:
+        predecessor = None
+        if not nwp[i]:
+            d = absv(i - 1, j - 1) + sm[(lnz[i], seq[j])]
+            u = absv(i - 1, j) + sm[(lnz[i], "-")]
+            l = absv(i, j - 1) + sm[("-", seq[j])]
+        else:
+            d = u = l = 0
+            for pred, paths in preds_and_paths(g, i):
+                if best_path in paths:
+                    predecessor = pred
+                    d = absv(pred, j - 1) + sm[(lnz[i], seq[j])]
+                    u = absv(pred, j) + sm[(lnz[i], "-")]
+                    l = absv(i, j - 1) + sm[("-", seq[j])]
+        mx = max(d, u, l)
+        if mx == d:
+            cigar.append("d" if lnz[i] != seq[j] else "D")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            i = i - 1 if predecessor is None else predecessor
+            j -= 1
+            path_length += 1
+        elif mx == u:
+            cigar.append("U")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            i = i - 1 if predecessor is None else predecessor
+            path_length += 1
+        else:
+            cigar.append("L")
+            j -= 1
+    while j > 0:
+        cigar.append("L")
+        j -= 1
+    if global_align:
+        while i > 0:
+            cigar.append("U")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            path_length += 1
+            if not nwp[i]:
+                i = i - 1
+            else:
+                p = 0
+                for pred, paths in preds_and_paths(g, i):
+                    if best_path in paths:
+                        p = pred
+                i = p
+    cigar.reverse()
+    pseq.reverse()
+    L = len(dpm[0])
+    hia = dedup(hia)
+    hia.reverse()
+    plen, ps, pe = get_path_len_start_end(ids, i if i == 0 else i + 1, ending_node, path_length)
+    comments = f"{build_cigar(cigar)}, best path: {best_path}, score: {score}\t{''.join(pseq)}"
+    return gaf_string(name, L - 1, 0, L - 2, "+", hia, plen, ps, pe, 0, "*", "*", comments)
+
+
+def mode4(seq, g, sm, name):
+    """pathwise_alignment.rs:5-340"""
+    dpm = _dp(seq, g, sm, False, False, True)
+    n, L, P = len(g.lnz), len(seq), g.P
+    ending = [0] * P
+    results = [0] * P
+    for pred, paths in preds_and_paths(g, n - 1):
+        for path in sorted(paths):
+            if path == g.alphas[pred]:
+                results[path] = dpm[pred][L - 1][path]
+            else:
+                results[path] = dpm[pred][L - 1][path] + dpm[pred][L - 1][g.alphas[pred]]
+            ending[path] = pred
+    best = max((s, p) for p, s in enumerate(results))[1]
+    return build_alignment(dpm, g, seq, sm, best, ending[best], True, name)
+
+
+def mode5(seq, g, sm, name):
+    """pathwise_alignment_semiglobal.rs:6-277"""
+    dpm = _dp(seq, g, sm, False, True, True)
+    n, L, P = len(g.lnz), len(seq), g.P
+    mx, ending_node, chosen = None, 0, 0
+    for i in range(1, n - 1):
+        paths = g.pn[i]
+        ab = list(dpm[i][L - 1])
+        for path in sorted(paths):
+            if path != g.alphas[i]:
+                ab[path] = ab[path] + ab[g.alphas[i]]
+        bp = None
+        for path, score in enumerate(ab):
+            if path in paths and (bp is None or bp[0] < score):
+                bp = (score, path)
+        if mx is None or bp[0] > mx:
+            mx, ending_node, chosen = bp[0], i, bp[1]
+    return build_alignment(dpm, g, seq, sm, chosen, ending_node, False, name)
+
+
+# ------------------------------------------------------------------------------------------------ modes 8 / 9
+def absolute_scores(dpm, g):
+    """pathwise_alignment_recombination.rs:747-757 (the last row is left as it is)"""
+    for i in range(len(dpm) - 1):
+        a = g.alphas[i]
+        for j in range(len(dpm[i])):
+            row = dpm[i][j]
+            for path in g.pn[i]:
+                if path != a:
+                    row[path] += row[a]
+
+
+def get_rev_sequence(seq):
+    return list(seq[1:]) + ["F"]
+
+
+def best_alignment(m, w, displ, brc, mrc, mode, g, rbw):
+    """pathwise_alignment_recombination.rs:759-873"""
+    n, L, P = len(m), len(m[0]), g.P
+    pn, ids = g.pn, g.ids
+    mx, best_path = None, None
+    if mode == 8:
+        for pred, paths in preds_and_paths(g, n - 1):
+            for path in sorted(paths):
+                if mx is None or mx < m[pred][L - 1][path]:
+                    mx, best_path = m[pred][L - 1][path], path
+    else:
+        for i in range(n - 1):
+            for path in range(P):
+                if path in pn[i]:
+                    if mx is None or mx < m[i][L - 1][path]:
+                        mx, best_path = m[i][L - 1][path], path
+    curr = F32(mx)
+    fbp = rbp = best_path
+    onedge = False
+    oob = max(int(F32(F32(L) * F32(F32(1.0) - F32(rbw))) / F32(2.0)), 1)
+    fen = rsn = col = 0
+    rec_pen = 0
+    brc_f, mrc_f = F32(brc), F32(mrc)
+    # The triple loop of the reference, with the innermost loop (over rev_i, ascending) evaluated as numpy float32 vectors:
+    # every candidate is computed with the same three separately rounded f32 operations, and the sequential acceptance rule
+    # is applied by jumping to the next index that satisfies it (each acceptance raises curr or sets onedge).
+    nid = np.array(ids)
+    inner = np.arange(1, n - 1)
+    edge_ri = nid[1:n - 1] != nid[0:n - 2]
+    dfs, dfe = np.array(displ.dfs), np.array(displ.dfe)
+    for j in range(oob, L - oob):
+        fp_of = [max((s, p) for p, s in enumerate(m[i][j]))[1] for i in range(n)]
+        rp_of = [max((s, p) for p, s in enumerate(w[i][j]))[1] for i in range(n)]
+        rp_arr = np.array(rp_of[1:n - 1])
+        wv = np.array([w[ri][j][rp_of[ri]] for ri in range(1, n - 1)], dtype=np.int64)
+        rmemb = np.array([rp_of[ri] in pn[ri] for ri in range(1, n - 1)])
+        for i in range(1, n - 1):
+            fp = fp_of[i]
+            if fp not in pn[i]:
+                continue
+            ok = (nid[1:n - 1] != nid[i]) & (rp_arr != fp) & rmemb
+            if not ok.any():
+                continue
+            dd = np.abs(dfs[i] - dfs[1:n - 1]) + np.abs(dfe[i] - dfe[1:n - 1])
+            dd = np.where(inner == i, 0, dd)
+            penalty = (brc_f + (mrc_f * dd.astype(F32)).astype(F32)).astype(F32)
+            new = ((m[i][j][fp] + wv).astype(F32) - penalty).astype(F32)
+            iedge = (i + 1 == n or ids[i] != ids[i + 1])
+            edge = edge_ri & iedge
+            pos = 0
+            while True:
+                cond = ok & ((new > curr) | ((new == curr) & (not onedge) & edge))
+                cond[:pos] = False
+                hit = np.flatnonzero(cond)
+                if hit.size == 0:
+                    break
+                k = int(hit[0])
+                onedge = bool(edge[k])
+                curr = new[k]
+                fen, rsn, fbp, rbp, col, rec_pen = i, k + 1, fp, int(rp_arr[k]), j, int(dd[k])
+                pos = k + 1
+    return fen, rsn, fbp, rbp, col, (curr, rec_pen)
+
+
+def ending_node_of(dpm, best_path, g):
+    """pathwise_alignment_recombination.rs:885-897"""
+    best, node = None, 0
+    L = len(dpm[0])
+    for i in range(1, len(dpm) - 1):
+        if best_path in g.pn[i]:
+            if best is None or dpm[i][L - 1][best_path] > best:
+                best, node = dpm[i][L - 1][best_path], i
+    return node
+
+
+def _walk_fwd(dpm, g, seq, sm, best_path, i, j, pad_global):
+    """forward-matrix walk shared by the four builders (absolute scores)"""
+    lnz, nwp, ids = g.lnz, g.nwp, g.ids
+    cigar, hia, pseq = [], [], []
+    plen = 0
+    while i > 0 and j > 0:
+        predecessor = None
+        if not nwp[i]:
+            d = dpm[i - 1][j - 1][best_path] + sm[(lnz[i], seq[j])]
+            u = dpm[i - 1][j][best_path] + sm[(lnz[i], "-")]
+            l = dpm[i][j - 1][best_path] + sm[("-", seq[j])]
+        else:
+            d = u = l = 0
+            for pred, paths in preds_and_paths(g, i):
+                if best_path in paths:
+                    predecessor = pred
+                    d = dpm[pred][j - 1][best_path] + sm[(lnz[i], seq[j])]
+                    u = dpm[pred][j][best_path] + sm[(lnz[i], "-")]
+                    l = dpm[i][j - 1][best_path] + sm[("-", seq[j])]
+        mx = max(d, u, l)
+        if mx == d:
+            cigar.append("d" if lnz[i] != seq[j] else "D")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            i = i - 1 if predecessor is None else predecessor
+            j -= 1
+            plen += 1
+        elif mx == u:
+            cigar.append("U")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            i = i - 1 if predecessor is None else predecessor
+            plen += 1
+        else:
+            cigar.append("L")
+            j -= 1
+    while j > 0:
+        cigar.append("L")
+        j -= 1
+    if pad_global:
+        while i > 0:
+            cigar.append("U")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            predecessor = None
+            if nwp[i]:
+                for pred, paths in preds_and_paths(g, i):
+                    if best_path in paths:
+                        predecessor = pred
+            i = i - 1 if predecessor is None else predecessor
+            plen += 1
+    return cigar, hia, pseq, plen, i
+
+
+def gaf_no_rec(dpm, g, seq, sm, best_path, ending_node, glob, name):
+    """recombination_output.rs:239-361 (semiglobal) / 633-782 (global)"""
+    L = len(dpm[0])
+    if glob:
+        i = 0
+        for node, paths in preds_and_paths(g, len(dpm) - 1):
+            if best_path in paths:
+                i = node
+        ending_node = i
+    i, j = ending_node, L - 1
+    score = dpm[i][j][best_path]
+    cigar, hia, pseq, plen, i = _walk_fwd(dpm, g, seq, sm, best_path, i, j, glob)
+    cigar.reverse()
+    pseq.reverse()
+    hia = dedup(hia)
+    hia.reverse()
+    pl, ps, pe = get_path_len_start_end(g.ids, i if i == 0 else i + 1, ending_node, plen)
+    comments = f"{build_cigar(cigar)}, best path: {best_path}, score: {score}\t{''.join(pseq)}"
+    return gaf_string(name, L - 1, 0, L - 2, "+", hia, pl, ps, pe, 0, "*", "*", comments)
+
+
+def gaf_rec(dpm, rdpm, g, rg, seq, sm, bp, rbp, fen, rsn, rec_col, best_score, glob, name):
+    """recombination_output.rs:12-237 (semiglobal) / 363-631 (global)"""
+    lnz, ids = g.lnz, g.ids
+    n, L = len(dpm), len(dpm[0])
+    cigar, hia, pseq = [], [], []
+    rev_plen = 0
+    i, j = rsn, rec_col
+    rev_end = i
+    r_seq = get_rev_sequence(seq)
+    while i > 0 and i < n - 1 and j < L - 1:
+        predecessor = None
+        if not rg.nwp[i]:
+            d = rdpm[i + 1][j + 1][rbp] + sm[(lnz[i], r_seq[j])]
+            u = rdpm[i + 1][j][rbp] + sm[(lnz[i], "-")]
+            l = rdpm[i][j + 1][rbp] + sm[("-", r_seq[j])]
+        else:
+            d = u = l = 0
+            for pred, paths in preds_and_paths(rg, i):
+                if rbp in paths:
+                    predecessor = pred
+                    d = rdpm[pred][j + 1][rbp] + sm[(lnz[i], r_seq[j])]
+                    u = rdpm[pred][j][rbp] + sm[(lnz[i], "-")]
+                    l = rdpm[i][j + 1][rbp] + sm[("-", r_seq[j])]
+        mx = max(d, u, l)
+        rev_end = i
+        if mx == d:
+            cigar.append("d" if lnz[i] != r_seq[j] else "D")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            i = i + 1 if predecessor is None else predecessor
+            j += 1
+            rev_plen += 1
+        elif mx == u:
+            cigar.append("U")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            i = i + 1 if predecessor is None else predecessor
+            rev_plen += 1
+        else:
+            cigar.append("L")
+            j += 1
+    while j < L - 1:
+        cigar.append("L")
+        j += 1
+    if glob:
+        while i < n - 1:
+            cigar.append("U")
+            hia.append(ids[i])
+            pseq.append(lnz[i])
+            predecessor = None
+            if rg.nwp[i]:
+                for pred, paths in preds_and_paths(rg, i):
+                    if rbp in paths:
+                        predecessor = pred
+            i = i + 1 if predecessor is None else predecessor
+            rev_plen += 1
+    tc, th, tp, plen, i = _walk_fwd(dpm, g, seq, sm, bp, fen, rec_col, glob)
+    rec_edge = (len(tp) - 1) % (1 << 64)   # usize arithmetic of a release build
+    tc.reverse()
+    tc += cigar
+    th.reverse()
+    th += hia
+    th = dedup(th)
+    tp.reverse()
+    tp += pseq
+    start = i if i == 0 else i + 1
+    pl, ps, pe = get_rec_path_len_start_end(ids, fen, rsn, start, rev_end, plen, rev_plen)
+    if bp == rbp:
+        recomb = f"No recombination, best path: {bp}"
+    else:
+        recomb = (f"recombination path {bp} {rbp}, nodes {ids[fen]}[{get_node_offset(ids, fen)}] {ids[rsn]}[{get_node_offset(ids, rsn)}], "
+                  f"score: {f32_display(best_score[0])}, displacement: {best_score[1]}\t{''.join(tp)}\t{rec_edge}")
+    comments = f"{build_cigar(tc)}, {recomb}"
+    return gaf_string(name, L - 1, 0, L - 2, "+", th, pl, ps, pe, 0, "*", "*", comments)
+
+
+def mode89(mode, seq, g, rg, sm, brc, mrc, displ, rbw, name):
+    """pathwise_alignment_recombination.rs:23-127"""
+    free = mode == 9
+    m = _dp(seq, g, sm, False, free, True)
+    absolute_scores(m, g)
+    w = _dp(get_rev_sequence(seq), rg, sm, True, free, True)
+    absolute_scores(w, rg)
+    fen, rsn, fbp, rbp, col, score = best_alignment(m, w, displ, brc, mrc, mode, g, rbw)
+    if fbp == rbp:
+        if mode == 8:
+            return gaf_no_rec(m, g, seq, sm, fbp, None, True, name)
+        return gaf_no_rec(m, g, seq, sm, fbp, ending_node_of(m, fbp, g), False, name)
+    return gaf_rec(m, w, g, rg, seq, sm, fbp, rbp, fen, rsn, col, score, mode == 8, name)
+
+
+# ------------------------------------------------------------------------------------------------ driver
+def run(mode, fasta_text, gfa_text, match=2, mismatch=4, base_rec_cost=4, multi_rec_cost=0.1, rec_band_width=1.0, max_reads=None):
+    """main.rs:253-312 for modes 4, 5, 8, 9 with match / mismatch scoring; returns stdout."""
+    seqs, names = read_fasta(fasta_text)
+    segs, paths = read_gfa(gfa_text)
+    sm = score_matrix_match_mis(match, -mismatch)
+    g = create_path_graph(segs, paths)
+    out = []
+    if mode in (8, 9):
+        rg = create_reverse_path_graph(g)
+        displ = Displacement(g, rg)
+    for k, seq in enumerate(seqs):
+        if max_reads is not None and k >= max_reads:
+            break
+        if mode == 4:
+            out.append(mode4(seq, g, sm, names[k]))
+        elif mode == 5:
+            out.append(mode5(seq, g, sm, names[k]))
+        else:
+            out.append(mode89(mode, seq, g, rg, sm, base_rec_cost, multi_rec_cost, displ, rec_band_width, names[k]))
+    return "".join(x + "\n" for x in out)

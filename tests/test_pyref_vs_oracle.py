@@ -1,0 +1,67 @@
+"""Double pin of the parts of the path the reference's own tests do not cover: the C++ oracle (oracle/*.cpp, the
+checker of the CUDA path) against a SECOND, independent restatement written in Python from the Rust sources only
+(oracle/pyref/recgraph_pyref.py) — pathwise DP of modes 4 / 5, `align` / `rev_align` / `absolute_scores` /
+`best_alignment` of modes 8 / 9, `build_alignment`, the four `gaf_output_*` builders, path-length helpers and GAF text.
+Byte-identical stdout on the example and on 220 random small graphs (single source and sink)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from recgraph_b200 import synth
+from tests import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXAMPLE = os.path.join(ROOT, "tests", "golden", "example")
+_spec = importlib.util.spec_from_file_location("recgraph_pyref", os.path.join(ROOT, "oracle", "pyref", "recgraph_pyref.py"))
+pyref = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(pyref)
+
+
+def _oracle(mode, fa, gfa, extra=()):
+    rc, out, err = oracle_lib.run_cli(["-m", str(mode)] + list(extra) + [fa, gfa])
+    assert rc == 0, err
+    return out
+
+
+@pytest.mark.parametrize("mode", [4, 5, 8, 9])
+def test_example_first_reads(mode, tmp_path):
+    fa_text = open(os.path.join(EXAMPLE, "reads.fa")).read()
+    gfa_text = open(os.path.join(EXAMPLE, "graph.gfa")).read()
+    nreads = 2
+    lines = fa_text.splitlines()
+    fa = tmp_path / "r.fa"
+    fa.write_text("\n".join(lines[:2 * nreads]) + "\n")
+    got = pyref.run(mode, fa.read_text(), gfa_text)
+    assert got == _oracle(mode, str(fa), os.path.join(EXAMPLE, "graph.gfa"))
+
+
+def _case(seed):
+    rng = np.random.default_rng(seed)
+    bp = int(rng.integers(40, 130))
+    paths = int(rng.integers(2, 7))
+    g = synth.make_graph(bp, paths, seed=seed, mean_seg=int(rng.integers(3, 10)), p_snp=0.3, p_indel=0.15)
+    rlen = int(rng.integers(8, 40))
+    reads = synth.make_reads(g, 2, rlen, err=float(rng.choice([0.0, 0.05, 0.15])), seed=seed + 1, mosaic_breaks=int(rng.integers(0, 3)))
+    return g, reads
+
+
+@pytest.mark.parametrize("block", range(11))
+def test_random_small_graphs(block, tmp_path):
+    """20 graphs per block x modes 4, 5, 8, 9 (+ a second scoring for the recombination modes)."""
+    for seed in range(1000 + 20 * block, 1020 + 20 * block):
+        g, reads = _case(seed)
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        for mode in (4, 5, 8, 9):
+            got = pyref.run(mode, fa.read_text(), gfa.read_text())
+            exp = _oracle(mode, str(fa), str(gfa))
+            assert got == exp, f"seed {seed} mode {mode}:\n PY : {got[:500]}\n C++: {exp[:500]}"
+        if seed % 4 == 0:
+            for mode in (8, 9):
+                got = pyref.run(mode, fa.read_text(), gfa.read_text(), match=1, mismatch=3, base_rec_cost=1, multi_rec_cost=0.05,
+                                rec_band_width=0.7)
+                exp = _oracle(mode, str(fa), str(gfa), ["-M", "1", "-X", "3", "-R", "1", "-r", "0.05", "-B", "0.7"])
+                assert got == exp, f"seed {seed} mode {mode} (R=1 r=0.05 B=0.7)"
