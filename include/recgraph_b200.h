@@ -193,6 +193,13 @@ enum { RG_AMB_HANDLES = 2, RG_AMB_STRAND = 4 };
 int64_t rg_format_gaf(rg_ctx* ctx, int mode, const rg_batch_result* res, int32_t read_index, const char* read_name,
                       uint32_t read_len, int amb_mode, char* buf, size_t cap);
 
+/* The same for every read of a batch in input order, into one malloc'd buffer (free with rg_free): the per-read println! /
+ * write_gaf loop of main.rs:56-312 as one call, so that emitting GAF is not one FFI round trip per read. names may be NULL
+ * ("read<first_index + i>" is used, the naming of this repo's synthetic FASTA — first_index lets a shard of a larger read
+ * set keep its global numbering); read_off are the offsets given to rg_align_batch. */
+int rg_format_gaf_all(rg_ctx* ctx, int mode, const rg_batch_result* res, const char* const* names, int64_t first_index,
+                      const uint64_t* read_off, int amb_mode, char** out_text, size_t* out_len);
+
 /* FASTA reader with the reference's normalisation (sequences.rs:5-45: upper-case, '-' -> 'N'); encodes to codes.
  * Buffers are malloc'd; free with rg_free_reads. */
 typedef struct rg_reads {

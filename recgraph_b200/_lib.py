@@ -43,7 +43,7 @@ class Reads(ctypes.Structure):  # rg_reads
 SYMBOLS = ["rg_init", "rg_destroy", "rg_strerror", "rg_last_error", "rg_load_gfa_file", "rg_load_gfa_text",
            "rg_set_lnz_graph", "rg_graph_info", "rg_make_score_matrix", "rg_default_scoring", "rg_set_scoring",
            "rg_align_batch", "rg_upload_reads", "rg_align_staged", "rg_fetch_results", "rg_last_kernel_stats",
-           "rg_format_gaf", "rg_read_fasta_file", "rg_read_fasta_text", "rg_free_reads", "rg_cli_main", "rg_free",
+           "rg_format_gaf", "rg_format_gaf_all", "rg_read_fasta_file", "rg_read_fasta_text", "rg_free_reads", "rg_cli_main", "rg_free",
            "rg_int_peak", "rg_debug_dump_lnz", "rg_debug_dump_pathgraph"]
 
 _lib = None
@@ -87,6 +87,8 @@ def load():
     lib.rg_format_gaf.argtypes = [vp, ctypes.c_int, ctypes.POINTER(BatchResult), c_i32, ctypes.c_char_p, c_u32,
                                   ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
     lib.rg_format_gaf.restype = ctypes.c_int64
+    lib.rg_format_gaf_all.argtypes = [vp, ctypes.c_int, ctypes.POINTER(BatchResult), vp, ctypes.c_int64, vp, ctypes.c_int, ctypes.POINTER(vp),
+                                      ctypes.POINTER(ctypes.c_size_t)]
     lib.rg_read_fasta_file.argtypes = [ctypes.c_char_p, ctypes.POINTER(Reads), ctypes.c_char_p, ctypes.c_size_t]
     lib.rg_read_fasta_text.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(Reads), ctypes.c_char_p,
                                        ctypes.c_size_t]

@@ -169,6 +169,15 @@ class Aligner:
                                    buf, len(buf))
         return buf.value.decode()
 
+    def format_gaf_all(self, mode, res, off, amb_mode=False, first_index=0):
+        """GAF text of the whole batch in input order (read names "read<first_index + i>")."""
+        out, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(self.lib.rg_format_gaf_all(self.ctx, mode, ctypes.byref(res), None, first_index, off.ctypes.data, int(amb_mode),
+                                               ctypes.byref(out), ctypes.byref(n)))
+        text = ctypes.string_at(out, n.value).decode()
+        self.lib.rg_free(out)
+        return text
+
     def align(self, mode, reads, names=None):
         """Align a list of reads; returns (records, gaf_text)."""
         codes, off = self.pack_reads(reads)

@@ -1038,6 +1038,27 @@ int64_t rg_format_gaf(rg_ctx* c, int mode, const rg_batch_result* res, int32_t r
     return (int64_t)s.size();
 }
 
+int rg_format_gaf_all(rg_ctx* c, int mode, const rg_batch_result* res, const char* const* names, int64_t first_index,
+                      const uint64_t* read_off, int amb_mode, char** out_text, size_t* out_len) {
+    if (!c || !res || !read_off || !out_text || !c->has_graph) return RG_ERR_INVALID;
+    std::string s;
+    s.reserve((size_t)res->n_reads * 256);
+    char nm[32];
+    for (int32_t i = 0; i < res->n_reads; i++) {
+        const char* name = names ? names[i] : nm;
+        if (!names) snprintf(nm, sizeof nm, "read%lld", (long long)(first_index + i));
+        format_gaf(c->fg, mode, res->reads[i], res->runs, name, (uint32_t)(read_off[i + 1] - read_off[i]),
+                   amb_mode == 1 ? (RG_AMB_STRAND | RG_AMB_HANDLES) : amb_mode, s);
+    }
+    char* p = (char*)malloc(s.size() + 1);
+    if (!p) return RG_ERR_NOMEM;
+    memcpy(p, s.data(), s.size());
+    p[s.size()] = 0;
+    *out_text = p;
+    if (out_len) *out_len = s.size();
+    return RG_OK;
+}
+
 static int fill_reads(std::vector<std::string>& names, std::vector<uint8_t>& codes, std::vector<uint64_t>& off, rg_reads* out) {
     out->n_reads = (int32_t)names.size();
     out->codes = (uint8_t*)malloc(codes.size() + 1);
