@@ -149,6 +149,16 @@ int rg_load_gfa_text(rg_ctx* ctx, const char* text, size_t len);
  * entry in pred_hash have an empty range. seg_id may be NULL (GAF paths then use 0). Arrays are copied. */
 int rg_set_lnz_graph(rg_ctx* ctx, uint32_t n, const uint8_t* lnz_codes, const uint8_t* nwp,
                      const uint32_t* pred_off, const uint32_t* pred_idx, const uint64_t* seg_id);
+/* Replaces handing a prebuilt PathGraph {lnz, nwp, pred_hash, paths_nodes, alphas, paths_number, nodes_id_pos}
+ * (pathwise_graph.rs:10-18) to the pathwise exec functions — the form the reference's inline tests build
+ * (pathwise_graph.rs:364-544). PredHash as CSR: pred_off has n+1 entries, every (node, predecessor) entry k carries the
+ * bitset of the paths using that edge in edge_path_bits[k * PW .. (k+1) * PW), PW = (n_paths + 31) / 32, bit p of word
+ * p / 32. node_path_bits: n * PW words (paths_nodes); alphas: n entries; seg_id: nodes_id_pos (0 for rows 0 and n-1).
+ * The reverse graph and the distance vectors behind nodes_displacement_matrix (pathwise_graph.rs:250-354) are derived
+ * inside. Arrays are copied. After this call modes 4-9 use the given graph; the POA modes see the same predecessor lists. */
+int rg_set_path_graph(rg_ctx* ctx, uint32_t n, uint32_t n_paths, const uint8_t* lnz_codes, const uint8_t* nwp,
+                      const uint32_t* pred_off, const uint32_t* pred_idx, const uint32_t* edge_path_bits,
+                      const uint32_t* node_path_bits, const uint32_t* alphas, const uint64_t* seg_id);
 /* Graph facts for callers: n = lnz.len(), P = paths_number. */
 int rg_graph_info(const rg_ctx* ctx, uint32_t* n, uint32_t* n_segments, uint32_t* n_paths);
 

@@ -173,6 +173,29 @@ char* rgo_pathwise_one(const char* gfa_text, const char* read, int mode, int m, 
     }
 }
 
+// api.rs:11-40 (align_global_no_gap) and 76-99 (align_local_no_gap) with their defaults: f32 match/mismatch matrix whose
+// gap entries are X (score_matrix.rs:52-66), bases_to_add = (len * 0.1) as usize. Returns what exec_simd println!s
+// followed by the GAF record.
+char* rgo_api_no_gap(const char* gfa_text, const char* read, const char* name, int local) {
+    try {
+        HashGraph hg = parse_gfa_text(gfa_text);
+        std::vector<char> seq = build_align_string(read);
+        LnzGraph lg = create_graph_struct(hg, false);
+        ScoreMatrix sm = create_score_matrix_match_mis_f32(2, -4);
+        volatile float prod = (float)std::string(read).size() * 0.1f;
+        const size_t bta = (size_t)prod;
+        std::vector<size_t> r_values = set_r_values(lg);
+        std::vector<std::string> hofp = handle_pos_in_lnz(lg, hg, false);
+        std::string out;
+        PoaResult r = local ? local_poa_exec_simd(seq, name, 1, lg, sm, false, hofp, out)
+                            : global_abpoa_exec_simd(seq, name, 1, lg, sm, bta, false, hofp, r_values, out);
+        if (r.has_gaf) out += r.gaf.to_string() + "\n";
+        return dup(out);
+    } catch (const std::exception& ex) {
+        return dup(std::string("PANIC ") + ex.what());
+    }
+}
+
 char* rgo_rev_and_compl(const char* seq) {
     try {
         std::vector<char> s(seq, seq + strlen(seq));

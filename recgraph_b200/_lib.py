@@ -41,7 +41,7 @@ class Reads(ctypes.Structure):  # rg_reads
 
 # every symbol include/recgraph_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["rg_init", "rg_destroy", "rg_strerror", "rg_last_error", "rg_load_gfa_file", "rg_load_gfa_text",
-           "rg_set_lnz_graph", "rg_graph_info", "rg_make_score_matrix", "rg_default_scoring", "rg_set_scoring",
+           "rg_set_lnz_graph", "rg_set_path_graph", "rg_graph_info", "rg_make_score_matrix", "rg_default_scoring", "rg_set_scoring",
            "rg_align_batch", "rg_upload_reads", "rg_align_staged", "rg_fetch_results", "rg_last_kernel_stats",
            "rg_format_gaf", "rg_format_gaf_all", "rg_read_fasta_file", "rg_read_fasta_text", "rg_free_reads", "rg_cli_main", "rg_free",
            "rg_int_peak", "rg_debug_dump_lnz", "rg_debug_dump_pathgraph"]
@@ -69,6 +69,7 @@ def load():
     lib.rg_load_gfa_file.argtypes = [vp, ctypes.c_char_p]
     lib.rg_load_gfa_text.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
     lib.rg_set_lnz_graph.argtypes = [vp, c_u32, vp, vp, vp, vp, vp]
+    lib.rg_set_path_graph.argtypes = [vp, c_u32, c_u32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rg_graph_info.argtypes = [vp, ctypes.POINTER(c_u32), ctypes.POINTER(c_u32), ctypes.POINTER(c_u32)]
     lib.rg_make_score_matrix.argtypes = [ctypes.c_int, c_i32, c_i32, ctypes.POINTER(Scoring)]
     lib.rg_default_scoring.argtypes = [ctypes.POINTER(Scoring)]

@@ -97,6 +97,39 @@ class Aligner:
         self._check(self.lib.rg_set_lnz_graph(self.ctx, n, codes.ctypes.data, nwp.ctypes.data, off.ctypes.data,
                                               idx.ctypes.data, None if sid is None else sid.ctypes.data))
 
+    def set_path_graph(self, lnz, nwp, preds, paths_nodes, alphas, n_paths, nodes_id_pos=None):
+        """Prebuilt PathGraph (pathwise_graph.rs:10-18): lnz chars incl. '$' / 'F', nwp flags, preds = {node: {pred: set(paths)}},
+        paths_nodes = per-row sets of path ids, alphas per row."""
+        n = len(lnz)
+        PW = (n_paths + 31) // 32
+        codes = np.array([CODES.get(c, 0) for c in lnz], dtype=np.uint8)
+        nwp_a = np.array([1 if x else 0 for x in nwp], dtype=np.uint8)
+        off, idx, ebits = [0], [], []
+        for i in range(n):
+            for p, ps in preds.get(i, {}).items():
+                idx.append(p)
+                w = [0] * PW
+                for q in ps:
+                    w[q // 32] |= 1 << (q % 32)
+                ebits += w
+            off.append(len(idx))
+        nbits = []
+        for i in range(n):
+            w = [0] * PW
+            for q in paths_nodes[i]:
+                w[q // 32] |= 1 << (q % 32)
+            nbits += w
+        off = np.array(off, dtype=np.uint32)
+        idx = np.array(idx if idx else [0], dtype=np.uint32)
+        ebits = np.array(ebits if ebits else [0], dtype=np.uint32)
+        nbits = np.array(nbits, dtype=np.uint32)
+        al = np.array(alphas, dtype=np.uint32)
+        sid = None if nodes_id_pos is None else np.array(nodes_id_pos, dtype=np.uint64)
+        self._keep_graph = (codes, nwp_a, off, idx, ebits, nbits, al, sid)
+        self._check(self.lib.rg_set_path_graph(self.ctx, n, n_paths, codes.ctypes.data, nwp_a.ctypes.data, off.ctypes.data,
+                                               idx.ctypes.data, ebits.ctypes.data, nbits.ctypes.data, al.ctypes.data,
+                                               None if sid is None else sid.ctypes.data))
+
     def graph_info(self):
         n, s, p = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         self._check(self.lib.rg_graph_info(self.ctx, ctypes.byref(n), ctypes.byref(s), ctypes.byref(p)))

@@ -511,6 +511,21 @@ int rg_set_lnz_graph(rg_ctx* c, uint32_t n, const uint8_t* lnz_codes, const uint
     return upload_graph(c);
 }
 
+int rg_set_path_graph(rg_ctx* c, uint32_t n, uint32_t n_paths, const uint8_t* lnz_codes, const uint8_t* nwp, const uint32_t* pred_off,
+                      const uint32_t* pred_idx, const uint32_t* edge_path_bits, const uint32_t* node_path_bits,
+                      const uint32_t* alphas, const uint64_t* seg_id) {
+    if (!c || !lnz_codes || !nwp || !pred_off || !pred_idx || !edge_path_bits || !node_path_bits || !alphas) return RG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    std::string err;
+    FlatGraph tmp;
+    int rc = flat_from_path_graph(n, n_paths, lnz_codes, nwp, pred_off, pred_idx, edge_path_bits, node_path_bits, alphas, seg_id, tmp, err);
+    if (rc != RG_OK) return c->fail(rc, err);
+    c->fg = std::move(tmp);
+    rc = upload_graph(c);
+    if (rc != RG_OK) return rc;
+    return upload_path_graph(c);
+}
+
 int rg_graph_info(const rg_ctx* c, uint32_t* n, uint32_t* n_segments, uint32_t* n_paths) {
     if (!c || !c->has_graph) return RG_ERR_INVALID;
     if (n) *n = c->fg.n;

@@ -67,6 +67,10 @@ int flatten_graph(const GfaGraph& g, FlatGraph& f, std::string& err);
 int flat_from_lnz(uint32_t n, const uint8_t* lnz_codes, const uint8_t* nwp, const uint32_t* pred_off,
                   const uint32_t* pred_idx, const uint64_t* seg_id, FlatGraph& f, std::string& err);
 
+int flat_from_path_graph(uint32_t n, uint32_t P, const uint8_t* lnz_codes, const uint8_t* nwp, const uint32_t* pred_off,
+                         const uint32_t* pred_idx, const uint32_t* edge_bits, const uint32_t* node_bits, const uint32_t* alphas,
+                         const uint64_t* seg_id, FlatGraph& f, std::string& err);
+
 // score_matrix.rs builders on the 6x6 code table.
 int make_score_matrix(int kind, int32_t match, int32_t mismatch, rg_scoring* s);
 // (b + f * L) as usize in f32 arithmetic, saturating (main.rs:57,175). L includes the '$'.

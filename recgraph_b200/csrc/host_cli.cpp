@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/recgraph_b200.h"
@@ -18,6 +19,7 @@ struct Args {  // args_parser.rs:3-147: same flags and defaults
     std::string matrix = "none", amb_strand = "false";
     float multi_rec_cost = 0.1f, rec_band_width = 1.0f, extra_f = 0.01f;
     int extra_b = 1;
+    int gpus = 1;  // not a reference flag: --gpus N shards the reads over N devices of the box
 };
 
 struct OptName {
@@ -26,7 +28,7 @@ struct OptName {
 };
 const OptName OPTS[] = {{'o', "out_file"}, {'m', "aln-mode"}, {'M', "match"}, {'X', "mismatch"}, {'t', "matrix"},
                         {'O', "gap-open"}, {'E', "gap-ext"}, {'r', "multi-rec-cost"}, {'R', "base-rec-cost"},
-                        {'B', "rec-band-width"}, {'s', "amb-strand"}, {'b', "extra-b"}, {'f', "extra-f"}};
+                        {'B', "rec-band-width"}, {'s', "amb-strand"}, {'b', "extra-b"}, {'f', "extra-f"}, {'G', "gpus"}};
 
 bool assign(Args& a, char s, const std::string& v) {
     try {
@@ -45,6 +47,10 @@ bool assign(Args& a, char s, const std::string& v) {
             case 'E': a.gap_extension = std::stoi(v, &pos); break;
             case 'R': a.base_rec_cost = std::stoi(v, &pos); break;
             case 'b': a.extra_b = std::stoi(v, &pos); break;
+            case 'G':
+                a.gpus = std::stoi(v, &pos);
+                if (a.gpus < 1) return false;
+                break;
             case 'r': a.multi_rec_cost = std::stof(v, &pos); break;
             case 'B': a.rec_band_width = std::stof(v, &pos); break;
             case 'f': a.extra_f = std::stof(v, &pos); break;
@@ -133,6 +139,146 @@ bool write_gaf(const Args& a, const std::string& text, size_t number, std::strin
     return true;
 }
 
+// Everything one device does for a contiguous range [lo, hi) of the reads: own context, own copy of the graph, alignment,
+// `-s` retries, text. Per read: the lines the reference println!s while aligning (warnings; the whole output for modes
+// 6 / 7) and the GAF record that goes through write_gaf.
+struct ShardOut {
+    std::vector<std::string> pre, record;
+    int code = 0;        // 0 ok, 101 reference panic, 3 device / library error
+    std::string err;
+};
+
+void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int device, int32_t lo, int32_t hi, ShardOut& so) {
+    const int mode = a.alignment_mode;
+    const int32_t n = hi - lo;
+    so.pre.assign(n, "");
+    so.record.assign(n, "");
+    rg_ctx* ctx = nullptr;
+    int rc = rg_init(device, &ctx);
+    if (rc != RG_OK) {
+        so.code = 3;
+        so.err = std::string("recgraph_b200: device ") + std::to_string(device) + ": " + rg_strerror(rc) + "\n";
+        return;
+    }
+    struct Guard {
+        rg_ctx* c;
+        ~Guard() { rg_destroy(c); }
+    } guard{ctx};
+    auto panic = [&](const std::string& msg) {
+        so.code = 101;
+        so.err = "thread 'main' panicked at '" + msg + "'\n";
+    };
+    rc = rg_load_gfa_file(ctx, a.graph_path.c_str());
+    if (rc != RG_OK) return panic(rg_last_error(ctx));
+    rg_set_scoring(ctx, &sc);
+    if (n == 0) return;
+    const bool amb_strand = a.amb_strand == "true";
+    struct Batch {
+        std::vector<std::string> warn, record;
+        std::vector<int32_t> score;
+        std::vector<uint32_t> best_path;
+    };
+    std::vector<char> buf(1 << 16);
+    // idx: position inside this shard of every read of the batch (empty = identity)
+    auto run_batch = [&](int dev_mode, int32_t nb, const uint8_t* codes, const uint64_t* off, const std::vector<int32_t>& idx,
+                         int amb_flags, Batch& bt) -> bool {
+        rg_batch_result res;
+        int r = rg_align_batch(ctx, dev_mode, nb, codes, off, &res);
+        if (r == RG_ERR_REF_PANIC) {
+            panic(rg_last_error(ctx));
+            return false;
+        }
+        if (r != RG_OK) {
+            so.err += std::string("recgraph_b200: ") + rg_strerror(r) + ": " + rg_last_error(ctx) + "\n";
+            so.code = 3;
+            return false;
+        }
+        bt.warn.resize(nb);
+        bt.record.resize(nb);
+        bt.score.resize(nb);
+        bt.best_path.resize(nb);
+        for (int32_t k = 0; k < nb; k++) {
+            bt.best_path[k] = res.reads[k].best_path;
+            const int32_t i = lo + (idx.empty() ? k : idx[k]);   // index in the input file
+            if (res.reads[k].status & RG_READ_REF_PANIC) {
+                panic("reference panic while aligning read " + std::to_string(i + 1) + " (see DESIGN.md, reference quirks)");
+                return false;
+            }
+            if (res.reads[k].status & RG_READ_TRACE_OVERFLOW) {
+                so.err += "recgraph_b200: trace buffers overflowed for read " + std::to_string(i + 1) + "\n";
+                so.code = 3;
+                return false;
+            }
+            uint32_t len = (uint32_t)(off[k + 1] - off[k]);
+            int64_t need = rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
+            if (need < 0) {
+                so.code = 3;
+                return false;
+            }
+            if ((size_t)need >= buf.size()) {
+                buf.resize((size_t)need + 1);
+                rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
+            }
+            std::string text(buf.data(), (size_t)need);
+            size_t cut = text.size() > 1 ? text.rfind('\n', text.size() - 2) : std::string::npos;
+            if (cut != std::string::npos) {
+                bt.warn[k] = text.substr(0, cut + 1);
+                text.erase(0, cut + 1);
+            }
+            bt.record[k] = std::move(text);
+            bt.score[k] = res.reads[k].score;
+        }
+        return true;
+    };
+    Batch fwd;
+    if (!run_batch(mode, n, reads.codes, reads.off + lo, {}, 0, fwd)) return;
+    // ---- -s true: reverse-complement retries (main.rs:82-101 mode 0, 150-164 mode 1, 198-214 mode 2, 233-249 mode 3)
+    Batch rev;
+    std::vector<int32_t> rev_of(n, -1);
+    if (amb_strand && mode <= 3) {
+        std::vector<int32_t> idx;
+        for (int32_t i = 0; i < n; i++)
+            if (mode == 1 || mode == 3 || fwd.score[i] < 0) {  // modes 0 / 2 retry only when the forward score is negative
+                rev_of[i] = (int32_t)idx.size();
+                idx.push_back(i);
+            }
+        if (!idx.empty()) {
+            std::vector<uint8_t> rcs;
+            std::vector<uint64_t> roff{0};
+            for (int32_t i : idx) {
+                for (uint64_t k = reads.off[lo + i + 1]; k-- > reads.off[lo + i];) {  // sequences.rs:64-82
+                    uint8_t c = reads.codes[k];
+                    rcs.push_back(c < 4 ? (uint8_t)(3 - c) : c);
+                }
+                roff.push_back(rcs.size());
+            }
+            // mode 0 retries with the scalar routine (global_abpoa::exec); mode 3 keeps amb_mode = false (main.rs:242)
+            const int rmode = mode == 0 ? RG_MODE_GLOBAL_SCALAR : mode;
+            const int flags = mode == 3 ? RG_AMB_HANDLES : (RG_AMB_HANDLES | RG_AMB_STRAND);
+            if (!run_batch(rmode, (int32_t)idx.size(), rcs.data(), roff.data(), idx, flags, rev)) return;
+        }
+    }
+    for (int32_t i = 0; i < n; i++) {
+        // warning lines are println!'d to stdout by the reference even with -o; only the record goes to the file
+        so.pre[i] = fwd.warn[i];
+        if (mode == 6 || mode == 7) {
+            // main.rs:271-288: exec println!s the CIGAR line, main the best path; no GAF record, -o is not used
+            so.pre[i] += fwd.record[i];
+            so.pre[i] += "Best path sequence " + std::to_string(lo + i) + ": " + std::to_string(fwd.best_path[i]) + "\n";
+            continue;
+        }
+        const std::string* rec = &fwd.record[i];
+        if (rev_of[i] >= 0) {
+            const int32_t k = rev_of[i];
+            so.pre[i] += rev.warn[k];
+            const bool take_rev = mode == 1 ? !(fwd.score[i] < rev.score[k])  // main.rs:160-164 keeps the LOWER score
+                                            : rev.score[k] > fwd.score[i];
+            if (take_rev) rec = &rev.record[k];
+        }
+        so.record[i] = *rec;
+    }
+}
+
 }  // namespace
 
 extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** err_text) {
@@ -140,11 +286,9 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
     std::string out, err;
     int rc = 0;
     Args a;
-    rg_ctx* ctx = nullptr;
     rg_reads reads;
     memset(&reads, 0, sizeof reads);
     auto finish = [&](int code) {
-        if (ctx) rg_destroy(ctx);
         rg_free_reads(&reads);
         if (out_text) *out_text = dup_text(out);
         if (err_text) *err_text = dup_text(err);
@@ -159,13 +303,6 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
     char ebuf[512] = {0};
     rc = rg_read_fasta_file(a.sequence_path.c_str(), &reads, ebuf, sizeof ebuf);
     if (rc != RG_OK) return panic(ebuf);
-    rc = rg_init(0, &ctx);
-    if (rc != RG_OK) {
-        err += std::string("recgraph_b200: ") + rg_strerror(rc) + "\n";
-        return finish(3);
-    }
-    rc = rg_load_gfa_file(ctx, a.graph_path.c_str());
-    if (rc != RG_OK) return panic(rg_last_error(ctx));
 
     rg_scoring sc;
     rg_default_scoring(&sc);
@@ -185,118 +322,45 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
     sc.extra_b = (float)a.extra_b;
     sc.extra_f = a.extra_f;
     sc.fixed_bta = -1;
-    rg_set_scoring(ctx, &sc);
 
     const int mode = a.alignment_mode;
     if (mode < 0 || mode > 9) return panic("Alignment mode must be in [0..9]");
-    const bool amb_strand = a.amb_strand == "true";
-    // One batch through the device + the text of every read, split into the lines the reference println!s while
-    // aligning (warnings) and the GAF record.
-    struct Batch {
-        std::vector<std::string> warn, record;
-        std::vector<int32_t> score;
-        std::vector<uint32_t> best_path;
-    };
-    std::vector<char> buf(1 << 16);
-    int fail_code = 0;
-    auto run_batch = [&](int dev_mode, int32_t n, const uint8_t* codes, const uint64_t* off, const std::vector<int32_t>& idx,
-                         int amb_flags, Batch& bt) -> bool {
-        rg_batch_result res;
-        int r = rg_align_batch(ctx, dev_mode, n, codes, off, &res);
-        if (r == RG_ERR_REF_PANIC) {
-            fail_code = panic(rg_last_error(ctx));
-            return false;
+
+    // ---- reads are independent: contiguous shards balanced by read length (every mode's cost grows with it), one host
+    // thread + context + graph replica per device, no exchange between devices; records are emitted in input order
+    const int G = a.gpus;
+    std::vector<int32_t> bound(G + 1, 0);
+    {
+        const uint64_t total = reads.off[reads.n_reads] - reads.off[0];
+        int32_t i = 0;
+        for (int d = 1; d < G; d++) {
+            const uint64_t target = reads.off[0] + total * (uint64_t)d / (uint64_t)G;
+            while (i < reads.n_reads && reads.off[i + 1] <= target) i++;
+            bound[d] = i;
         }
-        if (r != RG_OK) {
-            err += std::string("recgraph_b200: ") + rg_strerror(r) + ": " + rg_last_error(ctx) + "\n";
-            fail_code = finish(3);
-            return false;
-        }
-        bt.warn.resize(n);
-        bt.record.resize(n);
-        bt.score.resize(n);
-        bt.best_path.resize(n);
-        for (int32_t k = 0; k < n; k++) {
-            bt.best_path[k] = res.reads[k].best_path;
-            const int32_t i = idx.empty() ? k : idx[k];
-            if (res.reads[k].status & RG_READ_REF_PANIC) {
-                fail_code = panic("reference panic while aligning read " + std::to_string(i + 1) + " (see DESIGN.md, reference quirks)");
-                return false;
-            }
-            if (res.reads[k].status & RG_READ_TRACE_OVERFLOW) {
-                err += "recgraph_b200: trace buffers overflowed for read " + std::to_string(i + 1) + "\n";
-                fail_code = finish(3);
-                return false;
-            }
-            uint32_t len = (uint32_t)(off[k + 1] - off[k]);
-            int64_t need = rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
-            if (need < 0) {
-                fail_code = finish(3);
-                return false;
-            }
-            if ((size_t)need >= buf.size()) {
-                buf.resize((size_t)need + 1);
-                rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
-            }
-            std::string text(buf.data(), (size_t)need);
-            size_t cut = text.size() > 1 ? text.rfind('\n', text.size() - 2) : std::string::npos;
-            if (cut != std::string::npos) {
-                bt.warn[k] = text.substr(0, cut + 1);
-                text.erase(0, cut + 1);
-            }
-            bt.record[k] = std::move(text);
-            bt.score[k] = res.reads[k].score;
-        }
-        return true;
-    };
-    Batch fwd;
-    if (!run_batch(mode, reads.n_reads, reads.codes, reads.off, {}, 0, fwd)) return fail_code;
-    // ---- -s true: reverse-complement retries (main.rs:82-101 mode 0, 150-164 mode 1, 198-214 mode 2, 233-249 mode 3)
-    Batch rev;
-    std::vector<int32_t> rev_of(reads.n_reads, -1);
-    if (amb_strand && mode <= 3) {
-        std::vector<int32_t> idx;
-        for (int32_t i = 0; i < reads.n_reads; i++)
-            if (mode == 1 || mode == 3 || fwd.score[i] < 0) {  // modes 0 / 2 retry only when the forward score is negative
-                rev_of[i] = (int32_t)idx.size();
-                idx.push_back(i);
-            }
-        if (!idx.empty()) {
-            std::vector<uint8_t> rc;
-            std::vector<uint64_t> roff{0};
-            for (int32_t i : idx) {
-                for (uint64_t k = reads.off[i + 1]; k-- > reads.off[i];) {  // sequences.rs:64-82
-                    uint8_t c = reads.codes[k];
-                    rc.push_back(c < 4 ? (uint8_t)(3 - c) : c);
-                }
-                roff.push_back(rc.size());
-            }
-            // mode 0 retries with the scalar routine (global_abpoa::exec); mode 3 keeps amb_mode = false (main.rs:242)
-            const int rmode = mode == 0 ? RG_MODE_GLOBAL_SCALAR : mode;
-            const int flags = mode == 3 ? RG_AMB_HANDLES : (RG_AMB_HANDLES | RG_AMB_STRAND);
-            if (!run_batch(rmode, (int32_t)idx.size(), rc.data(), roff.data(), idx, flags, rev)) return fail_code;
-        }
+        bound[G] = reads.n_reads;
     }
-    for (int32_t i = 0; i < reads.n_reads; i++) {
-        size_t number = mode <= 3 ? (size_t)i + 1 : (size_t)i;
-        // warning lines are println!'d to stdout by the reference even with -o; only the record goes to the file
-        out += fwd.warn[i];
-        if (mode == 6 || mode == 7) {
-            // main.rs:271-288: exec println!s the CIGAR line, main the best path; no GAF record, -o is not used
-            out += fwd.record[i];
-            out += "Best path sequence " + std::to_string(i) + ": " + std::to_string(fwd.best_path[i]) + "\n";
-            continue;
-        }
-        const std::string* rec = &fwd.record[i];
-        if (rev_of[i] >= 0) {
-            const int32_t k = rev_of[i];
-            out += rev.warn[k];
-            const bool take_rev = mode == 1 ? !(fwd.score[i] < rev.score[k])  // main.rs:160-164 keeps the LOWER score
-                                            : rev.score[k] > fwd.score[i];
-            if (take_rev) rec = &rev.record[k];
-        }
-        if (!write_gaf(a, *rec, number, out)) return panic("unable to create file");
+    std::vector<ShardOut> shards(G);
+    if (G == 1) {
+        run_shard(a, sc, reads, 0, 0, reads.n_reads, shards[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < G; d++) th.emplace_back([&, d] { run_shard(a, sc, reads, d, bound[d], bound[d + 1], shards[d]); });
+        for (auto& t : th) t.join();
     }
+    for (int d = 0; d < G; d++)
+        if (shards[d].code) {
+            err += shards[d].err;
+            return finish(shards[d].code);
+        }
+    for (int d = 0; d < G; d++)
+        for (int32_t k = 0; k < bound[d + 1] - bound[d]; k++) {
+            const int32_t i = bound[d] + k;
+            const size_t number = mode <= 3 ? (size_t)i + 1 : (size_t)i;
+            out += shards[d].pre[k];
+            if (mode == 6 || mode == 7) continue;
+            if (!write_gaf(a, shards[d].record[k], number, out)) return panic("unable to create file");
+        }
     auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
     err += "Done in " + std::to_string(secs) + ".\n";  // main.rs:322
     return finish(0);

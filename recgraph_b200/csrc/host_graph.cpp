@@ -291,6 +291,105 @@ int flat_from_lnz(uint32_t n, const uint8_t* lnz_codes, const uint8_t* nwp, cons
     return RG_OK;
 }
 
+// Reverse graph (pathwise_graph.rs:250-282: every (node, pred, paths) entry transposed), look-backs and the distance vectors of
+// pathwise_graph.rs:306-354, from the forward PathGraph CSR (entries of a node in ascending predecessor order).
+static void finish_path_graph(FlatGraph& f) {
+    const uint32_t n = f.n, PW = f.PW;
+    {
+        std::vector<uint32_t> cnt(n + 1, 0);
+        for (uint32_t i = 0; i < n; i++)
+            for (uint32_t k = f.pw_pred_off[i]; k < f.pw_pred_off[i + 1]; k++) cnt[f.pw_pred_idx[k] + 1]++;
+        f.rv_pred_off.assign(n + 1, 0);
+        for (uint32_t i = 0; i < n; i++) f.rv_pred_off[i + 1] = f.rv_pred_off[i] + cnt[i + 1];
+        f.rv_pred_idx.assign(f.pw_pred_idx.size(), 0);
+        f.rv_edge_bits.assign(f.pw_edge_bits.size(), 0);
+        std::vector<uint32_t> fill(f.rv_pred_off.begin(), f.rv_pred_off.end() - 1);
+        for (uint32_t i = 0; i < n; i++)   // ascending node => ascending "predecessor" inside every reverse list
+            for (uint32_t k = f.pw_pred_off[i]; k < f.pw_pred_off[i + 1]; k++) {
+                const uint32_t p = f.pw_pred_idx[k], dst = fill[p]++;
+                f.rv_pred_idx[dst] = i;
+                for (uint32_t w = 0; w < PW; w++) f.rv_edge_bits[(size_t)dst * PW + w] = f.pw_edge_bits[(size_t)k * PW + w];
+            }
+    }
+    f.rv_nwp.assign(n, 0);
+    for (uint32_t i = 0; i < n; i++)
+        if (f.rv_pred_off[i + 1] > f.rv_pred_off[i]) f.rv_nwp[i] = 1;
+    f.pw_max_lookback = 1;
+    f.rv_max_lookback = 1;
+    for (uint32_t i = 1; i + 1 < n; i++) {
+        for (uint32_t k = f.pw_pred_off[i]; k < f.pw_pred_off[i + 1]; k++)
+            f.pw_max_lookback = std::max(f.pw_max_lookback, i - f.pw_pred_idx[k]);
+        for (uint32_t k = f.rv_pred_off[i]; k < f.rv_pred_off[i + 1]; k++)
+            f.rv_max_lookback = std::max(f.rv_max_lookback, f.rv_pred_idx[k] - i);
+    }
+    // distances (pathwise_graph.rs:306-354)
+    {
+        std::vector<int64_t> r(n, -1);
+        r[0] = 0;
+        for (uint32_t k = f.rv_pred_off[0]; k < f.rv_pred_off[1]; k++) r[f.rv_pred_idx[k]] = 1;
+        for (uint32_t i = 1; i + 1 < n; i++) {
+            if (r[i] == -1 || r[i] > r[i - 1] + 1) r[i] = r[i - 1] + 1;
+            if (f.rv_nwp[i])
+                for (uint32_t k = f.rv_pred_off[i]; k < f.rv_pred_off[i + 1]; k++) {
+                    uint32_t p = f.rv_pred_idx[k];
+                    if (r[p] == -1 || r[p] > r[i] + 1) r[p] = r[i] + 1;
+                }
+        }
+        f.dfs.resize(n);
+        for (uint32_t i = 0; i < n; i++) f.dfs[i] = (int32_t)r[i];
+    }
+    {
+        std::vector<int64_t> r(n, -1);
+        r[n - 1] = 0;
+        for (uint32_t k = f.pw_pred_off[n - 1]; k < f.pw_pred_off[n]; k++) r[f.pw_pred_idx[k]] = 1;
+        for (uint32_t i = n - 2; i >= 1; i--) {
+            if (r[i] == -1 || r[i] > r[i + 1] + 1) r[i] = r[i + 1] + 1;
+            if (f.pw_nwp[i])
+                for (uint32_t k = f.pw_pred_off[i]; k < f.pw_pred_off[i + 1]; k++) {
+                    uint32_t p = f.pw_pred_idx[k];
+                    if (r[p] == -1 || r[p] > r[i] + 1) r[p] = r[i] + 1;
+                }
+        }
+        f.dfe.resize(n);
+        for (uint32_t i = 0; i < n; i++) f.dfe[i] = (int32_t)r[i];
+    }
+}
+
+// A prebuilt PathGraph (pathwise_graph.rs:10-18): lnz, nwp, PredHash as CSR with one path bitset per (node, predecessor)
+// entry, paths_nodes, alphas, nodes_id_pos. The LnzGraph side of the FlatGraph is filled from the same predecessor lists.
+int flat_from_path_graph(uint32_t n, uint32_t P, const uint8_t* lnz_codes, const uint8_t* nwp, const uint32_t* pred_off,
+                         const uint32_t* pred_idx, const uint32_t* edge_bits, const uint32_t* node_bits, const uint32_t* alphas,
+                         const uint64_t* seg_id, FlatGraph& f, std::string& err) {
+    if (P == 0) {
+        err = "a PathGraph needs at least one path";
+        return RG_ERR_INVALID;
+    }
+    int rc = flat_from_lnz(n, lnz_codes, nwp, pred_off, pred_idx, seg_id, f, err);
+    if (rc != RG_OK) return rc;
+    const uint32_t PW = (P + 31) / 32;
+    f.P = P;
+    f.PW = PW;
+    f.has_paths = true;
+    f.pw_nwp.assign(nwp, nwp + n);
+    f.node_bits.assign(node_bits, node_bits + (size_t)n * PW);
+    f.alphas.assign(alphas, alphas + n);
+    // entries of a node in ascending predecessor order (the fixed order of this implementation)
+    f.pw_pred_off.assign(pred_off, pred_off + n + 1);
+    f.pw_pred_idx.clear();
+    f.pw_edge_bits.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        std::vector<uint32_t> ord;
+        for (uint32_t k = pred_off[i]; k < pred_off[i + 1]; k++) ord.push_back(k);
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return pred_idx[a] < pred_idx[b]; });
+        for (uint32_t k : ord) {
+            f.pw_pred_idx.push_back(pred_idx[k]);
+            for (uint32_t w = 0; w < PW; w++) f.pw_edge_bits.push_back(edge_bits[(size_t)k * PW + w]);
+        }
+    }
+    finish_path_graph(f);
+    return RG_OK;
+}
+
 int flatten_graph(const GfaGraph& g, FlatGraph& f, std::string& err) {
     f = FlatGraph();
     const uint32_t S = (uint32_t)g.seg_id.size();
@@ -444,53 +543,8 @@ int flatten_graph(const GfaGraph& g, FlatGraph& f, std::string& err) {
         }
         for (uint32_t i = 0; i < n; i++) off[i + 1] += off[i];
     };
-    std::vector<Edge> redges;
-    redges.reserve(edges.size());
-    for (auto& e : edges) redges.push_back({e.pred, e.node, e.path});
     build_csr(edges, f.pw_pred_off, f.pw_pred_idx, f.pw_edge_bits);
-    build_csr(redges, f.rv_pred_off, f.rv_pred_idx, f.rv_edge_bits);
-    f.rv_nwp.assign(n, 0);
-    for (uint32_t i = 0; i < n; i++)
-        if (f.rv_pred_off[i + 1] > f.rv_pred_off[i]) f.rv_nwp[i] = 1;
-    f.pw_max_lookback = 1;
-    f.rv_max_lookback = 1;
-    for (uint32_t i = 1; i + 1 < n; i++) {
-        for (uint32_t k = f.pw_pred_off[i]; k < f.pw_pred_off[i + 1]; k++)
-            f.pw_max_lookback = std::max(f.pw_max_lookback, i - f.pw_pred_idx[k]);
-        for (uint32_t k = f.rv_pred_off[i]; k < f.rv_pred_off[i + 1]; k++)
-            f.rv_max_lookback = std::max(f.rv_max_lookback, f.rv_pred_idx[k] - i);
-    }
-    // distances (pathwise_graph.rs:306-354)
-    {
-        std::vector<int64_t> r(n, -1);
-        r[0] = 0;
-        for (uint32_t k = f.rv_pred_off[0]; k < f.rv_pred_off[1]; k++) r[f.rv_pred_idx[k]] = 1;
-        for (uint32_t i = 1; i + 1 < n; i++) {
-            if (r[i] == -1 || r[i] > r[i - 1] + 1) r[i] = r[i - 1] + 1;
-            if (f.rv_nwp[i])
-                for (uint32_t k = f.rv_pred_off[i]; k < f.rv_pred_off[i + 1]; k++) {
-                    uint32_t p = f.rv_pred_idx[k];
-                    if (r[p] == -1 || r[p] > r[i] + 1) r[p] = r[i] + 1;
-                }
-        }
-        f.dfs.resize(n);
-        for (uint32_t i = 0; i < n; i++) f.dfs[i] = (int32_t)r[i];
-    }
-    {
-        std::vector<int64_t> r(n, -1);
-        r[n - 1] = 0;
-        for (uint32_t k = f.pw_pred_off[n - 1]; k < f.pw_pred_off[n]; k++) r[f.pw_pred_idx[k]] = 1;
-        for (uint32_t i = n - 2; i >= 1; i--) {
-            if (r[i] == -1 || r[i] > r[i + 1] + 1) r[i] = r[i + 1] + 1;
-            if (f.pw_nwp[i])
-                for (uint32_t k = f.pw_pred_off[i]; k < f.pw_pred_off[i + 1]; k++) {
-                    uint32_t p = f.pw_pred_idx[k];
-                    if (r[p] == -1 || r[p] > r[i] + 1) r[p] = r[i] + 1;
-                }
-        }
-        f.dfe.resize(n);
-        for (uint32_t i = 0; i < n; i++) f.dfe[i] = (int32_t)r[i];
-    }
+    finish_path_graph(f);
     return RG_OK;
 }
 

@@ -1,0 +1,101 @@
+"""CLI surface around the hot path: `-o` file semantics (utils.rs:200-219 with both numbering conventions: POA modes pass
+i + 1, pathwise modes pass i — main.rs:260,268,311 — so the second record of a pathwise run TRUNCATES the file), the
+api.rs no-gap entry points (f32 matrix with gap = X, api.rs:11-40,76-99), and the sharded multi-device driver (`--gpus N`:
+same text as one device)."""
+import os
+
+import pytest
+
+from recgraph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXAMPLE = os.path.join(ROOT, "tests", "golden", "example")
+EX = [os.path.join(EXAMPLE, "reads.fa"), os.path.join(EXAMPLE, "graph.gfa")]
+
+
+@pytest.mark.parametrize("mode", ["0", "2", "3", "4", "5", "9"])
+def test_out_file_semantics(tmp_path, mode):
+    from recgraph_b200 import run_cli
+    from tests import oracle_lib
+    a, b = tmp_path / "gpu.gaf", tmp_path / "ref.gaf"
+    extra = ["-b", "50"] if mode in ("0", "2") else []
+    rc, out, err = run_cli(["-m", mode, "-o", str(a)] + extra + EX)
+    orc, oout, oerr = oracle_lib.run_cli(["-m", mode, "-o", str(b)] + extra + EX)
+    assert rc == 0 and orc == 0, (err, oerr)
+    assert out == oout            # warnings still go to stdout
+    assert a.read_text() == b.read_text()
+    n = len(a.read_text().splitlines())
+    # POA modes: all 52 records; pathwise modes: the record of read 1 re-creates the file (number == 1), read 0's is lost
+    assert n == (52 if mode in ("0", "2", "3") else 51)
+    # an existing file is appended to unless number == 1
+    a.write_text("stale\n")
+    rc, out, err = run_cli(["-m", mode, "-o", str(a)] + extra + EX)
+    assert rc == 0
+    assert a.read_text().splitlines()[0] != "stale"
+
+
+def _example_reads():
+    names, seqs = [], []
+    for ln in open(EX[0]):
+        if ln.startswith(">"):
+            names.append(ln[1:].strip())
+        else:
+            seqs.append(ln.strip())
+    return names, seqs
+
+
+def test_api_no_gap_entry_points():
+    """align_global_no_gap / align_local_no_gap (api.rs:11-40,76-99): exec_simd with the f32 match/mismatch matrix whose
+    gap-vs-char entries are X (score_matrix.rs:52-66, not 2X as on the command line) and bases_to_add = 0.1 * len. The CLI
+    cannot express that matrix, so the expectation comes from the oracle's exec_simd through its own C entry point."""
+    import ctypes
+    import recgraph_b200 as rb
+    from tests import oracle_lib
+    names, seqs = _example_reads()
+    al = rb.Aligner()
+    al.load_gfa(EX[1])
+    lib = oracle_lib.load()
+    lib.rgo_api_no_gap.restype = ctypes.c_void_p
+    lib.rgo_api_no_gap.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    gfa_text = open(EX[1]).read().encode()
+    n_real = 0
+    for k in range(8):
+        for local in (0, 1):
+            p = lib.rgo_api_no_gap(gfa_text, seqs[k].encode(), names[k].encode(), local)
+            exp = ctypes.string_at(p).decode()
+            lib.rgo_free(p)
+            assert not exp.startswith("PANIC"), exp
+            g = rb.align_local_no_gap(seqs[k], al, (names[k], k + 1)) if local else rb.align_global_no_gap(seqs[k], al, (names[k], k + 1))
+            assert g.to_string() == exp.rstrip("\n").split("\n")[-1], (k, local)
+            n_real += "\t" in exp and not exp.startswith("\t")
+    assert n_real >= 8
+
+
+def test_gpus_flag_single_device_is_identity():
+    from recgraph_b200 import run_cli
+    for mode in ("2", "5"):
+        a = run_cli(["-m", mode] + EX)
+        b = run_cli(["-m", mode, "--gpus", "1"] + EX)
+        assert a[0] == 0 and a[:2] == b[:2]
+
+
+@pytest.mark.parametrize("mode", ["0", "2", "5", "7", "9"])
+def test_sharded_driver_two_devices(mode, tmp_path):
+    """`recgraph --gpus 2`: contiguous cost-balanced shards, one context + graph replica per device, records in input order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from recgraph_b200 import run_cli
+    g = synth.make_graph(3000, 6, seed=5)
+    reads = synth.make_reads(g, 41, 300, err=0.05, seed=6, mosaic_breaks=1, exact_len=False)
+    gfa, fa = tmp_path / "g.gfa", tmp_path / "r.fa"
+    gfa.write_text(g.gfa())
+    fa.write_text(synth.fasta(reads))
+    one = run_cli(["-m", mode, str(fa), str(gfa)])
+    two = run_cli(["-m", mode, "--gpus", "2", str(fa), str(gfa)])
+    assert one[0] == 0 and two[0] == 0, (one[2], two[2])
+    assert one[1] == two[1]
+    o = tmp_path / "out.gaf"
+    three = run_cli(["-m", mode, "--gpus", "2", "-o", str(o), str(fa), str(gfa)])
+    assert three[0] == 0
