@@ -19,8 +19,8 @@ _spec.loader.exec_module(pyref)
 # pathwise_graph.rs:364-404 (two paths through a diamond) and :406-449 / :498-544 (three paths, two starts, two ends)
 DIAMOND = "H\tVN:Z:1.0\nS\t1\tA\nS\t2\tT\nS\t3\tC\nS\t4\tG\nL\t1\t+\t2\t+\t0M\nL\t1\t+\t3\t+\t0M\nL\t2\t+\t4\t+\t0M\nL\t3\t+\t4\t+\t0M\n" \
           "P\tp1\t1+,2+,4+\t*\nP\tp2\t1+,3+,4+\t*\n"
-MULTI = "H\tVN:Z:1.0\nS\t1\tA\nS\t2\tT\nS\t3\tC\nS\t4\tG\nS\t5\tA\nS\t6\tT\nL\t1\t+\t3\t+\t0M\nL\t2\t+\t3\t+\t0M\nL\t2\t+\t4\t+\t0M\n" \
-        "L\t3\t+\t5\t+\t0M\nL\t4\t+\t5\t+\t0M\nL\t4\t+\t6\t+\t0M\nP\tp1\t1+,3+,5+\t*\nP\tp2\t2+,4+,5+\t*\nP\tp3\t2+,3+,5+\t*\n"
+MULTI = "H\tVN:Z:1.0\nS\t1\tA\nS\t2\tT\nS\t3\tC\nS\t4\tG\nS\t5\tA\nL\t1\t+\t3\t+\t0M\nL\t2\t+\t3\t+\t0M\nL\t2\t+\t4\t+\t0M\n" \
+        "L\t3\t+\t5\t+\t0M\nL\t4\t+\t5\t+\t0M\nP\tp1\t1+,3+,5+\t*\nP\tp2\t2+,4+,5+\t*\nP\tp3\t2+,3+,5+\t*\n"
 
 
 def _records(al, mode, reads):
