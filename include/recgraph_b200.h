@@ -59,8 +59,8 @@ typedef struct rg_scoring {
  * (global_abpoa::exec_simd / local_poa::exec_simd) as every x86-64 reference build does; the scalar
  * `exec` variants are RG_MODE_GLOBAL_SCALAR (global_abpoa::exec, global_abpoa.rs:260-427: the `-s` retry of mode 0,
  * main.rs:89-97) and RG_MODE_LOCAL_SCALAR (local_poa::exec, reached only on hosts without AVX2).
- * Device status: 0-5, 8, 9 and RG_MODE_GLOBAL_SCALAR run on the GPU; 6, 7 (experimental in the reference) and
- * RG_MODE_LOCAL_SCALAR return RG_ERR_UNSUPPORTED — there is no CPU fallback. */
+ * Device status: every mode runs on the GPU (6 / 7, experimental in the reference, keep its n x L x P tensors per read in
+ * flight); inputs outside a kernel's documented domain return RG_ERR_UNSUPPORTED — there is no CPU fallback. */
 enum {
     RG_MODE_GLOBAL = 0,
     RG_MODE_LOCAL = 1,

@@ -196,6 +196,24 @@ char* rgo_api_no_gap(const char* gfa_text, const char* read, const char* name, i
     }
 }
 
+// local_poa::exec (scalar routine, local_poa.rs:181-255; reached only on hosts without AVX2) with the CLI's default i32
+// matrix: stdout of exec followed by the GAF record.
+char* rgo_local_scalar_gaf(const char* gfa_text, const char* read, const char* name, int m, int x) {
+    try {
+        HashGraph hg = parse_gfa_text(gfa_text);
+        std::vector<char> seq = build_align_string(read);
+        LnzGraph lg = create_graph_struct(hg, false);
+        ScoreMatrix sm = create_score_matrix_match_mis(m, x);
+        std::vector<std::string> hofp = handle_pos_in_lnz(lg, hg, false);
+        std::string out;
+        PoaResult r = local_poa_exec(seq, name, 1, lg, sm, false, hofp, out);
+        if (r.has_gaf) out += r.gaf.to_string() + "\n";
+        return dup(out);
+    } catch (const std::exception& ex) {
+        return dup(std::string("PANIC ") + ex.what());
+    }
+}
+
 char* rgo_rev_and_compl(const char* seq) {
     try {
         std::vector<char> s(seq, seq + strlen(seq));

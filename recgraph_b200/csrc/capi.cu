@@ -609,14 +609,14 @@ static int align_poa(rg_ctx* c, int mode) {
     const FlatGraph& f = c->fg;
     const uint32_t n = f.n;
     const uint32_t Lmax = c->max_len + 1;
-    const bool lin = mode == RG_MODE_GLOBAL || mode == RG_MODE_LOCAL || mode == RG_MODE_GAP_LOCAL;
+    const bool lin = mode == RG_MODE_GLOBAL || mode == RG_MODE_LOCAL || mode == RG_MODE_GAP_LOCAL || mode == RG_MODE_LOCAL_SCALAR;
     const int trace_bytes = lin ? poa_lin_trace_bytes(f.max_indeg) : (f.max_indeg <= 4 ? 1 : 2);
     if (f.max_indeg > (lin ? 31u : 64u)) return c->fail(RG_ERR_UNSUPPORTED, "in-degree above the trace-code domain (31 for modes 0/1/3, 64 for mode 2)");
     if (mode == RG_MODE_GLOBAL || mode == RG_MODE_LOCAL)
         for (int k = 1; k < 5; k++)
             if (c->scoring.score[k][5] != c->scoring.score[0][5])
                 return c->fail(RG_ERR_UNSUPPORTED, "modes 0/1 need one gap score for all characters (true for every matrix the reference builds)");
-    if (mode == RG_MODE_GLOBAL_SCALAR)
+    if (mode == RG_MODE_GLOBAL_SCALAR || mode == RG_MODE_LOCAL_SCALAR)
         for (int k = 0; k < 5; k++)
             if (c->scoring.score[k][5] != c->scoring.score[0][5] || c->scoring.score[5][k] != c->scoring.score[0][5])
                 return c->fail(RG_ERR_UNSUPPORTED, "scalar mode 0 needs one gap score for all characters (true for every matrix the reference builds)");
@@ -984,6 +984,7 @@ int rg_align_staged(rg_ctx* c, int mode) {
         case RG_MODE_LOCAL:
         case RG_MODE_GAP_LOCAL:
         case RG_MODE_GLOBAL_SCALAR:
+        case RG_MODE_LOCAL_SCALAR:
         case RG_MODE_GAP_GLOBAL: rc = align_poa(c, mode); break;
         case RG_MODE_PATHWISE_GLOBAL:
         case RG_MODE_PATHWISE_SEMIGLOBAL:

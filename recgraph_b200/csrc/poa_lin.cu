@@ -44,7 +44,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     constexpr unsigned SLOT_ROW0 = SMASK;  // mode 3: "predecessor row 0" default of gap_local_poa.rs:131-187
     constexpr int DSH = 5, USH = 5 + SB;
     constexpr bool GLOBAL = MODE == RG_MODE_GLOBAL;
-    constexpr bool AFFINE = MODE == RG_MODE_GAP_LOCAL;
+    // RG_MODE_LOCAL_SCALAR (local_poa::exec, local_poa.rs:181-293) is the affine routine with o = 0 and e = the gap score:
+    // x[c] = m[c-1] + gap and y = max over predecessors of m + gap (y <= m always, so neither chain flag can be set), same
+    // `first = false` restart, same get_max_d_u_l tie order, same clamp and end cell — except that its vertical source is the
+    // best predecessor by m alone (get_best_u, local_poa.rs:277-293), never the y arg-max of gap_local_poa.rs:150-187.
+    constexpr bool NOY = MODE == RG_MODE_LOCAL_SCALAR;
+    constexpr bool AFFINE = MODE == RG_MODE_GAP_LOCAL || NOY;
     __shared__ int32_t s_sc[48];   // [graph][read]
     __shared__ int32_t s_sct[48];  // [read][graph]
     const int lane = threadIdx.x & 31;
@@ -64,8 +69,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     int32_t* ring_y = ws.ring_y + (size_t)slot * g.ring * STRIDE;
     TC* trace = reinterpret_cast<TC*>(ws.trace) + (size_t)slot * ws.trace_cap;
     rg_run* runs = ws.runs + (size_t)slot * ws.run_cap;
-    const int o = sc.o, e = sc.e;
     const int g_gr = sc.sc[0][5];  // score(graph char, '-'), uniform over the alphabet (checked on the host)
+    const int o = NOY ? 0 : sc.o, e = NOY ? g_gr : sc.e;
     const int g_rd = sc.sc[0][5];  // score(read char, '-')
     const int cbase = lane * C;
 
@@ -333,13 +338,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                             if (!real_nwp) {
                                 d = GD[k] + srowt[rc];
                                 const int uy = GY[k] + e, um = GA[k] + o + e;
-                                if (uy > um) cd |= 16u;
+                                if (!NOY && uy > um) cd |= 16u;
                                 u = max(uy, um);
                             } else {
                                 d = max(GD[k], 0) + srowt[rc];
                                 const int um = max(GA[k] == NEG_INF ? 0 : GA[k] + o, 0), uy = max(GY[k], 0);
                                 unsigned usl;
-                                if (um > uy) {
+                                if (NOY || um > uy) {
                                     u = um + e;
                                     usl = s & 0xffu;
                                 } else {
@@ -652,6 +657,7 @@ int launch_poa_lin(int mode, int C, const DevGraph& g, const DevScoring& s, cons
         case RG_MODE_GLOBAL: return launch_m<RG_MODE_GLOBAL>(C, g, s, ws, b, trace_bytes, blocks, st);
         case RG_MODE_LOCAL: return launch_m<RG_MODE_LOCAL>(C, g, s, ws, b, trace_bytes, blocks, st);
         case RG_MODE_GAP_LOCAL: return launch_m<RG_MODE_GAP_LOCAL>(C, g, s, ws, b, trace_bytes, blocks, st);
+        case RG_MODE_LOCAL_SCALAR: return launch_m<RG_MODE_LOCAL_SCALAR>(C, g, s, ws, b, trace_bytes, blocks, st);
         default: return -2;
     }
 }

@@ -72,6 +72,59 @@ def test_api_no_gap_entry_points():
     assert n_real >= 8
 
 
+def test_scalar_local_mode_on_the_device():
+    """RG_MODE_LOCAL_SCALAR = local_poa::exec (local_poa.rs:181-255, the routine of hosts without AVX2): the reference's two
+    inline vectors (local_poa.rs:304-338, 341-377) and GAF text against the oracle's restatement of that routine."""
+    import ctypes
+    import recgraph_b200 as rb
+    from tests import oracle_lib
+    from tests.test_oracle_golden import POA_CASES
+    al = rb.Aligner()
+    idx = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 4, "-": 5}
+    seen = 0
+    for variant, (lnz, nwp, preds), read, scores, o, e, bta, expected, cite in POA_CASES:
+        if variant != 1:
+            continue
+        table = [[-1] * 6 for _ in range(6)]
+        for (a, b), v in scores.items():
+            table[idx[a]][idx[b]] = v
+        table[5][5] = 0
+        al.set_lnz_graph(lnz, nwp, preds)
+        al.set_scoring(table=table)
+        recs, _ = al.align(11, [read[1:]])
+        assert recs[0].score == expected, cite
+        seen += 1
+    assert seen == 2
+    lib = oracle_lib.load()
+    lib.rgo_local_scalar_gaf.restype = ctypes.c_void_p
+    lib.rgo_local_scalar_gaf.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    names, seqs = _example_reads()
+    gfa_text = open(EX[1]).read().encode()
+    al2 = rb.Aligner()
+    al2.load_gfa(EX[1])
+    for (m, x) in ((2, 4), (1, 1), (3, 2)):
+        al2.set_scoring(match=m, mismatch=x)
+        recs, text = al2.align(11, seqs[:12], names=names[:12])
+        got = text.splitlines()
+        for k in range(12):
+            p = lib.rgo_local_scalar_gaf(gfa_text, seqs[k].encode(), names[k].encode(), m, -x)
+            exp = ctypes.string_at(p).decode()
+            lib.rgo_free(p)
+            assert not exp.startswith("PANIC"), exp
+            assert got[k] == exp.rstrip("\n").split("\n")[-1], (m, x, k)
+    g = synth.make_graph(2500, 5, seed=9)
+    reads = synth.make_reads(g, 10, 200, err=0.06, seed=10)
+    al3 = rb.Aligner()
+    al3.load_gfa_text(g.gfa())
+    al3.set_scoring()
+    recs, text = al3.align(11, reads)
+    for k, ln in enumerate(text.splitlines()):
+        p = lib.rgo_local_scalar_gaf(g.gfa().encode(), reads[k].encode(), f"read{k}".encode(), 2, -4)
+        exp = ctypes.string_at(p).decode()
+        lib.rgo_free(p)
+        assert ln == exp.rstrip("\n").split("\n")[-1], k
+
+
 def test_gpus_flag_single_device_is_identity():
     from recgraph_b200 import run_cli
     for mode in ("2", "5"):
