@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_build", "librecgraph_b200.so")
+# RG_LIB_DIR: an alternative in-tree build directory (kernel tuning experiments: `make OUT=../_build_x EXTRA=-D...`)
+LIB_PATH = os.path.join(os.environ.get("RG_LIB_DIR") or os.path.join(HERE, "_build"), "librecgraph_b200.so")
 
 c_i32, c_u32, c_u64, c_f32 = ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_float
 

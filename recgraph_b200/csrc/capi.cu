@@ -9,6 +9,7 @@
 #include <numeric>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device.h"
@@ -1057,21 +1058,42 @@ int64_t rg_format_gaf(rg_ctx* c, int mode, const rg_batch_result* res, int32_t r
 int rg_format_gaf_all(rg_ctx* c, int mode, const rg_batch_result* res, const char* const* names, int64_t first_index,
                       const uint64_t* read_off, int amb_mode, char** out_text, size_t* out_len) {
     if (!c || !res || !read_off || !out_text || !c->has_graph) return RG_ERR_INVALID;
-    std::string s;
-    s.reserve((size_t)res->n_reads * 256);
-    char nm[32];
-    for (int32_t i = 0; i < res->n_reads; i++) {
-        const char* name = names ? names[i] : nm;
-        if (!names) snprintf(nm, sizeof nm, "read%lld", (long long)(first_index + i));
-        format_gaf(c->fg, mode, res->reads[i], res->runs, name, (uint32_t)(read_off[i + 1] - read_off[i]),
-                   amb_mode == 1 ? (RG_AMB_STRAND | RG_AMB_HANDLES) : amb_mode, s);
+    // records are independent: contiguous chunks of reads are formatted by one host thread each and concatenated in order
+    const int32_t n = res->n_reads;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)hw, (int64_t)32, (int64_t)(n / 64 + 1)}));
+    std::vector<std::string> part(T);
+    const int flags = amb_mode == 1 ? (RG_AMB_STRAND | RG_AMB_HANDLES) : amb_mode;
+    auto work = [&](int t) {
+        const int32_t lo = (int32_t)((int64_t)n * t / T), hi = (int32_t)((int64_t)n * (t + 1) / T);
+        std::string& s = part[t];
+        s.reserve((size_t)(hi - lo) * 512);
+        char nm[32];
+        for (int32_t i = lo; i < hi; i++) {
+            const char* name = names ? names[i] : nm;
+            if (!names) snprintf(nm, sizeof nm, "read%lld", (long long)(first_index + i));
+            format_gaf(c->fg, mode, res->reads[i], res->runs, name, (uint32_t)(read_off[i + 1] - read_off[i]), flags, s);
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
     }
-    char* p = (char*)malloc(s.size() + 1);
+    size_t total = 0;
+    for (auto& s : part) total += s.size();
+    char* p = (char*)malloc(total + 1);
     if (!p) return RG_ERR_NOMEM;
-    memcpy(p, s.data(), s.size());
-    p[s.size()] = 0;
+    size_t o = 0;
+    for (auto& s : part) {
+        memcpy(p + o, s.data(), s.size());
+        o += s.size();
+    }
+    p[total] = 0;
     *out_text = p;
-    if (out_len) *out_len = s.size();
+    if (out_len) *out_len = total;
     return RG_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <thread>
 #include <vector>
@@ -178,7 +179,6 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
         std::vector<int32_t> score;
         std::vector<uint32_t> best_path;
     };
-    std::vector<char> buf(1 << 16);
     // idx: position inside this shard of every read of the batch (empty = identity)
     auto run_batch = [&](int dev_mode, int32_t nb, const uint8_t* codes, const uint64_t* off, const std::vector<int32_t>& idx,
                          int amb_flags, Batch& bt) -> bool {
@@ -199,6 +199,7 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
         bt.best_path.resize(nb);
         for (int32_t k = 0; k < nb; k++) {
             bt.best_path[k] = res.reads[k].best_path;
+            bt.score[k] = res.reads[k].score;
             const int32_t i = lo + (idx.empty() ? k : idx[k]);   // index in the input file
             if (res.reads[k].status & RG_READ_REF_PANIC) {
                 panic("reference panic while aligning read " + std::to_string(i + 1) + " (see DESIGN.md, reference quirks)");
@@ -209,25 +210,46 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
                 so.code = 3;
                 return false;
             }
-            uint32_t len = (uint32_t)(off[k + 1] - off[k]);
-            int64_t need = rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
-            if (need < 0) {
+        }
+        // text of the records: independent per read, formatted by a few host threads (rg_format_gaf only reads the context)
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::max(1u, std::thread::hardware_concurrency()), (int64_t)16,
+                                                                  (int64_t)(nb / 64 + 1)}));
+        std::vector<int> bad(T, 0);
+        auto work = [&](int t) {
+            std::vector<char> buf(1 << 16);
+            for (int32_t k = (int32_t)((int64_t)nb * t / T); k < (int32_t)((int64_t)nb * (t + 1) / T); k++) {
+                const int32_t i = lo + (idx.empty() ? k : idx[k]);
+                uint32_t len = (uint32_t)(off[k + 1] - off[k]);
+                int64_t need = rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
+                if (need < 0) {
+                    bad[t] = 1;
+                    return;
+                }
+                if ((size_t)need >= buf.size()) {
+                    buf.resize((size_t)need + 1);
+                    rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
+                }
+                std::string text(buf.data(), (size_t)need);
+                size_t cut = text.size() > 1 ? text.rfind('\n', text.size() - 2) : std::string::npos;
+                if (cut != std::string::npos) {
+                    bt.warn[k] = text.substr(0, cut + 1);
+                    text.erase(0, cut + 1);
+                }
+                bt.record[k] = std::move(text);
+            }
+        };
+        if (T == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; t++) th.emplace_back(work, t);
+            for (auto& x : th) x.join();
+        }
+        for (int t = 0; t < T; t++)
+            if (bad[t]) {
                 so.code = 3;
                 return false;
             }
-            if ((size_t)need >= buf.size()) {
-                buf.resize((size_t)need + 1);
-                rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
-            }
-            std::string text(buf.data(), (size_t)need);
-            size_t cut = text.size() > 1 ? text.rfind('\n', text.size() - 2) : std::string::npos;
-            if (cut != std::string::npos) {
-                bt.warn[k] = text.substr(0, cut + 1);
-                text.erase(0, cut + 1);
-            }
-            bt.record[k] = std::move(text);
-            bt.score[k] = res.reads[k].score;
-        }
         return true;
     };
     Batch fwd;
