@@ -106,7 +106,7 @@ struct rg_ctx {
     // score-transport kernel (pathwise_tr.cu): per-row records of both directions and its work-space
     DevBuf<PwtRow> d_pwt_rows, d_pwt_rrows;
     DevBuf<int32_t> d_nonmem_hi;
-    DevBuf<int32_t> d_tr_tables, d_tr_ring_lead, d_tr_lastcol, d_tr_colmax;
+    DevBuf<int32_t> d_tr_tables, d_tr_ring_lead, d_tr_lastcol, d_tr_colmax, d_tr_stage;
     DevBuf<uint16_t> d_tr_ring_org;
     DevBuf<uint4> d_tr_ring_meta;
     DevBuf<uint8_t> d_tr_mv_f, d_tr_mv_r, d_tr_own;
@@ -754,80 +754,125 @@ static int align_pathwise(rg_ctx* c, int mode) {
     const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
     if (f.P > 128) return c->fail(RG_ERR_UNSUPPORTED, "more than 128 paths are not supported on the device yet");
     if (n >= (1u << 21)) return c->fail(RG_ERR_UNSUPPORTED, "graph too large for the pathwise kernels");
-    const int cpt = pathwise_tr_cpt(c->max_len + 1);
-    if (c->pw_v1 || cpt == 0) return align_pathwise_v1(c, mode);
-    PwtWorkspace ws{};
-    ws.CPT = (uint32_t)cpt;
-    ws.LP = 256u * cpt;
-    ws.LT = ws.LP + 32;
-    ws.Pp = PW * 32;
-    ws.TRmax = std::max(c->dpg.TR, rec ? c->dpg_rev.TR : 2u);
-    ws.ringmax = std::max(c->dpg.ring, rec ? c->dpg_rev.ring : 2u);
-    ws.run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * ws.LP), 1u << 22);
-    ws.diag = getenv("RG_PW_DIAG") ? 1u : 0u;
-    int bps = 1;
-    int lc = pathwise_tr_blocks_per_sm(c->dpg, c->dpg_rev, c->ds, ws, mode != RG_MODE_PATHWISE_GLOBAL, &bps);
-    if (lc == -3) return align_pathwise_v1(c, mode);
-    if (lc != 0) return c->cuda_fail("kernel configuration");
-    if (bps < 1) bps = 1;
-    if (const char* e = getenv("RG_PW_BPS")) bps = std::max(1, std::min(bps, atoi(e)));  // testing: CTAs per SM
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    free_b += (c->d_tr_tables.cap + c->d_tr_ring_lead.cap + c->d_tr_lastcol.cap + c->d_tr_own_pred.cap) * 4 +
-              c->d_tr_ring_org.cap * 2 + c->d_tr_ring_meta.cap * 16 + c->d_tr_mv_f.cap + c->d_tr_mv_r.cap + c->d_tr_own.cap +
-              (c->d_tr_cb_f.cap + c->d_tr_cb_r.cap) * 8 + (c->d_slot_runs.cap + c->d_out_runs.cap) * sizeof(rg_run);
-    const size_t sz_tables = (size_t)ws.TRmax * ws.Pp * ws.LT, sz_ring = (size_t)ws.ringmax * ws.LP;
-    const size_t sz_mvf = (size_t)c->dpg.n_groups * (ws.LP / 4), sz_mvr = rec ? (size_t)c->dpg_rev.n_groups * (ws.LP / 4) : 0;
-    const size_t sz_own = (size_t)n * (ws.LP / 4), sz_cb = rec ? (size_t)n * ws.LP : 0, sz_last = rec ? (size_t)n * ws.Pp : 0;
-    const size_t per_slot = sz_tables * 4 + sz_ring * 6 + (size_t)ws.ringmax * 16 + sz_mvf + sz_mvr + sz_own + (size_t)n * 4 +
-                            sz_cb * 16 + sz_last * 4 + (size_t)ws.run_cap * sizeof(rg_run);
-    const size_t budget_all = (size_t)(free_b * 0.85);
-    size_t out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(ws.run_cap, 16384), (budget_all / 8) / sizeof(rg_run));
-    out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
-    const size_t budget = budget_all - out_runs_cap * sizeof(rg_run);
-    uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * bps, (uint32_t)c->n_reads);
-    slots = (uint32_t)std::min<size_t>(slots, budget / per_slot);
-    if (slots < 1) return c->fail(RG_ERR_NOMEM, "not enough device memory for one pathwise read in flight");
-    ws.slots = slots;
-    bool ok = c->d_tr_tables.ensure(slots * sz_tables) && c->d_tr_ring_lead.ensure(slots * sz_ring) &&
-              c->d_tr_ring_org.ensure(slots * sz_ring) && c->d_tr_ring_meta.ensure((size_t)slots * ws.ringmax) &&
-              c->d_tr_mv_f.ensure(slots * sz_mvf) && c->d_tr_mv_r.ensure(slots * sz_mvr) && c->d_tr_own.ensure(slots * sz_own) &&
-              c->d_tr_own_pred.ensure((size_t)slots * n) && c->d_tr_cb_f.ensure(slots * sz_cb) && c->d_tr_cb_r.ensure(slots * sz_cb) &&
-              c->d_tr_lastcol.ensure(slots * sz_last) && c->d_tr_colmax.ensure((size_t)slots * 2 * ws.LP) && c->d_slot_runs.ensure((size_t)slots * ws.run_cap) &&
-              c->d_out_runs.ensure(out_runs_cap) && c->d_results.ensure(c->n_reads + 1) && c->d_counters.ensure(4);
-    if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
-    ws.tables = c->d_tr_tables.p;
-    ws.ring_lead = c->d_tr_ring_lead.p;
-    ws.ring_org = c->d_tr_ring_org.p;
-    ws.ring_meta = c->d_tr_ring_meta.p;
-    ws.mv_f = c->d_tr_mv_f.p;
-    ws.mv_r = c->d_tr_mv_r.p;
-    ws.own = c->d_tr_own.p;
-    ws.own_pred = c->d_tr_own_pred.p;
-    ws.cb_f = c->d_tr_cb_f.p;
-    ws.cb_r = c->d_tr_cb_r.p;
-    ws.lastcol = c->d_tr_lastcol.p;
-    ws.colmax = c->d_tr_colmax.p;
-    ws.runs = c->d_slot_runs.p;
-    PoaBatch b{};
-    b.reads = c->d_reads.p;
-    b.read_off = c->d_read_off.p;
-    b.n_reads = c->n_reads;
-    b.order = c->d_order.p;
-    b.results = c->d_results.p;
-    b.out_runs = c->d_out_runs.p;
-    b.out_run_cap = out_runs_cap;
-    b.counters = c->d_counters.p;
+    if (c->pw_v1) return align_pathwise_v1(c, mode);
+    // ---- reads are grouped by the column block they need (256 x {4, 8, 16, 32} columns, 384 x 32 for the longest): the
+    // processing order is longest-first, so every class is a contiguous range of it; one launch per class, each with a
+    // work-space sized for its own read length
+    struct Cls {
+        int32_t lo, hi;     // range of the processing order
+        uint32_t LP, cpt, NT;
+    };
+    std::vector<Cls> classes;
+    {
+        std::vector<int32_t> order(c->n_reads);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            return c->h_off[a + 1] - c->h_off[a] > c->h_off[b + 1] - c->h_off[b];
+        });   // the same order rg_upload_reads stored on the device
+        for (int32_t k = 0; k < c->n_reads; k++) {
+            const uint32_t L = (uint32_t)(c->h_off[order[k] + 1] - c->h_off[order[k]]) + 1;
+            uint32_t cpt = (uint32_t)pathwise_tr_cpt(L), nt = 256;
+            if (!cpt) {
+                cpt = (uint32_t)pathwise_tr_cpt_wide(L);
+                nt = 384;
+            }
+            if (!cpt) return align_pathwise_v1(c, mode);   // beyond 12 287 bases: the per-path kernel (bounded by shared memory)
+            if (classes.empty() || classes.back().cpt != cpt || classes.back().NT != nt) classes.push_back({k, k, nt * cpt, cpt, nt});
+            classes.back().hi = k + 1;
+        }
+    }
+    if (!c->d_results.ensure(c->n_reads + 1) || !c->d_counters.ensure(4)) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
     cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(unsigned long long), c->stream);
-    cudaEventRecord(c->ev0, c->stream);
-    int rc = launch_pathwise_tr(mode, c->dpg, c->dpg_rev, c->ds, ws, b, (int)slots, c->stream);
-    cudaEventRecord(c->ev1, c->stream);
-    if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("pathwise kernel");
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-    c->kernel_ms += ms;
-    c->launches += 1;
-    c->slots_used = slots;
+    // one run buffer for the whole batch, sized before the per-class work-spaces
+    size_t out_runs_cap;
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        free_b += c->d_out_runs.cap * sizeof(rg_run);
+        const uint32_t rc_max = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * classes.front().LP), 1u << 22);
+        out_runs_cap = std::min<uint64_t>((uint64_t)c->n_reads * std::min<uint32_t>(rc_max, 16384), ((size_t)(free_b * 0.85) / 8) / sizeof(rg_run));
+        out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
+        if (!c->d_out_runs.ensure(out_runs_cap)) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
+    }
+    for (const Cls& cl : classes) {
+        const bool wide = cl.NT == 384;
+        PwtWorkspace ws{};
+        ws.CPT = cl.cpt;
+        ws.NT = cl.NT;
+        ws.LP = cl.LP;
+        ws.LT = ws.LP + 32;
+        ws.Pp = PW * 32;
+        ws.TRmax = std::max(c->dpg.TR, rec ? c->dpg_rev.TR : 2u);
+        ws.ringmax = std::max(c->dpg.ring, rec ? c->dpg_rev.ring : 2u);
+        ws.run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)n + 2 * ws.LP), 1u << 22);
+        ws.diag = getenv("RG_PW_DIAG") ? 1u : 0u;
+        ws.stage = wide ? (int32_t*)1 : nullptr;   // non-null: sizes the shared memory for the wide layout (pointer set below)
+        int bps = 1;
+        const bool mx = mode != RG_MODE_PATHWISE_GLOBAL;
+        int lc = wide ? pathwise_tr_blocks_per_sm_wide(c->dpg, c->dpg_rev, c->ds, ws, mx, &bps)
+                      : pathwise_tr_blocks_per_sm(c->dpg, c->dpg_rev, c->ds, ws, mx, &bps);
+        if (lc == -3) return c->fail(RG_ERR_UNSUPPORTED, "read too long for the pathwise kernel's shared memory");
+        if (lc != 0) return c->cuda_fail("kernel configuration");
+        if (bps < 1) bps = 1;
+        if (const char* e = getenv("RG_PW_BPS")) bps = std::max(1, std::min(bps, atoi(e)));  // testing: CTAs per SM
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        free_b += (c->d_tr_tables.cap + c->d_tr_ring_lead.cap + c->d_tr_lastcol.cap + c->d_tr_own_pred.cap + c->d_tr_colmax.cap + c->d_tr_stage.cap) * 4 +
+                  c->d_tr_ring_org.cap * 2 + c->d_tr_ring_meta.cap * 16 + c->d_tr_mv_f.cap + c->d_tr_mv_r.cap + c->d_tr_own.cap +
+                  (c->d_tr_cb_f.cap + c->d_tr_cb_r.cap) * 8 + c->d_slot_runs.cap * sizeof(rg_run);
+        const size_t sz_tables = (size_t)ws.TRmax * ws.Pp * ws.LT, sz_ring = (size_t)ws.ringmax * ws.LP;
+        const size_t sz_mvf = (size_t)c->dpg.n_groups * (ws.LP / 4), sz_mvr = rec ? (size_t)c->dpg_rev.n_groups * (ws.LP / 4) : 0;
+        const size_t sz_own = (size_t)n * (ws.LP / 4), sz_cb = rec ? (size_t)n * ws.LP : 0, sz_last = rec ? (size_t)n * ws.Pp : 0;
+        const size_t sz_stage = wide ? (size_t)2 * ws.LP : 0;
+        const size_t per_slot = sz_tables * 4 + sz_ring * 6 + (size_t)ws.ringmax * 16 + sz_mvf + sz_mvr + sz_own + (size_t)n * 4 +
+                                sz_cb * 16 + sz_last * 4 + (size_t)2 * ws.LP * 4 + sz_stage * 4 + (size_t)ws.run_cap * sizeof(rg_run);
+        const size_t budget = (size_t)(free_b * 0.9);
+        uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * bps, (uint32_t)(cl.hi - cl.lo));
+        slots = (uint32_t)std::min<size_t>(slots, budget / per_slot);
+        if (slots < 1) return c->fail(RG_ERR_NOMEM, "not enough device memory for one pathwise read in flight");
+        ws.slots = slots;
+        bool ok = c->d_tr_tables.ensure(slots * sz_tables) && c->d_tr_ring_lead.ensure(slots * sz_ring) &&
+                  c->d_tr_ring_org.ensure(slots * sz_ring) && c->d_tr_ring_meta.ensure((size_t)slots * ws.ringmax) &&
+                  c->d_tr_mv_f.ensure(slots * sz_mvf) && c->d_tr_mv_r.ensure(slots * sz_mvr) && c->d_tr_own.ensure(slots * sz_own) &&
+                  c->d_tr_own_pred.ensure((size_t)slots * n) && c->d_tr_cb_f.ensure(slots * sz_cb) && c->d_tr_cb_r.ensure(slots * sz_cb) &&
+                  c->d_tr_lastcol.ensure(slots * sz_last) && c->d_tr_colmax.ensure((size_t)slots * 2 * ws.LP) &&
+                  c->d_tr_stage.ensure(slots * sz_stage) && c->d_slot_runs.ensure((size_t)slots * ws.run_cap);
+        if (!ok) return c->fail(RG_ERR_NOMEM, "device workspace allocation failed");
+        ws.tables = c->d_tr_tables.p;
+        ws.ring_lead = c->d_tr_ring_lead.p;
+        ws.ring_org = c->d_tr_ring_org.p;
+        ws.ring_meta = c->d_tr_ring_meta.p;
+        ws.mv_f = c->d_tr_mv_f.p;
+        ws.mv_r = c->d_tr_mv_r.p;
+        ws.own = c->d_tr_own.p;
+        ws.own_pred = c->d_tr_own_pred.p;
+        ws.cb_f = c->d_tr_cb_f.p;
+        ws.cb_r = c->d_tr_cb_r.p;
+        ws.lastcol = c->d_tr_lastcol.p;
+        ws.colmax = c->d_tr_colmax.p;
+        ws.stage = wide ? c->d_tr_stage.p : nullptr;
+        ws.runs = c->d_slot_runs.p;
+        PoaBatch b{};
+        b.reads = c->d_reads.p;
+        b.read_off = c->d_read_off.p;
+        b.n_reads = cl.hi - cl.lo;
+        b.order = c->d_order.p + cl.lo;
+        b.results = c->d_results.p;
+        b.out_runs = c->d_out_runs.p;
+        b.out_run_cap = out_runs_cap;
+        b.counters = c->d_counters.p;
+        cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long), c->stream);   // the ticket restarts, the run count goes on
+        cudaEventRecord(c->ev0, c->stream);
+        int rc = wide ? launch_pathwise_tr_wide(mode, c->dpg, c->dpg_rev, c->ds, ws, b, (int)slots, c->stream)
+                      : launch_pathwise_tr(mode, c->dpg, c->dpg_rev, c->ds, ws, b, (int)slots, c->stream);
+        cudaEventRecord(c->ev1, c->stream);
+        if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("pathwise kernel");
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->kernel_ms += ms;
+        c->launches += 1;
+        c->slots_used = slots;
+    }
     cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("result copy");
     c->n_runs_total = std::min<uint64_t>(c->h_counters.p[1], out_runs_cap);

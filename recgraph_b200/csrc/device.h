@@ -165,12 +165,19 @@ struct PwtWorkspace {
     uint32_t LP, LT, Pp, CPT;   // columns (= 256 * CPT), table row stride (LP + 32), padded paths, columns per thread
     uint32_t TRmax, ringmax;
     uint32_t run_cap, slots;
+    int32_t* stage;     // wide instance only: slots * 2 * LP staging rows of the materialising rows (else nullptr: shared memory)
+    uint32_t NT;        // threads per CTA of the instance that runs (256 / 384)
     uint32_t diag;      // RG_PW_DIAG: per-read phase timings (kilo-cycles) overwrite result fields — profiling only
 };
 int pathwise_tr_cpt(uint32_t Lmax);   // columns per thread for reads of up to Lmax columns; 0 = too long
 int pathwise_tr_blocks_per_sm(const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws, bool rec, int* nb);
 int launch_pathwise_tr(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws,
                        const PoaBatch& b, int blocks, void* stream);
+// the same kernel with 384 threads per CTA (pathwise_tr_wide.cu): reads of up to 12 287 bases
+int pathwise_tr_cpt_wide(uint32_t Lmax);
+int pathwise_tr_blocks_per_sm_wide(const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws, bool rec, int* nb);
+int launch_pathwise_tr_wide(int mode, const DevPathGraph& g, const DevPathGraph& rg_, const DevScoring& s, const PwtWorkspace& ws,
+                            const PoaBatch& b, int blocks, void* stream);
 // Modes 6 / 7 (pathwise_gap.cu): the reference's three delta-encoded tensors per read in flight.
 struct PwGapWorkspace {
     int32_t* T;      // slots * 3 * n * Lp * Pp   (dpm, x, y)
