@@ -113,6 +113,8 @@ struct rg_ctx {
     DevBuf<uint32_t> d_tr_own_pred;
     DevBuf<int2> d_tr_cb_f, d_tr_cb_r;
     DevBuf<int32_t> d_gapT;
+    uint64_t tr_sig = 0;     // shape of the transport kernel's current work-space (mode, column class, batch size, rows)
+    uint32_t tr_slots = 0;
     bool pw_v1 = getenv("RG_PW_V1") != nullptr;   // testing: the per-path kernel of round 1 (pathwise.cu) for A/B runs
     DevBuf<int32_t> d_pwS, d_pwLead;
     DevBuf<uint32_t> d_pwTrace;
@@ -606,7 +608,23 @@ int rg_upload_reads(rg_ctx* c, int32_t n_reads, const uint8_t* read_codes, const
     return RG_OK;
 }
 
+// Work-spaces are sized from the free memory of the device: a family that starts after another one first returns that
+// family's buffers (they are re-created on demand).
+static void release_pathwise_ws(rg_ctx* c) {
+    c->d_tr_tables.release(), c->d_tr_ring_lead.release(), c->d_tr_lastcol.release(), c->d_tr_colmax.release(), c->d_tr_stage.release();
+    c->d_tr_ring_org.release(), c->d_tr_ring_meta.release(), c->d_tr_mv_f.release(), c->d_tr_mv_r.release(), c->d_tr_own.release();
+    c->d_tr_own_pred.release(), c->d_tr_cb_f.release(), c->d_tr_cb_r.release(), c->d_gapT.release();
+    c->d_pwS.release(), c->d_pwLead.release(), c->d_pwTrace.release(), c->d_rS.release(), c->d_rLead.release(), c->d_rTrace.release();
+    c->d_fm.release(), c->d_rwbest.release(), c->d_lastcol.release();
+    c->tr_sig = 0;
+    c->tr_slots = 0;
+}
+static void release_poa_ws(rg_ctx* c) {
+    c->d_rowmeta.release(), c->d_ring_m.release(), c->d_ring_y.release(), c->d_trace.release();
+}
+
 static int align_poa(rg_ctx* c, int mode) {
+    release_pathwise_ws(c);
     const FlatGraph& f = c->fg;
     const uint32_t n = f.n;
     const uint32_t Lmax = c->max_len + 1;
@@ -654,7 +672,7 @@ static int align_poa(rg_ctx* c, int mode) {
     const int tb_alloc = blk2 ? 1 : trace_bytes;
     const uint64_t full = blk2 ? plane_bytes + side_bytes
                           : blkC ? (uint64_t)n * wstride  // fixed row stride, absolute columns
-                              : std::min<uint64_t>((uint64_t)n * Lmax, 0x7ffffe00ull);  // the band can open to the whole row
+                              : (uint64_t)n * (Lmax + 15);  // the band can open to the whole row; rows start at multiples of 16 cells
     const uint32_t run_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4096, (uint64_t)(n / 4 + 2 * Lmax)), 1u << 22);
     const size_t per_slot_fixed = (size_t)n * sizeof(RowMeta) + (size_t)c->dg.ring * wstride * 8 + (size_t)run_cap * sizeof(rg_run);
     const size_t budget_all = (size_t)(free_b * 0.85);
@@ -671,7 +689,12 @@ static int align_poa(rg_ctx* c, int mode) {
         if ((size_t)slots * per_slot > budget) {
             uint32_t min_slots = std::min<uint32_t>(slots, std::max<uint32_t>(8, (uint32_t)c->sms * 8 >> attempt));
             uint32_t fit = (uint32_t)std::min<size_t>(budget / per_slot, 1u << 20) / 8 * 8;
-            if (fit >= min_slots) {
+            if (blkC) {
+                // the blocked kernels address their trace by row: a slot needs the whole n x 32C trace, so large graphs
+                // simply run with fewer reads in flight
+                if (fit < 8) return c->fail(RG_ERR_NOMEM, "not enough device memory for the blocked kernel's trace");
+                slots = std::min(slots, fit);
+            } else if (fit >= min_slots) {
                 slots = fit;
             } else {
                 slots = min_slots;
@@ -681,6 +704,7 @@ static int align_poa(rg_ctx* c, int mode) {
             }
         }
         trace_cap = (trace_cap + 255) & ~255ull;  // round UP: `full` must always fit
+        if (blkC && trace_cap < full) return c->fail(RG_ERR_NOMEM, "not enough device memory for the blocked kernel's trace");
         bool ok = c->d_rowmeta.ensure((size_t)slots * n) && c->d_ring_m.ensure((size_t)slots * c->dg.ring * wstride) &&
                   c->d_ring_y.ensure((size_t)slots * c->dg.ring * wstride) &&
                   c->d_trace.ensure((size_t)slots * trace_cap * tb_alloc) &&
@@ -754,6 +778,7 @@ static int align_pathwise(rg_ctx* c, int mode) {
     const bool rec = mode == RG_MODE_REC_GLOBAL || mode == RG_MODE_REC_SEMIGLOBAL;
     if (f.P > 128) return c->fail(RG_ERR_UNSUPPORTED, "more than 128 paths are not supported on the device yet");
     if (n >= (1u << 21)) return c->fail(RG_ERR_UNSUPPORTED, "graph too large for the pathwise kernels");
+    release_poa_ws(c);
     if (c->pw_v1) return align_pathwise_v1(c, mode);
     // ---- reads are grouped by the column block they need (256 x {4, 8, 16, 32} columns, 384 x 32 for the longest): the
     // processing order is longest-first, so every class is a contiguous range of it; one launch per class, each with a
@@ -815,11 +840,18 @@ static int align_pathwise(rg_ctx* c, int mode) {
         if (lc != 0) return c->cuda_fail("kernel configuration");
         if (bps < 1) bps = 1;
         if (const char* e = getenv("RG_PW_BPS")) bps = std::max(1, std::min(bps, atoi(e)));  // testing: CTAs per SM
+        // The work-space of a (mode, column class, batch size) is kept between calls; any other shape starts from a clean
+        // slate, so that the sizes below are taken from what is really free (a buffer that stays larger than needed would be
+        // counted as reusable without being so).
+        const uint64_t sig = ((uint64_t)mode << 56) ^ ((uint64_t)cl.LP << 32) ^ ((uint64_t)cl.NT << 24) ^ (uint64_t)(cl.hi - cl.lo) ^
+                             ((uint64_t)n << 8) ^ ((uint64_t)c->dpg.n_groups << 40);
+        const bool same_shape = sig == c->tr_sig && c->tr_slots > 0;
+        if (!same_shape) {
+            release_pathwise_ws(c);
+            c->d_slot_runs.release();
+        }
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        free_b += (c->d_tr_tables.cap + c->d_tr_ring_lead.cap + c->d_tr_lastcol.cap + c->d_tr_own_pred.cap + c->d_tr_colmax.cap + c->d_tr_stage.cap) * 4 +
-                  c->d_tr_ring_org.cap * 2 + c->d_tr_ring_meta.cap * 16 + c->d_tr_mv_f.cap + c->d_tr_mv_r.cap + c->d_tr_own.cap +
-                  (c->d_tr_cb_f.cap + c->d_tr_cb_r.cap) * 8 + c->d_slot_runs.cap * sizeof(rg_run);
         const size_t sz_tables = (size_t)ws.TRmax * ws.Pp * ws.LT, sz_ring = (size_t)ws.ringmax * ws.LP;
         const size_t sz_mvf = (size_t)c->dpg.n_groups * (ws.LP / 4), sz_mvr = rec ? (size_t)c->dpg_rev.n_groups * (ws.LP / 4) : 0;
         const size_t sz_own = (size_t)n * (ws.LP / 4), sz_cb = rec ? (size_t)n * ws.LP : 0, sz_last = rec ? (size_t)n * ws.Pp : 0;
@@ -828,9 +860,11 @@ static int align_pathwise(rg_ctx* c, int mode) {
                                 sz_cb * 16 + sz_last * 4 + (size_t)2 * ws.LP * 4 + sz_stage * 4 + (size_t)ws.run_cap * sizeof(rg_run);
         const size_t budget = (size_t)(free_b * 0.9);
         uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * bps, (uint32_t)(cl.hi - cl.lo));
-        slots = (uint32_t)std::min<size_t>(slots, budget / per_slot);
+        slots = same_shape ? c->tr_slots : (uint32_t)std::min<size_t>(slots, budget / per_slot);
         if (slots < 1) return c->fail(RG_ERR_NOMEM, "not enough device memory for one pathwise read in flight");
         ws.slots = slots;
+        c->tr_sig = sig;
+        c->tr_slots = slots;
         bool ok = c->d_tr_tables.ensure(slots * sz_tables) && c->d_tr_ring_lead.ensure(slots * sz_ring) &&
                   c->d_tr_ring_org.ensure(slots * sz_ring) && c->d_tr_ring_meta.ensure((size_t)slots * ws.ringmax) &&
                   c->d_tr_mv_f.ensure(slots * sz_mvf) && c->d_tr_mv_r.ensure(slots * sz_mvr) && c->d_tr_own.ensure(slots * sz_own) &&
@@ -964,6 +998,7 @@ static int align_pathwise_gap(rg_ctx* c, int mode) {
     const FlatGraph& f = c->fg;
     const uint32_t n = f.n;
     if (f.P > 128) return c->fail(RG_ERR_UNSUPPORTED, "more than 128 paths are not supported on the device yet");
+    release_poa_ws(c);
     PwGapWorkspace ws{};
     ws.Lp = c->max_len + 1;
     ws.Pp = f.PW * 32;

@@ -330,14 +330,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
             }
             if (lane == 0) {
                 RowMeta rm;
-                rm.base = (int32_t)((int64_t)off - (int64_t)left);
+                rm.base = (int32_t)(off >> 4);   // rows start at multiples of 16 cells: 2^31 x 16 cells of trace per read
                 rm.left = left;
                 rm.right = right;
                 rm.bsp = row_best_col;
                 rowmeta[i] = rm;
             }
             __syncwarp();
-            off += W;
+            off += (W + 15) & ~15ull;
             prev_left = left;
             prev_right = right;
             prev_bsp = row_best_col;
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
             int bandchk = -1;  // -1 undecided, 0 false, 1 true
             bool panic = false;
             for (;;) {
-                uint32_t code = trace[(int64_t)meta.base + col];
+                uint32_t code = trace[((int64_t)meta.base << 4) + ((int64_t)col - (int64_t)meta.left)];
                 uint32_t dir = code & 3u;
                 if (dir == DIR_O) break;
                 if (bandchk < 0) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                                 break;
                             }
                             col -= 1;
-                            code = trace[(int64_t)meta.base + col];
+                            code = trace[((int64_t)meta.base << 4) + ((int64_t)col - (int64_t)meta.left)];
                         }
                     } else {
                         em.step(RG_OP_L, row, lane);
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                                 panic = true;
                                 break;
                             }
-                            code = trace[(int64_t)meta.base + col];
+                            code = trace[((int64_t)meta.base << 4) + ((int64_t)col - (int64_t)meta.left)];
                         }
                     } else {
                         uint32_t p = rnwp ? g.pred_idx[g.pred_off[row] + ((code >> (4 + SB)) & SMASK)] : row - 1;
