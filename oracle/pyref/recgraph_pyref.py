@@ -12,6 +12,11 @@ the CUDA path — is itself checked by a second reading of the reference for the
   recombination_output.rs:12-782                 the four gaf_output_* builders
   utils.rs:221-323, gaf_output.rs:70-94          get_path_len_start_end, get_rec_path_len_start_end, GAFStruct::to_string
   score_matrix.rs:35-51, sequences.rs:5-45, main.rs:253-312
+and, for the headline mode 2 whose traceback the reference's unit tests do not pin either:
+  graph.rs:31-123, utils.rs:17-72,103-165      create_graph_struct, set_ampl_for_row, set_r_values, handle map
+  gap_global_abpoa.rs:11-455                     exec, get_best_d / u / l, band_ampl_enough
+  bitfield_path.rs:3-44                          the 32-bit trace cell with its 16-bit predecessor
+  gaf_output.rs:96-253,867-892                   gaf_of_gap_abpoa, node_start, set_cigar_substring
 
 `rev_align` is `align` mirrored in i and j (checked mechanically: sed 's/i + 1/i - 1/; s/j + 1/j - 1/' on lines 129-435
 diffs clean against 436-745 apart from the border cases), so one cell routine parameterised by direction serves both.
@@ -865,6 +870,370 @@ def mode89(mode, seq, g, rg, sm, brc, mrc, displ, rbw, name):
             return gaf_no_rec(m, g, seq, sm, fbp, None, True, name)
         return gaf_no_rec(m, g, seq, sm, fbp, ending_node_of(m, fbp, g), False, name)
     return gaf_rec(m, w, g, rg, seq, sm, fbp, rbp, fen, rsn, col, score, mode == 8, name)
+
+
+# ------------------------------------------------------------------------------------------------ mode 2 (POA, affine, banded)
+def read_gfa_links(text):
+    """left neighbours of every segment in L-line order (handlegraph: handle_edges_iter(h, Left))"""
+    left = {}
+    for ln in text.splitlines():
+        f = ln.split("\t")
+        if f[0] == "L":
+            a, b = int(f[1]), int(f[3])
+            if a not in left.setdefault(b, []):
+                left[b].append(a)
+    return left
+
+
+def create_graph_struct(segs, left):
+    """graph.rs:31-123 (amb_mode = false)"""
+    lnz = ["$"]
+    pos = {}
+    for sid in sorted(segs):
+        start = len(lnz)
+        lnz += list(segs[sid])
+        pos[sid] = (start, len(lnz) - 1)
+    last_nodes = {sid: pos[sid][1] for sid in segs}
+    nwp = [False] * (len(lnz) + 1)
+    pred = {}
+    for sid in sorted(segs):
+        hs = pos[sid][0]
+        ln = left.get(sid, [])
+        if not ln:
+            nwp[hs] = True
+            pred.setdefault(hs, []).append(0)
+        for p in ln:
+            last_nodes.pop(p, None)
+            nwp[hs] = True
+            pred.setdefault(hs, []).append(pos[p][1])
+    lnz.append("F")
+    nwp[len(lnz) - 1] = True
+    for idx in sorted(last_nodes.values()):
+        pred.setdefault(len(lnz) - 1, []).append(idx)
+    hofp = {0: "-1"}
+    cur = 0
+    ids = sorted(segs)
+    for i in range(1, len(nwp) - 1):
+        if nwp[i]:
+            cur += 1
+        hofp[i] = str(ids[cur - 1])
+    return lnz, nwp, pred, hofp
+
+
+def set_r_values(nwp, pred, n):
+    """utils.rs:103-126"""
+    r = [-1] * n
+    r[n - 1] = 0
+    for p in pred[n - 1]:
+        r[p] = 0
+    for i in range(n - 2, 0, -1):
+        if r[i] == -1 or r[i] > r[i + 1] + 1:
+            r[i] = r[i + 1] + 1
+        if nwp[i]:
+            for p in pred[i]:
+                if r[p] == -1 or r[p] > r[i] + 1:
+                    r[p] = r[i] + 1
+    return [x if x >= 0 else (1 << 64) - 1 for x in r]   # `as usize`
+
+
+def _as_i32(v):
+    v &= 0xffffffff
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+def set_ampl_for_row(i, p_arr, r_val, bsp, seq_len, bta):
+    """utils.rs:17-72 (simd_version = false)"""
+    if i == 0:
+        ms = me = 0
+    elif not p_arr:
+        ms = me = bsp[i - 1] + 1
+    else:
+        pl = min(bsp[p] for p in p_arr)
+        pr = max(bsp[p] for p in p_arr)
+        ms, me = pl + 1, pr + 1
+    tmp = min(_as_i32(ms), _as_i32(_as_i32(seq_len) - _as_i32(r_val)) - _as_i32(bta))
+    band_start = 0 if tmp < 0 else max(0, tmp)
+    if seq_len > r_val:
+        band_end = min(seq_len, max(me, seq_len - r_val) + bta)
+    else:
+        band_end = min(seq_len, me + bta)
+    return band_start, band_end
+
+
+def cell(pred, d):
+    """bitfield_path.rs:39-44: the predecessor is truncated to 16 bits"""
+    return (pred & 0xffff, d)
+
+
+def mode2_exec(seq, name, lnz, nwp, pred, sm, o, e, bta, hofp):
+    """gap_global_abpoa.rs:11-250; returns (stdout text of the call, score)"""
+    n, L = len(lnz), len(seq)
+    m, x, y = [[] for _ in range(n)], [[] for _ in range(n)], [[] for _ in range(n)]
+    path, path_x, path_y = [[] for _ in range(n)], [[] for _ in range(n)], [[] for _ in range(n)]
+    r_values = set_r_values(nwp, pred, n)
+    bsp = [0] * n
+    ampl = [(0, 0)] * n
+
+    def jpos(p, i, j):
+        lp, li = ampl[p][0], ampl[i][0]
+        return j + (li - lp) if lp < li else j - (lp - li)
+
+    for i in range(n - 1):
+        p_arr = pred[i] if nwp[i] else []
+        left, right = set_ampl_for_row(i, p_arr, r_values[i], bsp, L, bta)
+        ampl[i] = (left, right)
+        W = right - left
+        if W <= 0:
+            raise RuntimeError("empty band row (the reference panics)")
+        m[i], x[i], y[i] = [0] * W, [0] * W, [0] * W
+        path[i], path_x[i], path_y[i] = [(0, "O")] * W, [(0, "O")] * W, [(0, "O")] * W
+        best = 0
+        for j in range(W):
+            if i == 0 and j == 0:
+                m[i][j] = 0
+                path[i][j] = cell(0, "O")
+            elif i == 0:
+                y[i][j] = o + e * (j + left)
+                m[i][j] = y[i][j]
+                path[i][j] = cell(i, "L")
+            elif j == 0 and left == 0:
+                best_p = i - 1 if not nwp[i] else min(pred[i])
+                x[i][j] = o + e * (best_p + 1)
+                m[i][j] = x[i][j]
+                path[i][j] = cell(best_p, "U")
+            else:
+                pa = pred[i] if nwp[i] else [i - 1]
+                best_p = i - 1 if not nwp[i] else min(pred[i])
+                # l
+                if j > 0:
+                    l_x, l_m = x[i][j - 1], m[i][j - 1] + o
+                    if l_x > l_m:
+                        x[i][j] = l_x + e
+                        path_x[i][j] = cell(i, "X")
+                    else:
+                        x[i][j] = l_m + e
+                    l_pred = i
+                else:
+                    x[i][j] = 2 * o + e * (best_p + 1) + e * (j + left)
+                    l_pred = best_p
+                # u
+                first = True
+                u_m = u_y = um_i = uy_i = 0
+                for p in pa:
+                    if ampl[p][0] <= j + left < ampl[p][1]:
+                        jp = jpos(p, i, j)
+                        cm, cy = m[p][jp] + o, y[p][jp]
+                        if first:
+                            first = False
+                            u_m, u_y, um_i, uy_i = cm, cy, p, p
+                        if cm > u_m:
+                            u_m, um_i = cm, p
+                        if cy > u_y:
+                            u_y, uy_i = cy, p
+                if first:
+                    y[i][j] = 2 * o + e * (best_p + 1) + e * (j + left)
+                    u_pred = best_p
+                elif u_y > u_m:
+                    y[i][j] = u_y + e
+                    u_pred = uy_i
+                    path_y[i][j] = cell(uy_i, "Y")
+                else:
+                    y[i][j] = u_m + e
+                    u_pred = um_i
+                # d
+                first = True
+                d = d_idx = 0
+                for p in pa:
+                    if ampl[p][0] < j + left <= ampl[p][1]:
+                        cd = m[p][jpos(p, i, j) - 1]
+                        if first:
+                            d, d_idx, first = cd, p, False
+                        if cd > d:
+                            d, d_idx = cd, p
+                l, u = x[i][j], y[i][j]
+                if not first:
+                    d += sm[(lnz[i], seq[j + left])]
+                    if d < l:
+                        if l < u:
+                            if u_pred == 0:
+                                raise RuntimeError("set_path_cell(u_pred, 'u'): impossible direction char (reference panic)")
+                            path[i][j] = cell(u_pred, "U")
+                            m[i][j] = u
+                        else:
+                            path[i][j] = cell(l_pred, "L")
+                            m[i][j] = l
+                    elif d < u:
+                        path[i][j] = cell(u_pred, "U")
+                        m[i][j] = u
+                    else:
+                        path[i][j] = cell(d_idx, "D" if lnz[i] == seq[j + left] else "d")
+                        m[i][j] = d
+                elif l < u:
+                    path[i][j] = cell(u_pred, "U")
+                    m[i][j] = u
+                else:
+                    path[i][j] = cell(l_pred, "L")
+                    m[i][j] = l
+            if m[i][j] >= m[i][best]:
+                best = j
+        bsp[i] = best + left
+    last_row = n - 2
+    last_col = len(m[last_row]) - 1
+    for p in pred[n - 1]:
+        t = (ampl[p][1] - ampl[p][0]) - 1
+        if m[p][t] > m[last_row][last_col]:
+            last_row, last_col = p, t
+    best_value = m[last_row][last_col]
+    out = ""
+    if not band_ampl_enough(path, path_x, path_y, last_row, last_col, ampl, L):
+        out += "Band length probably too short, maybe try with larger b and f\n"
+    out += gaf_of_gap_abpoa(path, path_x, path_y, seq, name, ampl, last_row, last_col, hofp) + "\n"
+    return out, best_value
+
+
+def band_ampl_enough(path, path_x, path_y, i, j, ampl, L):
+    """gap_global_abpoa.rs:371-455"""
+    def jp(p, row, col):
+        lp, lr = ampl[p][0], ampl[row][0]
+        return col + (lr - lp) if lp < lr else col - (lp - lr)
+
+    while path[i][j][1] != "O":
+        left, right = ampl[i]
+        if i == 0 or (j == 0 and left == 0):
+            return True
+        if (j == 0 and left != 0) or (j == right - left - 1 and right != L):
+            return False
+        pred, d = path[i][j]
+        if d in ("D", "d"):
+            j = jp(pred, i, j) - 1
+            i = pred
+        elif d == "L":
+            if path_x[i][j][1] == "X":
+                while path_x[i][j][1] == "X" and j > 0:
+                    j -= 1
+            else:
+                j -= 1
+        elif d == "U":
+            if path_y[i][j][1] == "Y":
+                while path_y[i][j][1] == "Y":
+                    p = path_y[i][j][0]
+                    j = jp(p, i, j)
+                    i = p
+            else:
+                j = jp(pred, i, j)
+                i = pred
+        else:
+            return False
+    return True
+
+
+def set_cigar_substring(cm, ci, cd, cs):
+    """gaf_output.rs:876-892"""
+    assert cm * ci + ci * cd + cm * cd == 0, "wrong format in cigar string"
+    if cm > 0:
+        return f"{cm}M{cs}"
+    if ci > 0:
+        return f"{ci}I{cs}"
+    if cd > 0:
+        return f"{cd}D{cs}"
+    return cs
+
+
+def node_start(hofp, row):
+    """gaf_output.rs:867-874"""
+    h = hofp[row]
+    i = row
+    while hofp[i] == h and i > 0:
+        i -= 1
+    return row - i
+
+
+def gaf_of_gap_abpoa(path, path_x, path_y, seq, name, ampl, last_row, last_col, hofp):
+    """gaf_output.rs:96-253 (amb_mode = false)"""
+    col, row = last_col, last_row
+    hia, cigars = [], []
+    cigar = ""
+    cm = ci = cd = 0
+    curr_handle, last_dir = "", " "
+    path_length = residues = 0
+    while path[row][col][1] != "O":
+        pred, d = path[row][col]
+        if hofp[row] != curr_handle:
+            cigar = set_cigar_substring(cm, ci, cd, cigar)
+            cigars.insert(0, cigar)
+            cigar = ""
+            cm = ci = cd = 0
+        curr_handle = hofp[row]
+        if d.upper() != last_dir.upper():
+            cigar = set_cigar_substring(cm, ci, cd, cigar)
+            cm = ci = cd = 0
+        last_dir = d
+        p_left = ampl[pred][0]
+        if ampl[row][0] < p_left:
+            j_pos = col - (p_left - ampl[row][0])
+        else:
+            j_pos = col + (ampl[row][0] - p_left)
+        if d == "D":
+            hia.append(hofp[row])
+            row, col = pred, j_pos - 1
+            cm += 1
+            path_length += 1
+            residues += 1
+        elif d == "d":
+            hia.append(hofp[row])
+            row, col = pred, j_pos - 1
+            cm += 1
+            path_length += 1
+        elif d == "L":
+            if path_x[row][col][1] == "X":
+                while path_x[row][col][1] == "X":
+                    cd += 1
+                    col -= 1
+            else:
+                cd += 1
+                col -= 1
+        elif d == "U":
+            if path_y[row][col][1] == "Y":
+                while path_y[row][col][1] == "Y":
+                    lr = ampl[row][0]
+                    p = path_y[row][col][0]
+                    lp = ampl[p][0]
+                    jp = col + (lr - lp) if lp < lr else col - (lp - lr)
+                    hia.append(hofp[row])
+                    ci += 1
+                    path_length += 1
+                    col, row = jp, p
+            else:
+                hia.append(hofp[row])
+                ci += 1
+                path_length += 1
+                row, col = pred, j_pos
+        else:
+            raise RuntimeError("impossible value in poa path")
+    cigar = set_cigar_substring(cm, ci, cd, cigar)
+    cigars.insert(0, cigar)
+    hia = dedup(hia)
+    hia.reverse()
+    comments = ",".join(cigars[:-1])
+    return gaf_string(name, len(seq) - 1, col, last_col + ampl[last_row][0], "+", [int(h) for h in hia], path_length,
+                      node_start(hofp, row), node_start(hofp, last_row), residues, "*", "*", comments)
+
+
+def run_mode2(fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01, max_reads=None):
+    """main.rs:171-214 without -s; returns stdout"""
+    seqs, names = read_fasta(fasta_text)
+    segs, _paths = read_gfa(gfa_text)
+    lnz, nwp, pred, hofp = create_graph_struct(segs, read_gfa_links(gfa_text))
+    sm = score_matrix_match_mis(match, -mismatch)
+    out = ""
+    for k, seq in enumerate(seqs):
+        if max_reads is not None and k >= max_reads:
+            break
+        v = F32(F32(extra_b) + F32(F32(extra_f) * F32(len(seq))))
+        bta = 0 if not (v > 0) else int(v)
+        text, _score = mode2_exec(seq, names[k], lnz, nwp, pred, sm, -gap_open, -gap_ext, bta, hofp)
+        out += text
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ driver

@@ -65,3 +65,35 @@ def test_random_small_graphs(block, tmp_path):
                                 rec_band_width=0.7)
                 exp = _oracle(mode, str(fa), str(gfa), ["-M", "1", "-X", "3", "-R", "1", "-r", "0.05", "-B", "0.7"])
                 assert got == exp, f"seed {seed} mode {mode} (R=1 r=0.05 B=0.7)"
+
+
+# ---------------------------------------------------------------------------------------------------------------- mode 2
+def test_mode2_example(tmp_path):
+    """gap_global_abpoa::exec + gaf_of_gap_abpoa + band_ampl_enough (the headline mode): example reads, default band and -b 50"""
+    fa_text = open(os.path.join(EXAMPLE, "reads.fa")).read()
+    gfa_text = open(os.path.join(EXAMPLE, "graph.gfa")).read()
+    fa = tmp_path / "r.fa"
+    fa.write_text("\n".join(fa_text.splitlines()[:12]) + "\n")
+    for kw, extra in (({}, []), ({"extra_b": 50}, ["-b", "50"]), ({"gap_open": 10, "gap_ext": 1}, ["-O", "10", "-E", "1"])):
+        got = pyref.run_mode2(fa.read_text(), gfa_text, **kw)
+        assert got == _oracle(2, str(fa), os.path.join(EXAMPLE, "graph.gfa"), extra), extra
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_mode2_random_small_graphs(block, tmp_path):
+    for seed in range(3000 + 25 * block, 3025 + 25 * block):
+        rng = np.random.default_rng(seed)
+        g = synth.make_graph(int(rng.integers(60, 400)), 3, seed=seed, mean_seg=int(rng.integers(3, 12)), p_snp=0.25, p_indel=0.15)
+        reads = synth.make_reads(g, 2, int(rng.integers(10, 120)), err=float(rng.choice([0.0, 0.05, 0.2])), seed=seed + 1)
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        b, f = int(rng.integers(0, 6)), float(rng.choice([0.0, 0.01, 0.1, 0.5]))
+        rc, exp, err = oracle_lib.run_cli(["-m", "2", "-b", str(b), "-f", str(f), str(fa), str(gfa)])
+        try:
+            got = pyref.run_mode2(fa.read_text(), gfa.read_text(), extra_b=b, extra_f=f)
+        except RuntimeError as ex:   # inputs on which the reference panics (empty band row, the 'u' trace code)
+            assert rc == 101, f"seed {seed}: pyref says the reference panics ({ex}), the oracle exits with {rc}"
+            continue
+        assert rc == 0, err
+        assert got == exp, f"seed {seed} -b {b} -f {f}:\n PY : {got[:400]}\n C++: {exp[:400]}"
