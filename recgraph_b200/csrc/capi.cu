@@ -680,7 +680,8 @@ static int align_poa(rg_ctx* c, int mode) {
     out_runs_cap = std::max<size_t>(out_runs_cap, 1024);
     const size_t budget = budget_all - out_runs_cap * sizeof(rg_run);
     const uint32_t reads8 = (uint32_t)((c->n_reads + 7) / 8 * 8);
-    uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * blocks_per_sm * 8, reads8);
+    const uint32_t wpb = blk2 ? (uint32_t)gap_blk_warps_per_block() : 8u;   // warps (= slots) per CTA of the kernel that will run
+    uint32_t slots = std::min<uint32_t>((uint32_t)c->sms * blocks_per_sm * wpb, reads8);
     for (int attempt = 0; attempt < 8; attempt++) {
         // Reads in flight are limited by trace memory: prefer the full n x L trace per slot (never overflows),
         // shrink the number of slots down to one block per SM before shrinking the trace.
@@ -736,7 +737,7 @@ static int align_poa(rg_ctx* c, int mode) {
         cudaEventRecord(c->ev0, c->stream);
         if (blkC && trace_cap < full) return c->fail(RG_ERR_NOMEM, "not enough device memory for the blocked kernel's trace");
         int rc = lin ? launch_poa_lin(mode, blkC, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), c->stream)
-                 : blkC ? launch_gap_global_blk(blkC, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), c->stream)
+                 : blkC ? launch_gap_global_blk(blkC, c->dg, c->ds, ws, b, trace_bytes, (int)((slots + wpb - 1) / wpb), c->stream)
                       : launch_poa(mode, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), ws_cols, c->stream);
         cudaEventRecord(c->ev1, c->stream);
         if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("alignment kernel");

@@ -198,6 +198,7 @@ int launch_poa(int mode, const DevGraph& g, const DevScoring& s, const PoaWorksp
 // register-blocked mode-2 kernel (poa_gap_blk.cu)
 int gap_blk_cols(uint32_t Lmax);
 int gap_blk_blocks_per_sm(int C, int trace_bytes, int* nb);
+int gap_blk_warps_per_block();
 int launch_gap_global_blk(int C, const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b,
                           int trace_bytes, int blocks, void* stream);
 // modes 0 / 1 / 3 (poa_lin.cu)

@@ -23,13 +23,21 @@ namespace rg {
 // ---- trace layout of this kernel: four bit planes per row (instead of one code byte per cell)
 //   plane 0 (T): the cell's m is max(d, x), i.e. the move is not vertical     plane 2 (X): path_x flag (x extends)
 //   plane 1 (D): d >= x, i.e. diagonal rather than horizontal when T is set   plane 3 (Y): path_y flag (y extends)
-// Lane t owns the 4*C bits of its C columns: bit p*C + k = plane p of column t*C + k, stored in NW = max(1, C/8)
-// words at word offset row * 32*NW + t*NW. Rows that gather several predecessors additionally keep 2*SB slot planes
+// Lane t owns the 4*C bits of its C columns: bit p*C + PlaneFmt<C>::perm(k) = plane p of column t*C + k, stored in
+// NW = max(1, C/8) words at word offset row * 32*NW + t*NW. The bit order inside a plane is the one the packed row
+// produces for free: the flag words of two consecutive cell pairs go through ONE byte permute with sign replication
+// (a byte of 0xff / 0x00 per cell) and one AND-OR, so bit b of byte j collects pair 2b + (j & 1), half j >> 1. Rows that gather several predecessors additionally keep 2*SB slot planes
 // (diagonal source, vertical source) in a side array indexed by DevGraph::nwp_ord.
 template <int C>
 struct PlaneFmt {
     static constexpr int NW = (C >= 8) ? C / 8 : 1;
     static constexpr int ROWW = 32 * NW;
+    static constexpr int H = C / 2, G = C / 4;   // cells per half, bits per group (4 groups: lo-even, lo-odd, hi-even, hi-odd)
+    // plane bit of column k of a lane's block
+    __host__ __device__ static constexpr unsigned perm(unsigned k) {
+        const unsigned half = k >= (unsigned)H ? 1u : 0u, kk = k - half * H;
+        return (2u * half + (kk & 1u)) * G + (kk >> 1);
+    }
 };
 
 template <int C>
@@ -52,10 +60,11 @@ __device__ __forceinline__ void planes_from_codes(const unsigned (&code)[C], uns
 #pragma unroll
     for (int k = 0; k < C; k++) {
         const unsigned cd = code[k], dir = cd & 3u;
-        P[0] |= (dir != (unsigned)DIR_U ? 1u : 0u) << k;
-        P[1] |= (dir == (unsigned)DIR_D ? 1u : 0u) << k;
-        P[2] |= ((cd >> 2) & 1u) << k;
-        P[3] |= ((cd >> 3) & 1u) << k;
+        const unsigned pk = PlaneFmt<C>::perm((unsigned)k);
+        P[0] |= (dir != (unsigned)DIR_U ? 1u : 0u) << pk;
+        P[1] |= (dir == (unsigned)DIR_D ? 1u : 0u) << pk;
+        P[2] |= ((cd >> 2) & 1u) << pk;
+        P[3] |= ((cd >> 3) & 1u) << pk;
 #pragma unroll
         for (int q = 0; q < SB; q++) {
             SD[q] |= ((cd >> (4 + q)) & 1u) << k;
@@ -73,7 +82,7 @@ struct PlaneTrace {
     const uint32_t* nwp_ord;
     __device__ __forceinline__ uint32_t code(int64_t rr, int64_t cc) const {
         constexpr int NW = PlaneFmt<C>::NW;
-        const uint32_t ln = (uint32_t)cc / C, k = (uint32_t)cc % C;
+        const uint32_t ln = (uint32_t)cc / C, kc = (uint32_t)cc % C, k = PlaneFmt<C>::perm(kc);
         const uint32_t* w = planes + (size_t)rr * PlaneFmt<C>::ROWW + ln * NW;
         unsigned t, d, x, y;
         if constexpr (C == 32) {
@@ -93,8 +102,8 @@ struct PlaneTrace {
             const uint32_t* sp = side + (size_t)nwp_ord[rr] * (2 * SB * 32) + ln;
 #pragma unroll
             for (int q = 0; q < SB; q++) {
-                cd |= ((sp[q * 32] >> k) & 1u) << (4 + q);
-                cd |= ((sp[(SB + q) * 32] >> k) & 1u) << (4 + SB + q);
+                cd |= ((sp[q * 32] >> kc) & 1u) << (4 + q);               // the slot planes keep the column order
+                cd |= ((sp[(SB + q) * 32] >> kc) & 1u) << (4 + SB + q);
             }
         }
         return cd;
@@ -130,10 +139,10 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int (&v)[C]) {
 #define PK_ENTER_LO (-12000)  // a row may enter the packed form when its real cells lie in base16 + [LO, HI]
 #define PK_ENTER_HI (1000)
 #define PK_GATHER_LO (-20000)  // predecessor rows gathered while packed (base16 may be up to ~4000 stale)
-#define PK_GATHER_HI (3000)   // + 32 rows of upward drift (30 per row) = 3960: still 32768 below the lowest padding value
+#define PK_GATHER_HI (3000)   // + 32 rows of upward drift (60 per row: 30 of score, 30 of the moving base) = 4920: still 32768 below the lowest padding value
 #define PK_SPREAD (14000)     // guard: leave the packed form when a real cell falls this far below the row maximum
 #define PK_REBASE (2000)      // guard: re-base when the row maximum drifted this far from base16
-#define PK_GUARD_ROWS 32      // rows between two guards; scores move by at most 60 per row (see en16)
+#define PK_GUARD_ROWS 32      // rows between two guards; fields move by at most 90 per row (60 of score, see en16, + |e| of the moving base)
 __device__ __forceinline__ unsigned pk16(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(unsigned v) { return (int)v >> 16; }
@@ -143,8 +152,15 @@ __device__ __forceinline__ unsigned add2(int c) { return (unsigned)c * 65537u; }
 #ifndef RG_BLK_CTAS
 #define RG_BLK_CTAS 1
 #endif
+// One CTA of 12 warps per SM (170 registers per thread): the packed row body is spill-free at that size and three warps
+// per scheduler hide its fixed-latency dependencies better than two (8 warps x 255 registers: 449 vs 484 ms per 3 552
+// reads; 16 warps x 128 registers spill 2.7 KB per thread and are slower than either).
+#ifndef RG_BLK_WARPS
+#define RG_BLK_WARPS 12
+#endif
+constexpr int BLK_WARPS = RG_BLK_WARPS;   // warps (= reads in flight) per CTA of this kernel
 template <int C, int SB, bool SIMPLE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
+__global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
     k_gap_global_blk(DevGraph g, DevScoring sc, PoaWorkspace ws, PoaBatch b) {
     static_assert(C % 4 == 0, "C must be a multiple of 4");
     constexpr int STRIDE = 32 * C;
@@ -152,7 +168,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
     __shared__ int32_t s_sc[48];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const uint32_t slot = blockIdx.x * WARPS_PER_BLOCK + wib;
+    const uint32_t slot = blockIdx.x * BLK_WARPS + wib;
     if (threadIdx.x < 48) s_sc[threadIdx.x] = (&sc.sc[0][0])[threadIdx.x];
     __syncthreads();
     if (slot >= ws.slots) return;
@@ -253,16 +269,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                     // column can never be the row maximum and needs no band mask in the packed path
                     const int sl = (cbase + r >= L) ? PADSUB16 : ((bse < 4 && rl == bse) ? s_match : s_mis);
                     const int sh = (cbase + r + H >= L) ? PADSUB16 : ((bse < 4 && rh == bse) ? s_match : s_mis);
-                    subtab[(bse * H + r) * 32 + lane] = (unsigned)(sh * 65536 + sl);  // addend: sl on the lo field, sh on the hi field
+                    // addend: sl on the lo field, sh on the hi field; - e because every packed row moves base16 by e (row16)
+                    subtab[(bse * H + r) * 32 + lane] = (unsigned)((sh - e) * 65536 + (sl - e));
                 }
             }
             __syncwarp();
         }
-        bool rep16 = false;   // the previous row is held packed (A[r], B[r] for r < H hold m and y + e relative to base16)
+        bool rep16 = false;   // the previous row is held packed (A[r], B[r] for r < H hold m and y relative to base16)
         int base16 = 0, rows16 = 0, prev_tmax = 0;
         const unsigned C1F = pk16(e + max(o, 0), e + max(o, 0));  // per-field operand of VIADDMNMX.U16x2
-        const unsigned C1A = add2(e + max(o, 0)), C2A = add2(o + e), EEA = add2(e);   // 32-bit addends
-        const unsigned KY = BIAS2 - add2(1), KX = BIAS2 - add2(o + 1);
+        const unsigned C2A = add2(o + e);   // 32-bit addend
+        const unsigned OF = pk16(o, o);     // per-field operand of VIADDMNMX.U16x2
+        const unsigned KX = BIAS2 - add2(o + 1);
         // The integer ALU pipe issues one warp instruction every two clocks and so does the multiply-add pipe. The row
         // body is ALU-bound (maxima, shifts, logic), so the differences behind the flags are written as multiply-adds
         // with multipliers the compiler cannot fold (ws.use16 is 1 whenever this code runs): they issue as IMAD.
@@ -289,24 +307,33 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
         bool have_planes = false;
         int bestv = NEG_INF;
         int bcol = 0;
+        unsigned bp16 = 0;           // packed row: maxima of my lo / hi cells (biased fields)
         // Packed row (two cells per register) for a row whose band and whose predecessor row(s) span the whole read.
         // A / B hold the (gathered) predecessor row on entry and this row on exit; leaves P, bestv, bcol.
         auto row16 = [&]() {
             const unsigned* tab = subtab + (size_t)li * H * 32 + lane;
+            // The row is computed relative to base16 + e: y = max(m' + o, y') + e of the previous row's fields m', y' is then
+            // max(m' + o, y') as it stands, and the e is folded into the substitution addends — no per-cell "+ e" at all.
+            base16 += e;
             unsigned D16[H], YV[H];
-            // flag accumulators: bit r <- lo cell r, bit 16 + r <- hi cell r
-            unsigned fy = 0, fd = 0, ft = 0, fx = 0, fb = 0;
-            auto flag = [](unsigned& acc, unsigned f, int r) {
-                acc |= (f >> (15 - r)) & ((1u << r) | (1u << (16 + r)));
+            // Flag accumulators in the plane bit order (PlaneFmt::perm). A flag is bit 15 / bit 31 of a difference word;
+            // the words of pairs r, r + 1 (r even) become one byte of 0xff / 0x00 per cell with one PRMT (sign replication:
+            // bytes lo r, lo r+1, hi r, hi r+1) and enter bit r / 2 of the four byte groups with one AND-OR.
+            unsigned fy = 0, fd = 0, ft = 0, fx = 0;
+            auto flag2 = [](unsigned& acc, unsigned f_even, unsigned f_odd, int r_even) {
+                unsigned w;   // PTX prmt: bit 3 of a selector nibble replicates the byte's sign (__byte_perm drops that bit)
+                asm("prmt.b32 %0, %1, %2, 0xfbd9;" : "=r"(w) : "r"(f_even), "r"(f_odd));
+                acc |= w & (0x01010101u << (r_even / 2));
             };
             // ---- pass A: y and d of both halves of every pair (descending: A[r-1] is still the previous row)
             const unsigned up = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
             const unsigned dg0 = __byte_perm(up, (unsigned)A[H - 1], 0x5432);  // lo <- cell cbase-1, hi <- cell H-1
+            unsigned fyo = 0;
 #pragma unroll
             for (int r = H - 1; r >= 0; r--) {
-                const unsigned um2 = (unsigned)A[r] + C2A;                    // m + o + e
-                const unsigned yv = __vmaxu2(um2, (unsigned)B[r]);            // max(m + o, y) + e
-                flag(fy, (unsigned)B[r] * ONE + (um2 * NEG1 + KY), r);        // Y: y > m + o   (B + KY - um2)
+                const unsigned yv = __viaddmax_u16x2((unsigned)A[r], OF, (unsigned)B[r]);   // max(m + o, y) (+ e: the base moved)
+                const unsigned fyr = (unsigned)B[r] + KX - (unsigned)A[r];                  // Y: y > m + o
+                if (r & 1) fyo = fyr; else flag2(fy, fyr, fyo, r);
                 const unsigned dd = ((r == 0) ? dg0 : (unsigned)A[r - 1]) + tab[r * 32];
                 D16[r] = dd;
                 YV[r] = yv;
@@ -320,19 +347,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
             }
             // ---- pass B: two in-lane chains (lo cells 0..H-1, hi cells H..C-1); generator of cell c is h[c-1] + c2.
             // Only the value leaving my last column is needed here (for the cross-lane scan); pass C runs the chain again
-            // from the true incoming value instead of keeping 16 intermediate registers.
+            // from the true incoming value instead of keeping 16 intermediate registers. The chain runs on x - c2, whose
+            // generator is h[c-1] itself (one instruction per pair).
             const unsigned hup = __shfl_up_sync(FULL, (unsigned)A[H - 1], 1);
-            unsigned g0 = __byte_perm(hup, (unsigned)A[H - 1], 0x5432) + C2A;
+            const unsigned g0s = __byte_perm(hup, (unsigned)A[H - 1], 0x5432);
+            unsigned g0 = g0s + C2A;
             if (lane == 0) g0 = (g0 & 0xffff0000u) | ((unsigned)(o + e * (best_p + 1) - base16 + 32768) & 0xffffu);  // seed, :88
             unsigned xe;
             {
-                unsigned xl = FLB | (FLB << 16);
+                unsigned xl = (FLB | (FLB << 16)) - C2A;
 #pragma unroll
-                for (int r = 0; r < H; r++) {
-                    const unsigned gen = (r == 0) ? g0 : (unsigned)A[r - 1] + C2A;
-                    xl = __viaddmax_u16x2(xl, C1F, gen);
-                }
-                xe = xl;
+                for (int r = 0; r < H; r++) xl = __viaddmax_u16x2(xl, C1F, (r == 0) ? g0 - C2A : (unsigned)A[r - 1]);
+                xe = xl + C2A;
             }
             // cross-lane max-plus scan on the in-lane value of my last column (biased integers)
             const int c1s = e + max(o, 0);
@@ -349,6 +375,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
             // ---- pass C
             unsigned bestp = FLB | (FLB << 16);
             unsigned hprev = 0;
+            unsigned fde = 0, fte = 0, fxe = 0;
 #pragma unroll
             for (int r = 0; r < H; r++) {
                 const unsigned gen = (r == 0) ? g0 : hprev + C2A;
@@ -356,25 +383,46 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                 xl = __viaddmax_u16x2(xl, C1F, gen);
                 const unsigned x = xl;
                 const unsigned t = __vmaxu2(D16[r], x);
-                flag(fd, D16[r] * ONE + (x * NEG1 + BIAS2), r);      // D: dd >= x
+                const unsigned fdr = D16[r] * ONE + (x * NEG1 + BIAS2);      // D: dd >= x
                 const unsigned m = __vmaxu2(t, YV[r]);
-                flag(ft, t * ONE + (YV[r] * NEG1 + BIAS2), r);       // T: max(dd, x) >= y
-                flag(fx, m * NEG1 + (x * ONE + KX), r);              // x > m + o
-                flag(fb, m * ONE + (bestp * NEG1 + BIAS2), r);       // m >= best so far: right-most maximum
+                const unsigned ftr = t * ONE + (YV[r] * NEG1 + BIAS2);       // T: max(dd, x) >= y
+                const unsigned fxr = m * NEG1 + (x * ONE + KX);              // x > m + o
+                if (r & 1) {
+                    flag2(fd, fde, fdr, r - 1);
+                    flag2(ft, fte, ftr, r - 1);
+                    flag2(fx, fxe, fxr, r - 1);
+                } else {
+                    fde = fdr, fte = ftr, fxe = fxr;
+                }
                 bestp = __vmaxu2(m, bestp);
                 A[r] = (int)m;
-                B[r] = (int)(YV[r] + EEA);
+                B[r] = (int)YV[r];
             }
-            if constexpr (H < 16) {  // accumulators are laid out for 16 pairs: close the gap between the halves
-                auto squeeze = [](unsigned v) { return (v & ((1u << H) - 1u)) | ((v >> 16) << H); };
-                fy = squeeze(fy), fd = squeeze(fd), ft = squeeze(ft), fx = squeeze(fx), fb = squeeze(fb);
+            if constexpr (H < 16) {  // the byte groups hold G = H / 2 bits each: close the gaps
+                constexpr int G = H / 2;
+                auto squeeze = [](unsigned v) {
+                    constexpr unsigned gm = (1u << G) - 1u;
+                    return (v & gm) | (((v >> 8) & gm) << G) | (((v >> 16) & gm) << (2 * G)) | (((v >> 24) & gm) << (3 * G));
+                };
+                fy = squeeze(fy), fd = squeeze(fd), ft = squeeze(ft), fx = squeeze(fx);
             }
-            unsigned carry = __shfl_up_sync(FULL, fx >> (C - 1), 1) & 1u;   // fx bit k: x[c] > m[c] + o of my column k
+            // path_x of column c is the flag of column c - 1 (gap_global_abpoa.rs:358-364): move every bit to the plane
+            // position of the next column (even cell -> odd cell of its pair group: + G; odd cell -> next even: - G + 1;
+            // last cell of the lo half -> first of the hi half: + 1; last cell of the block -> next lane)
+            unsigned carry = __shfl_up_sync(FULL, fx >> (C - 1), 1) & 1u;   // fx bit of column k: x[c] > m[c] + o
             if (lane == 0) carry = 0;
+            {
+                constexpr int G = C / 4;
+                constexpr unsigned gm = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
+                constexpr unsigned EVEN = gm | (gm << (2 * G));
+                constexpr unsigned ODDIN = ((gm >> 1) << G) | ((gm >> 1) << (3 * G));   // odd cells except the last of each half
+                constexpr unsigned LOLAST = 1u << (2 * G - 1);
+                unsigned nx = ((fx & EVEN) << G) | ((fx & LOLAST) << 1) | carry;
+                if constexpr (G > 1) nx |= (fx & ODDIN) >> (G - 1);
+                P[2] = nx;
+            }
             P[0] = ft;
             P[1] = fd;
-            P[2] = (fx << 1) | carry;            // path_x of column c: x[c-1] > m[c-1] + o (gap_global_abpoa.rs:358-364)
-            if constexpr (C < 32) P[2] &= (1u << C) - 1u;
             P[3] = fy;
             if (lane == 0) {                     // first-column cell: vertical move to the smallest predecessor, no flags
                 P[0] &= ~1u;
@@ -383,17 +431,28 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                 P[3] &= ~1u;
             }
             have_planes = true;
-            {
-                const int blo = (int)(bestp & 0xffffu), bhi = (int)(bestp >> 16);
-                const unsigned fbl = fb & ((1u << H) - 1u), fbh = fb >> H;
-                if (bhi >= blo) {
-                    bestv = base16 + bhi - 32768;
-                    bcol = cbase + H + 31 - __clz(fbh | 1u);
-                } else {
-                    bestv = base16 + blo - 32768;
-                    bcol = cbase + 31 - __clz(fbl | 1u);
-                }
+            bp16 = bestp;
+            bestv = base16 + (int)max(bestp & 0xffffu, bestp >> 16) - 32768;
+        };
+        // right-most column of my block that holds my maximum of the packed row just computed (A = its m values)
+        auto bcol16 = [&]() {
+            const unsigned blo = bp16 & 0xffffu, bhi = bp16 >> 16;
+            const bool hi = bhi >= blo;
+            const unsigned tgt = hi ? bhi : blo;
+            int pos = 0;
+#pragma unroll
+            for (int r = 0; r < H; r++) {
+                const unsigned f = hi ? ((unsigned)A[r] >> 16) : ((unsigned)A[r] & 0xffffu);
+                if (f == tgt) pos = r;
             }
+            bcol = cbase + (hi ? H : 0) + pos;
+        };
+        // fy in column order (the slot planes of a gathered row are kept in column order)
+        auto unperm = [](unsigned v) {
+            unsigned out = 0;
+#pragma unroll
+            for (int k = 0; k < C; k++) out |= ((v >> PlaneFmt<C>::perm((unsigned)k)) & 1u) << k;
+            return out;
         };
 
         // Packed gather of the predecessor rows of a segment start (all of them span the whole read, none is row 0):
@@ -413,10 +472,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
             auto take = [&](int r, int vml, int vmh, int vyl, int vyh) {
                 const int cl = cbase + r, ch = cbase + r + H;
                 const bool rl = cl < L, rh = ch < L;
-                ok = ok && (!rl || ((unsigned)(vml - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO) && (cl == 0 || (unsigned)(vyl + e - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO))));
-                ok = ok && (!rh || ((unsigned)(vmh - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO) && (unsigned)(vyh + e - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO)));
+                ok = ok && (!rl || ((unsigned)(vml - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO) && (cl == 0 || (unsigned)(vyl - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO))));
+                ok = ok && (!rh || ((unsigned)(vmh - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO) && (unsigned)(vyh - lo_ok) <= (unsigned)(PK_GATHER_HI - PK_GATHER_LO)));
                 const unsigned nm = pk16(rl ? vml - base16 : FLOOR16, rh ? vmh - base16 : FLOOR16);
-                const unsigned ny = pk16((rl && cl != 0) ? vyl + e - base16 : FLOOR16, rh ? vyh + e - base16 : FLOOR16);
+                const unsigned ny = pk16((rl && cl != 0) ? vyl - base16 : FLOOR16, rh ? vyh - base16 : FLOOR16);
                 if (q == 0) {
                     A[r] = (int)nm;
                     B[r] = (int)ny;
@@ -466,6 +525,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
         // is the y-winner where y extends and the m-winner where it opens; the first-column cell goes to the smallest
         // predecessor (slot mps)
         auto slots16 = [&](unsigned mps, unsigned (&SD)[SB], unsigned (&SU)[SB]) {
+            const unsigned py = unperm(P[3]);
 #pragma unroll
             for (int bq = 0; bq < SB; bq++) {
                 const unsigned mm = mm_lo[bq] | (mm_hi[bq] << H), ym = ym_lo[bq] | (ym_hi[bq] << H);
@@ -473,7 +533,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                 if (lane == 0) cin = 0;
                 SD[bq] = (mm << 1) | cin;
                 if constexpr (C < 32) SD[bq] &= (1u << C) - 1u;
-                SU[bq] = (P[3] & ym) | (~P[3] & mm);
+                SU[bq] = (py & ym) | (~py & mm);
                 if (lane == 0) SU[bq] = (SU[bq] & ~1u) | ((mps >> bq) & 1u);
             }
         };
@@ -492,9 +552,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                 const unsigned pa = (unsigned)A[r] ^ BIAS2, py = (unsigned)B[r] ^ BIAS2;
                 const int cl = cbase + r, ch = cbase + r + H;
                 VM[r + H] = (ch < L) ? base16 + hi16(pa) : NEG_INF;
-                VY[r + H] = (ch < L) ? base16 + hi16(py) - e : NEG_INF;
+                VY[r + H] = (ch < L) ? base16 + hi16(py) : NEG_INF;
                 VM[r] = (cl < L) ? base16 + lo16(pa) : NEG_INF;
-                VY[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py) - e) : NEG_INF;
+                VY[r] = (cl < L) ? ((cl == 0) ? 0 : base16 + lo16(py)) : NEG_INF;
             }
         };
         // the ring keeps 32-bit rows: unpack on the way out
@@ -521,7 +581,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
             const int rel = tmax - base16;
             if (lm - rel < -PK_SPREAD) return true;
             if (rel > PK_REBASE || rel < -PK_REBASE) {
-                // |rel| <= PK_REBASE + PK_GUARD_ROWS * 60: no field can leave its half; padding is pulled back to the floor
+                // |rel| <= PK_REBASE + PK_GUARD_ROWS * 90: no field can leave its half; padding is pulled back to the floor
                 const unsigned dl = add2(-rel), fl = (unsigned)(FLOOR16 + 32768) * 65537u;
 #pragma unroll
                 for (int r = 0; r < H; r++) {
@@ -570,7 +630,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                     {   // the first-column seed o + e * (best_p + 1) (:88) follows the ROW INDEX of the smallest predecessor,
                         // not the scores: after a long skip edge it can sit thousands above / below the row. Outside the
                         // packed window the row is done by the exact 32-bit path (the dispatcher re-checks and unpacks).
-                        const int sd = o + e * (rv.y + 1) - base16;
+                        const int sd = o + e * (rv.y + 1) - (base16 + e);   // row16 moves the base by e first
                         if (sd < PK_GATHER_LO || sd > PK_GATHER_HI) break;
                     }
                     if (gat && !gather16((uint32_t)rv.z, rb >> 24)) {
@@ -583,7 +643,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                     row16();
                     const int tmax = __reduce_max_sync(FULL, bestv);
                     const unsigned eq = __ballot_sync(FULL, bestv == tmax);
-                    const uint32_t row_bsp = (uint32_t)__shfl_sync(FULL, bcol, 31 - __clz(eq));
+                    // Column of the right-most row maximum (gap_global_abpoa.rs:198-203). It only feeds the bands of the rows
+                    // that have this row as predecessor (utils.rs:17-66): their left edge is min(bsp + 1, L - r - bta) and
+                    // their right edge min(L, max(bsp + 1, ..) + bta). Every such row j has r_j >= r_i - 1 (set_r_values,
+                    // utils.rs:106-126), so with r_i - 1 >= L - bta its left edge is 0 whatever bsp is, and any lower bound
+                    // lb of bsp with lb + 1 + bta >= L gives the right edge L exactly like bsp itself. The start of the
+                    // half block that holds the maximum is such a bound for most rows; the exact column is searched
+                    // otherwise.
+                    uint32_t row_bsp = (uint32_t)__shfl_sync(FULL, cbase + (((bp16 >> 16) >= (bp16 & 0xffffu)) ? H : 0), 31 - __clz(eq));
+                    if (!(rv.x >= 1 && rv.x - 1 >= L - bta && (int)row_bsp + 1 + bta >= L)) {
+                        bcol16();
+                        row_bsp = (uint32_t)__shfl_sync(FULL, bcol, 31 - __clz(eq));
+                    }
                     store_planes<C>(planes + (size_t)i * PlaneFmt<C>::ROWW + lane * NW, P);
                     if (lane == 0) {
                         RowMeta rm;
@@ -673,7 +744,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
             const bool plain = left == 0 && prev_left == 0 && right <= prev_right;
 
             // first-column seed of a packed row (see the steady loop): must fit the packed window around the base the row will use
-            const int sd16 = o + e * (best_p + 1) - (rep16 ? base16 : prev_tmax);
+            const int sd16 = o + e * (best_p + 1) - ((rep16 ? base16 : prev_tmax) + e);
             const bool seed_ok = sd16 >= PK_GATHER_LO && sd16 <= PK_GATHER_HI;
             bool f16 = en16 && seed_ok && fast && plain && right == (uint32_t)L && prev_right == (uint32_t)L;
             // Packed segment-start row: every predecessor row (none of them row 0) and this row span the whole read, so
@@ -700,7 +771,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                     const int c = cbase + k;
                     if (c < L) {
                         ok = ok && (A[k] - prev_tmax >= PK_ENTER_LO) && (A[k] - prev_tmax <= PK_ENTER_HI);
-                        if (c != 0) ok = ok && (B[k] + e - prev_tmax >= PK_ENTER_LO) && (B[k] + e - prev_tmax <= PK_ENTER_HI);
+                        if (c != 0) ok = ok && (B[k] - prev_tmax >= PK_ENTER_LO) && (B[k] - prev_tmax <= PK_ENTER_HI);
                     }
                 }
                 if (__all_sync(FULL, ok)) {
@@ -709,7 +780,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
                     for (int r = 0; r < H; r++) {
                         const int cl = cbase + r, ch = cbase + r + H;
                         const int al = (cl < L) ? A[r] - base16 : FLOOR16, ah = (ch < L) ? A[r + H] - base16 : FLOOR16;
-                        const int yl = (cl < L && cl != 0) ? B[r] + e - base16 : FLOOR16, yh = (ch < L) ? B[r + H] + e - base16 : FLOOR16;
+                        const int yl = (cl < L && cl != 0) ? B[r] - base16 : FLOOR16, yh = (ch < L) ? B[r + H] - base16 : FLOOR16;
                         A[r] = (int)pk16b(al, ah);
                         B[r] = (int)pk16b(yl, yh);
                     }
@@ -836,12 +907,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RG_BLK_CTAS)
             };
             if (g16) {
                 row16();
+                bcol16();
                 slots16(mps, SD, SU);
 #ifdef RG_ROWSTATS
                 st_kind = 1;
 #endif
             } else if (f16) {
                 row16();
+                bcol16();
 #ifdef RG_ROWSTATS
                 st_kind = 0;
 #endif
@@ -1187,20 +1260,20 @@ template <int C>
 static int launch_c(const DevGraph& g, const DevScoring& s, const PoaWorkspace& ws, const PoaBatch& b, int trace_bytes,
                     int blocks, cudaStream_t st) {
     const bool simple = simple_scoring(s);
-    const size_t smem = (size_t)WARPS_PER_BLOCK * 5 * (C / 2) * 32 * sizeof(unsigned);
+    const size_t smem = (size_t)BLK_WARPS * 5 * (C / 2) * 32 * sizeof(unsigned);
     const void* k = trace_bytes == 1 ? (simple ? (const void*)k_gap_global_blk<C, 2, true> : (const void*)k_gap_global_blk<C, 2, false>)
                                      : (simple ? (const void*)k_gap_global_blk<C, 6, true> : (const void*)k_gap_global_blk<C, 6, false>);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     if (trace_bytes == 1) {
         if (simple)
-            k_gap_global_blk<C, 2, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, 2, true><<<blocks, BLK_WARPS * 32, smem, st>>>(g, s, ws, b);
         else
-            k_gap_global_blk<C, 2, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, 2, false><<<blocks, BLK_WARPS * 32, smem, st>>>(g, s, ws, b);
     } else {
         if (simple)
-            k_gap_global_blk<C, 6, true><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, 6, true><<<blocks, BLK_WARPS * 32, smem, st>>>(g, s, ws, b);
         else
-            k_gap_global_blk<C, 6, false><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(g, s, ws, b);
+            k_gap_global_blk<C, 6, false><<<blocks, BLK_WARPS * 32, smem, st>>>(g, s, ws, b);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1220,10 +1293,11 @@ int launch_gap_global_blk(int C, const DevGraph& g, const DevScoring& s, const P
 template <int C>
 static int occ_c(int trace_bytes, int* nb) {
     const void* k = trace_bytes == 1 ? (const void*)k_gap_global_blk<C, 2, true> : (const void*)k_gap_global_blk<C, 6, true>;
-    const size_t smem = (size_t)WARPS_PER_BLOCK * 5 * (C / 2) * 32 * sizeof(unsigned);
+    const size_t smem = (size_t)BLK_WARPS * 5 * (C / 2) * 32 * sizeof(unsigned);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, WARPS_PER_BLOCK * 32, smem) == cudaSuccess ? 0 : -1;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k, BLK_WARPS * 32, smem) == cudaSuccess ? 0 : -1;
 }
+int gap_blk_warps_per_block() { return BLK_WARPS; }
 int gap_blk_blocks_per_sm(int C, int trace_bytes, int* nb) {
     switch (C) {
         case 4: return occ_c<4>(trace_bytes, nb);

@@ -28,6 +28,12 @@ for _ in range(a.passes):
     print("kernel_ms, launches, cells:", al.kernel_stats())
 res = al.fetch()
 print("cells", sum(res.reads[i].cells for i in range(res.n_reads)))
+import hashlib
+h = hashlib.sha256()
+for i in range(res.n_reads):
+    r = res.reads[i]
+    h.update(repr((r.status, r.score, r.end_row, r.end_col, r.start_row, r.start_col, r.n_runs, r.cells)).encode())
+print("result checksum", h.hexdigest()[:16], "gaf sha", hashlib.sha256(al.format_gaf_all(a.mode, res, off).encode()).hexdigest()[:16])
 import numpy as np
 dp = np.array([res.reads[i].fen for i in range(res.n_reads)], dtype=np.float64)
 tb = np.array([res.reads[i].rsn for i in range(res.n_reads)], dtype=np.float64)
