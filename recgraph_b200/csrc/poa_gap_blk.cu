@@ -315,10 +315,12 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
             // The row is computed relative to base16 + e: y = max(m' + o, y') + e of the previous row's fields m', y' is then
             // max(m' + o, y') as it stands, and the e is folded into the substitution addends — no per-cell "+ e" at all.
             base16 += e;
-            unsigned D16[H], YV[H];
+            unsigned D16[H];   // B[r] becomes this row's y in pass A and stays
             // Flag accumulators in the plane bit order (PlaneFmt::perm). A flag is bit 15 / bit 31 of a difference word;
             // the words of pairs r, r + 1 (r even) become one byte of 0xff / 0x00 per cell with one PRMT (sign replication:
-            // bytes lo r, lo r+1, hi r, hi r+1) and enter bit r / 2 of the four byte groups with one AND-OR.
+            // bytes lo r, lo r+1, hi r, hi r+1) and enter bit r / 2 of the four byte groups with one AND-OR. (The same step as
+            // a multiply-add — a word of 0xff / 0x00 bytes times 0xfefefeff << q, the inverse of 255 modulo 2^32 — measured
+            // no faster: the row is bound by issue slots, not by one pipe.)
             unsigned fy = 0, fd = 0, ft = 0, fx = 0;
             auto flag2 = [](unsigned& acc, unsigned f_even, unsigned f_odd, int r_even) {
                 unsigned w;   // PTX prmt: bit 3 of a selector nibble replicates the byte's sign (__byte_perm drops that bit)
@@ -331,18 +333,18 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
             unsigned fyo = 0;
 #pragma unroll
             for (int r = H - 1; r >= 0; r--) {
-                const unsigned yv = __viaddmax_u16x2((unsigned)A[r], OF, (unsigned)B[r]);   // max(m + o, y) (+ e: the base moved)
                 const unsigned fyr = (unsigned)B[r] + KX - (unsigned)A[r];                  // Y: y > m + o
+                const unsigned yv = __viaddmax_u16x2((unsigned)A[r], OF, (unsigned)B[r]);   // max(m + o, y) (+ e: the base moved)
                 if (r & 1) fyo = fyr; else flag2(fy, fyr, fyo, r);
                 const unsigned dd = ((r == 0) ? dg0 : (unsigned)A[r - 1]) + tab[r * 32];
                 D16[r] = dd;
-                YV[r] = yv;
+                B[r] = (int)yv;
                 A[r] = (int)__vmaxu2(dd, yv);  // h
             }
             const unsigned FLB = (unsigned)(FLOOR16 + 32768);
             if (lane == 0) {  // first-column cell (gap_global_abpoa.rs:78-92): m = x only
                 D16[0] = (D16[0] & 0xffff0000u) | FLB;
-                YV[0] = (YV[0] & 0xffff0000u) | FLB;
+                B[0] = (int)(((unsigned)B[0] & 0xffff0000u) | FLB);
                 A[0] = (int)(((unsigned)A[0] & 0xffff0000u) | FLB);
             }
             // ---- pass B: two in-lane chains (lo cells 0..H-1, hi cells H..C-1); generator of cell c is h[c-1] + c2.
@@ -384,8 +386,8 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
                 const unsigned x = xl;
                 const unsigned t = __vmaxu2(D16[r], x);
                 const unsigned fdr = D16[r] * ONE + (x * NEG1 + BIAS2);      // D: dd >= x
-                const unsigned m = __vmaxu2(t, YV[r]);
-                const unsigned ftr = t * ONE + (YV[r] * NEG1 + BIAS2);       // T: max(dd, x) >= y
+                const unsigned m = __vmaxu2(t, (unsigned)B[r]);
+                const unsigned ftr = t * ONE + ((unsigned)B[r] * NEG1 + BIAS2);   // T: max(dd, x) >= y
                 const unsigned fxr = m * NEG1 + (x * ONE + KX);              // x > m + o
                 if (r & 1) {
                     flag2(fd, fde, fdr, r - 1);
@@ -394,9 +396,8 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
                 } else {
                     fde = fdr, fte = ftr, fxe = fxr;
                 }
-                bestp = __vmaxu2(m, bestp);
+                bestp = __vmaxu2(m, bestp);   // (pairs of these fuse into one three-input maximum)
                 A[r] = (int)m;
-                B[r] = (int)YV[r];
             }
             if constexpr (H < 16) {  // the byte groups hold G = H / 2 bits each: close the gaps
                 constexpr int G = H / 2;
