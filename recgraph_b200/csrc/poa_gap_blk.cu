@@ -602,6 +602,7 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
             // (32-bit rows, end-cell candidates, shifted bands, row 0 as predecessor) leaves the loop and goes through
             // the dispatcher below.
             if (rep16) {
+                bool full_next = false;   // the previous steady row proved that an in-segment successor has the band [0, L)
                 for (; i + 2 < n; i++) {
 #ifdef RG_ROWSTATS
                     const long long st_t1 = clock64();
@@ -625,9 +626,11 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
                         ms = pl + 1;
                         me = pr + 1;
                     }
-                    uint32_t lf, rt;
-                    band_for_row(ms, me, rv.x, L, bta, lf, rt);
-                    if (lf != 0 || rt != (uint32_t)L) break;
+                    if (gat || !full_next) {
+                        uint32_t lf, rt;
+                        band_for_row(ms, me, rv.x, L, bta, lf, rt);
+                        if (lf != 0 || rt != (uint32_t)L) break;
+                    }
                     {   // the first-column seed o + e * (best_p + 1) (:88) follows the ROW INDEX of the smallest predecessor,
                         // not the scores: after a long skip edge it can sit thousands above / below the row. Outside the
                         // packed window the row is done by the exact 32-bit path (the dispatcher re-checks and unpacks).
@@ -652,7 +655,8 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
                     // half block that holds the maximum is such a bound for most rows; the exact column is searched
                     // otherwise.
                     uint32_t row_bsp = (uint32_t)__shfl_sync(FULL, cbase + (((bp16 >> 16) >= (bp16 & 0xffffu)) ? H : 0), 31 - __clz(eq));
-                    if (!(rv.x >= 1 && rv.x - 1 >= L - bta && (int)row_bsp + 1 + bta >= L)) {
+                    full_next = rv.x >= 1 && rv.x - 1 >= L - bta && (int)row_bsp + 1 + bta >= L;   // (the successor's band too)
+                    if (!full_next) {
                         bcol16();
                         row_bsp = (uint32_t)__shfl_sync(FULL, bcol, 31 - __clz(eq));
                     }
