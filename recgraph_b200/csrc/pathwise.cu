@@ -8,14 +8,19 @@
 // restatement). The reverse pass of modes 8/9 (`rev_align`) is the same routine on the reverse graph, rows
 // descending, with the read reversed (column jj = L-1-j).
 //
-// One CTA per read. Scores live in an L2-resident ring of rows, layout [row][column][path] so that a warp whose
-// lanes are paths reads and writes 128-byte lines. Per row:
+// This is the PER-PATH kernel of round 1: every path of every row is computed. Since round 2 the product runs the
+// score-transport kernel (pathwise_tr_impl.cuh) for reads of up to 12 287 bases; this one is kept as its A/B reference
+// (RG_PW_V1=1, tools/ab_pathwise.py) and for longer reads.
+//
+// One CTA per read. Scores live in an L2-resident ring of rows, layout [row & RM][path][column] (path-major: a warp
+// works on ONE path, its lanes own 8 consecutive columns each and move 128-bit vectors). Per row:
 //   phase 1 (per group, all threads over column blocks): leader candidates, CTA-wide max-plus scan for the
 //           horizontal dependency, one move byte per column in shared memory;
-//   phase 2 (warps over column chunks, lanes = paths): members apply the move; each path also records its OWN
-//           arg-max (2 bits per path-cell, stored as two ballot bit-planes) — what build_alignment re-derives from
-//           the stored scores when it walks a path back. Modes 8/9 also keep, per (row, column), the arg-max over
-//           ALL path slots (non-member slots hold 0 as in the reference) for best_alignment.
+//   phase 2 (one warp per member path, lanes over columns): the path applies the leader's moves to its own scores
+//           (L runs inside a warp are resolved with one ballot + shuffle) and records its OWN arg-max (2 bits per
+//           path-cell, two bit planes) — what build_alignment re-derives from the stored scores when it walks a path
+//           back. Modes 8/9 also keep, per (row, column), the arg-max over ALL path slots (non-member slots hold 0 as
+//           in the reference) for best_alignment, collected with shared-memory atomics.
 // best_alignment (pathwise_alignment_recombination.rs:759-873) is an exact pruned reduction: a (column, node) pair
 // is expanded over the second node only if its upper bound m + max_w - R can still reach the running maximum;
 // the f32 arithmetic uses separately rounded mul / add / sub exactly as the reference, and the sequential

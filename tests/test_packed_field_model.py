@@ -2,7 +2,7 @@
 per 32-bit word as biased 16-bit fields. Checks, with numpy on uint32 words, the three facts the kernel relies on:
   1. a plain 32-bit add of `c * 65537` adds c to both fields while both results stay inside [0, 65535];
   2. bit 15 / bit 31 of `a + 0x80008000 - b` are the comparisons `a >= b` of the two fields whenever |a - b| < 32768;
-  3. with the kernel's bounds (real cells in [-21920, +3960], garbage never below -27000) every difference the row takes
+  3. with the kernel's bounds (real cells in [-21920, +4920], garbage never below -27000) every difference the row takes
      satisfies 2, and outside that window the trick does break (so the guards are needed, not decorative).
 No GPU, no product code: this is the design's arithmetic, not the implementation (the implementation is A/B-tested on
 the GPU against the 32-bit rows and the striped kernel)."""
@@ -10,7 +10,7 @@ import numpy as np
 
 BIAS = 32768
 K = np.uint32(0x80008000)
-REAL_LO, REAL_HI, GARBAGE_LO = -21920, 3960, -27000
+REAL_LO, REAL_HI, GARBAGE_LO = -21920, 4920, -27000
 
 
 def pack(lo, hi):
@@ -75,17 +75,96 @@ def test_outside_the_window_a_field_corrupts_its_neighbour():
     assert int(((f >> np.uint32(31)) & np.uint32(1))[0]) == 1
 
 
-def test_flag_words_land_in_natural_column_order():
-    # bit r <- lo cell of pair r, bit 16 + r <- hi cell: (f >> (15 - r)) & (1 << r | 1 << (16 + r)), as in the kernel
+def perm(k, C):
+    """PlaneFmt<C>::perm of csrc/poa_gap_blk.cu: plane bit of column k of a lane's block of C columns."""
+    H, G = C // 2, C // 4
+    half = 1 if k >= H else 0
+    kk = k - half * H
+    return (2 * half + (kk & 1)) * G + (kk >> 1)
+
+
+def prmt_sign_bytes(f_even, f_odd):
+    """prmt.b32 d, f_even, f_odd, 0xfbd9: bytes (f_even.b1, f_odd.b1, f_even.b3, f_odd.b3), each replaced by its sign bit
+    replicated over the byte (selector nibbles 9, d, b, f: bit 3 = replicate the msb)."""
+    out = np.zeros_like(f_even)
+    for j, (w, byte) in enumerate(((f_even, 1), (f_odd, 1), (f_even, 3), (f_odd, 3))):
+        sign = (w >> np.uint32(8 * byte + 7)) & np.uint32(1)
+        out |= (sign * np.uint32(0xFF)) << np.uint32(8 * j)
+    return out
+
+
+def packed_row_planes(lo, hi, C):
+    """Flag accumulation of row16: one byte permute per two cell pairs, AND-OR into bit r/2 of the four byte groups,
+    byte groups squeezed to G = C/4 bits for C < 32."""
+    H, G = C // 2, C // 4
+    n = lo.shape[0]
+    acc = np.zeros(n, dtype=np.uint32)
+    rng = np.random.default_rng(9)
+    f = []
+    for r in range(H):
+        garbage = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & ~np.uint32(0x80008000)
+        f.append(garbage | (lo[:, r] << np.uint32(15)) | (hi[:, r] << np.uint32(31)))
+    for r in range(0, H, 2):
+        acc |= prmt_sign_bytes(f[r], f[r + 1]) & np.uint32(0x01010101 << (r // 2))
+    if H < 16:
+        gm = np.uint32((1 << G) - 1)
+        acc = (acc & gm) | (((acc >> np.uint32(8)) & gm) << np.uint32(G)) | (((acc >> np.uint32(16)) & gm) << np.uint32(2 * G)) | \
+              (((acc >> np.uint32(24)) & gm) << np.uint32(3 * G))
+    return acc
+
+
+def test_plane_bit_order_is_a_permutation_and_the_byte_permute_produces_it():
     rng = np.random.default_rng(3)
-    lo = rng.integers(0, 2, (1000, 16)).astype(np.uint32)
-    hi = rng.integers(0, 2, (1000, 16)).astype(np.uint32)
-    acc = np.zeros(1000, dtype=np.uint32)
-    for r in range(16):
-        f = (lo[:, r] << np.uint32(15)) | (hi[:, r] << np.uint32(31)) | np.uint32(0x12340123)  # flags + garbage below them
-        f &= ~np.uint32(0x80008000) | (lo[:, r] << np.uint32(15)) | (hi[:, r] << np.uint32(31))
-        acc |= (f >> np.uint32(15 - r)) & np.uint32((1 << r) | (1 << (16 + r)))
-    want = np.zeros(1000, dtype=np.uint32)
-    for r in range(16):
-        want |= (lo[:, r] << np.uint32(r)) | (hi[:, r] << np.uint32(16 + r))
-    assert np.array_equal(acc, want)
+    for C in (4, 8, 16, 32):
+        H = C // 2
+        assert sorted(perm(k, C) for k in range(C)) == list(range(C))
+        assert perm(0, C) == 0 and perm(C - 1, C) == C - 1   # the first-column fix and the carry to the next lane rely on these
+        lo = rng.integers(0, 2, (2000, H)).astype(np.uint32)
+        hi = rng.integers(0, 2, (2000, H)).astype(np.uint32)
+        acc = packed_row_planes(lo, hi, C)
+        want = np.zeros(2000, dtype=np.uint32)
+        for r in range(H):
+            want |= (lo[:, r] << np.uint32(perm(r, C))) | (hi[:, r] << np.uint32(perm(r + H, C)))
+        assert np.array_equal(acc, want), C
+
+
+def test_path_x_shift_in_plane_order():
+    # path_x of column c is the x-flag of column c - 1: the kernel moves every bit to the plane position of the next column
+    rng = np.random.default_rng(4)
+    for C in (4, 8, 16, 32):
+        G = C // 4
+        gm = (1 << G) - 1 if G < 32 else 0xFFFFFFFF
+        EVEN = gm | (gm << (2 * G))
+        ODDIN = ((gm >> 1) << G) | ((gm >> 1) << (3 * G))
+        LOLAST = 1 << (2 * G - 1)
+        for _ in range(500):
+            flags = rng.integers(0, 2, C)
+            carry = int(rng.integers(0, 2))
+            fx = sum(int(flags[k]) << perm(k, C) for k in range(C))
+            nx = ((fx & EVEN) << G) | ((fx & LOLAST) << 1) | carry
+            if G > 1:
+                nx |= (fx & ODDIN) >> (G - 1)
+            nx &= (1 << C) - 1 if C < 32 else 0xFFFFFFFF
+            want = carry | sum(int(flags[k - 1]) << perm(k, C) for k in range(1, C))
+            assert nx == want, (C, flags, carry)
+            assert (fx >> (C - 1)) & 1 == flags[C - 1]   # what the next lane receives as its carry
+
+
+def test_moving_base_removes_the_per_cell_gap_extension_add():
+    # row16 computes a row relative to base + e: y = max(m' + o, y') + e of the previous row's fields is then
+    # max(m' + o, y') as it stands (one VIADDMNMX), and the diagonal uses substitution addends s - e
+    rng = np.random.default_rng(5)
+    n = 100000
+    o, e, base = -4, -2, 1234
+    m_prev = rng.integers(REAL_LO + 100, REAL_HI - 100, n)
+    y_prev = rng.integers(REAL_LO + 100, REAL_HI - 100, n)
+    s = rng.choice([2, -4], n)
+    field = lambda score, b: score - b + BIAS
+    y_new = np.maximum(m_prev + o, y_prev) + e
+    d_new = m_prev + s
+    nb = base + e
+    assert np.array_equal(field(y_new, nb), np.maximum(field(m_prev, base) + o, field(y_prev, base)))
+    assert np.array_equal(field(d_new, nb), field(m_prev, base) + (s - e))
+    # the Y flag: y' > m' + o  ==  y' + (BIAS2 - (o + 1)) - m' has its sign position set
+    w = pack(y_prev - base, y_prev - base) + (K - add2(o + 1)) - pack(m_prev - base, m_prev - base)
+    assert np.array_equal((w >> np.uint32(15)) & np.uint32(1), (y_prev > m_prev + o).astype(np.uint32))
