@@ -39,6 +39,35 @@ def build_workload(args, world):
 
 
 def clocks_sampler(stop, out, device_index):
+    """SM clock + throttle reasons during the timed region (the profiling recipe's clocks line). NVML in-process when
+    nvidia_ml_py is importable: forking nvidia-smi from a process that holds a >100 GB CUDA address space stalls the
+    launching thread for ~10 ms per sample; the nvidia-smi query is the fallback."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = device_index
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            idx = int(vis.split(",")[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = [(pynvml.nvmlClocksEventReasonHwSlowdown, 3), (pynvml.nvmlClocksEventReasonHwThermalSlowdown, 4),
+                (pynvml.nvmlClocksEventReasonSwThermalSlowdown, 5), (pynvml.nvmlClocksEventReasonSwPowerCap, 6)]
+        while not stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                f = [str(sm), str(mx), "", "", "", "", ""]
+                for bit, pos in bits:
+                    f[pos] = "Active" if (rs & bit) else "Not Active"
+                out.append(f)
+            except Exception:
+                pass
+            stop.wait(0.2)
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
