@@ -1,0 +1,71 @@
+"""The random small graphs on which the two CPU restatements are diffed (tests/test_pyref_vs_oracle.py: C++ oracle ==
+independent Python restatement, byte for byte) run through the DEVICE as well: same seeds, same generators, byte-exact
+command-line output against the oracle. Small multi-predecessor graphs with reads of 8-120 bases exercise what the
+full-size samples do not: the 4 / 8 / 16-column blocks of the mode-2 kernel, gather rows with few columns, bands of a few
+cells (random -b / -f), inputs on which the reference panics, path sets of 2-6 paths with recombination mosaics."""
+import numpy as np
+import pytest
+
+from recgraph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(args):
+    from recgraph_b200 import run_cli
+    from tests import oracle_lib
+    return run_cli(args), oracle_lib.run_cli(args)
+
+
+def _same(args, what):
+    (rc, out, err), (orc, oout, oerr) = _both(args)
+    assert rc == orc, f"{what}: exit code {rc} vs oracle {orc}\n{err[-300:]}\n{oerr[-300:]}"
+    assert out == oout, f"{what}:\n GPU: {out[:500]}\n REF: {oout[:500]}"
+    return orc
+
+
+def _pathwise_case(seed):   # == tests/test_pyref_vs_oracle.py::_case
+    rng = np.random.default_rng(seed)
+    bp = int(rng.integers(40, 130))
+    paths = int(rng.integers(2, 7))
+    g = synth.make_graph(bp, paths, seed=seed, mean_seg=int(rng.integers(3, 10)), p_snp=0.3, p_indel=0.15)
+    rlen = int(rng.integers(8, 40))
+    reads = synth.make_reads(g, 2, rlen, err=float(rng.choice([0.0, 0.05, 0.15])), seed=seed + 1, mosaic_breaks=int(rng.integers(0, 3)))
+    return g, reads
+
+
+@pytest.mark.parametrize("block", range(40))   # blocks 0-10 are the seeds the Python restatement is diffed on, 11-39 more of the same
+def test_pathwise_and_recombination_random_small_graphs(block, tmp_path):
+    for seed in range(1000 + 20 * block, 1020 + 20 * block):
+        g, reads = _pathwise_case(seed)
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        for mode in (4, 5, 8, 9):
+            _same(["-m", str(mode), str(fa), str(gfa)], f"seed {seed} mode {mode}")
+        if seed % 4 == 0:
+            for mode in (8, 9):
+                _same(["-m", str(mode), "-M", "1", "-X", "3", "-R", "1", "-r", "0.05", "-B", "0.7", str(fa), str(gfa)],
+                      f"seed {seed} mode {mode} (R=1 r=0.05 B=0.7)")
+        if seed % 5 == 0:
+            for mode in (6, 7):
+                _same(["-m", str(mode), str(fa), str(gfa)], f"seed {seed} mode {mode}")
+
+
+@pytest.mark.parametrize("block", range(16))   # blocks 0-3 are the seeds the Python restatement is diffed on
+def test_mode2_random_small_graphs_random_bands(block, tmp_path):
+    panics = 0
+    for seed in range(3000 + 25 * block, 3025 + 25 * block):   # == test_pyref_vs_oracle.py::test_mode2_random_small_graphs
+        rng = np.random.default_rng(seed)
+        g = synth.make_graph(int(rng.integers(60, 400)), 3, seed=seed, mean_seg=int(rng.integers(3, 12)), p_snp=0.25, p_indel=0.15)
+        reads = synth.make_reads(g, 2, int(rng.integers(10, 120)), err=float(rng.choice([0.0, 0.05, 0.2])), seed=seed + 1)
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        b, f = int(rng.integers(0, 6)), float(rng.choice([0.0, 0.01, 0.1, 0.5]))
+        rc = _same(["-m", "2", "-b", str(b), "-f", str(f), str(fa), str(gfa)], f"seed {seed} -b {b} -f {f}")
+        panics += rc == 101
+        # the other POA modes on the same input, default band
+        for mode in (0, 1, 3):
+            _same(["-m", str(mode), str(fa), str(gfa)], f"seed {seed} mode {mode}")
+    assert panics < 25   # most inputs align; the ones the reference panics on must panic here too (exit code 101)
