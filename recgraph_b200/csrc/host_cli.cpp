@@ -2,6 +2,8 @@
 #include <sys/stat.h>
 
 #include <chrono>
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -145,6 +147,8 @@ bool write_gaf(const Args& a, const std::string& text, size_t number, std::strin
 // 6 / 7) and the GAF record that goes through write_gaf.
 struct ShardOut {
     std::vector<std::string> pre, record;
+    int32_t emitted = 0; // leading reads of the shard whose output is valid: the reference prints read by read, so everything
+                         // before the first read it panics on has already been written when it dies
     int code = 0;        // 0 ok, 101 reference panic, 3 device / library error
     std::string err;
 };
@@ -178,6 +182,7 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
         std::vector<std::string> warn, record;
         std::vector<int32_t> score;
         std::vector<uint32_t> best_path;
+        int32_t panic_at = INT32_MAX;   // shard index of the first read the reference panics on
     };
     // idx: position inside this shard of every read of the batch (empty = identity)
     auto run_batch = [&](int dev_mode, int32_t nb, const uint8_t* codes, const uint64_t* off, const std::vector<int32_t>& idx,
@@ -202,8 +207,8 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
             bt.score[k] = res.reads[k].score;
             const int32_t i = lo + (idx.empty() ? k : idx[k]);   // index in the input file
             if (res.reads[k].status & RG_READ_REF_PANIC) {
-                panic("reference panic while aligning read " + std::to_string(i + 1) + " (see DESIGN.md, reference quirks)");
-                return false;
+                bt.panic_at = std::min(bt.panic_at, idx.empty() ? k : idx[k]);
+                continue;
             }
             if (res.reads[k].status & RG_READ_TRACE_OVERFLOW) {
                 so.err += "recgraph_b200: trace buffers overflowed for read " + std::to_string(i + 1) + "\n";
@@ -219,6 +224,7 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
             std::vector<char> buf(1 << 16);
             for (int32_t k = (int32_t)((int64_t)nb * t / T); k < (int32_t)((int64_t)nb * (t + 1) / T); k++) {
                 const int32_t i = lo + (idx.empty() ? k : idx[k]);
+                if ((idx.empty() ? k : idx[k]) >= bt.panic_at) continue;   // never printed by the reference
                 uint32_t len = (uint32_t)(off[k + 1] - off[k]);
                 int64_t need = rg_format_gaf(ctx, dev_mode, &res, k, reads.names[i], len, amb_flags, buf.data(), buf.size());
                 if (need < 0) {
@@ -254,12 +260,13 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
     };
     Batch fwd;
     if (!run_batch(mode, n, reads.codes, reads.off + lo, {}, 0, fwd)) return;
+    int32_t limit = std::min(n, fwd.panic_at);   // reads before the first panic are emitted, then the process dies like the reference
     // ---- -s true: reverse-complement retries (main.rs:82-101 mode 0, 150-164 mode 1, 198-214 mode 2, 233-249 mode 3)
     Batch rev;
     std::vector<int32_t> rev_of(n, -1);
     if (amb_strand && mode <= 3) {
         std::vector<int32_t> idx;
-        for (int32_t i = 0; i < n; i++)
+        for (int32_t i = 0; i < limit; i++)
             if (mode == 1 || mode == 3 || fwd.score[i] < 0) {  // modes 0 / 2 retry only when the forward score is negative
                 rev_of[i] = (int32_t)idx.size();
                 idx.push_back(i);
@@ -278,9 +285,12 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
             const int rmode = mode == 0 ? RG_MODE_GLOBAL_SCALAR : mode;
             const int flags = mode == 3 ? RG_AMB_HANDLES : (RG_AMB_HANDLES | RG_AMB_STRAND);
             if (!run_batch(rmode, (int32_t)idx.size(), rcs.data(), roff.data(), idx, flags, rev)) return;
+            limit = std::min(limit, rev.panic_at);
         }
     }
-    for (int32_t i = 0; i < n; i++) {
+    so.emitted = limit;
+    if (limit < n) panic("reference panic while aligning read " + std::to_string(lo + limit + 1) + " (see DESIGN.md, reference quirks)");
+    for (int32_t i = 0; i < limit; i++) {
         // warning lines are println!'d to stdout by the reference even with -o; only the record goes to the file
         so.pre[i] = fwd.warn[i];
         if (mode == 6 || mode == 7) {
@@ -370,19 +380,19 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
         for (int d = 0; d < G; d++) th.emplace_back([&, d] { run_shard(a, sc, reads, d, bound[d], bound[d + 1], shards[d]); });
         for (auto& t : th) t.join();
     }
-    for (int d = 0; d < G; d++)
-        if (shards[d].code) {
-            err += shards[d].err;
-            return finish(shards[d].code);
-        }
-    for (int d = 0; d < G; d++)
-        for (int32_t k = 0; k < bound[d + 1] - bound[d]; k++) {
+    for (int d = 0; d < G; d++) {
+        for (int32_t k = 0; k < shards[d].emitted; k++) {
             const int32_t i = bound[d] + k;
             const size_t number = mode <= 3 ? (size_t)i + 1 : (size_t)i;
             out += shards[d].pre[k];
             if (mode == 6 || mode == 7) continue;
             if (!write_gaf(a, shards[d].record[k], number, out)) return panic("unable to create file");
         }
+        if (shards[d].code) {   // a panic (or a device error) ends the output where the sequential reference would have stopped
+            err += shards[d].err;
+            return finish(shards[d].code);
+        }
+    }
     auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
     err += "Done in " + std::to_string(secs) + ".\n";  // main.rs:322
     return finish(0);

@@ -727,10 +727,49 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
             }
             uint32_t left, right;
             band_for_row(ms, me, riv.x, L, bta, left, right);
-            if (right <= left) {  // reference: empty row -> index / subtract-overflow panic later on
+            if (right < left) {  // reference: `right - left` overflows (gap_global_abpoa.rs:59)
                 status |= RG_READ_REF_PANIC;
                 abort_read = true;
                 break;
+            }
+            if (right == left) {
+                // An EMPTY row (only possible with b + f * L < 1) is legal in the reference: zero cells, best_scoring_pos =
+                // left (:203), and the rows after it find none of its cells available (every access is guarded by the
+                // band bounds, :254-346). Only the end-cell selection indexes it unconditionally (:205-215).
+                if ((rf & RF_F_PRED) || i == n - 2) {
+                    status |= RG_READ_REF_PANIC;
+                    abort_read = true;
+                    break;
+                }
+                rep16 = false;
+#pragma unroll
+                for (int k = 0; k < C; k++) A[k] = B[k] = NEG_INF;
+                P[0] = P[1] = P[2] = P[3] = 0u;
+                store_planes<C>(planes + (size_t)i * PlaneFmt<C>::ROWW + lane * NW, P);
+                if (nwp) {
+                    unsigned SD0[SB], SU0[SB];
+#pragma unroll
+                    for (int q = 0; q < SB; q++) SD0[q] = SU0[q] = 0u;
+                    side_store(i, SD0, SU0);
+                }
+                last_nonfull = (int)i;
+                if (rf & RF_IS_PRED) {
+                    store_row<C>(ring_m + (size_t)(i & RM) * STRIDE + cbase, A);
+                    store_row<C>(ring_y + (size_t)(i & RM) * STRIDE + cbase, B);
+                }
+                if (lane == 0) {
+                    RowMeta rm;
+                    rm.base = 0;
+                    rm.left = left;
+                    rm.right = right;
+                    rm.bsp = left;
+                    rowmeta[i] = rm;
+                }
+                __syncwarp();
+                prev_bsp = left;
+                prev_left = left;
+                prev_right = right;
+                continue;
             }
             cells += right - left;
             li = rbits & 0xffu;

@@ -97,10 +97,29 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
             uint32_t left, right;
             band_for_row(ms, me, g.r_values[i], L, bta, left, right);
             const uint32_t W = right - left;
-            if (W == 0 || right < left) {  // reference: empty row -> index / subtract-overflow panic later on
+            // `right - left` overflows in the reference when right < left (gap_global_abpoa.rs:59). An EMPTY row (b + f * L < 1
+            // only) is legal in mode 2: zero cells, best_scoring_pos = left, none of its cells available to later rows; only the
+            // end-cell selection indexes it unconditionally (:205-215). The scalar mode-0 routine reads m[best_p][0] of its
+            // smallest predecessor without a band check (global_abpoa.rs:318-321): an empty row stays a panic there.
+            if (right < left || (W == 0 && (LIN || (rf & RF_F_PRED) || i == n - 2))) {
                 status |= RG_READ_REF_PANIC;
                 abort_read = true;
                 break;
+            }
+            if (W == 0) {
+                if (lane == 0) {
+                    RowMeta rm;
+                    rm.base = (int32_t)(off >> 4);
+                    rm.left = left;
+                    rm.right = right;
+                    rm.bsp = left;
+                    rowmeta[i] = rm;
+                }
+                __syncwarp();
+                prev_left = left;
+                prev_right = right;
+                prev_bsp = left;
+                continue;
             }
             if (off + W > ws.trace_cap) {
                 status |= RG_READ_TRACE_OVERFLOW;

@@ -69,3 +69,26 @@ def test_mode2_random_small_graphs_random_bands(block, tmp_path):
         for mode in (0, 1, 3):
             _same(["-m", str(mode), str(fa), str(gfa)], f"seed {seed} mode {mode}")
     assert panics < 25   # most inputs align; the ones the reference panics on must panic here too (exit code 101)
+
+
+def test_mode2_zero_width_band_blocked_and_striped_kernels(tmp_path):
+    """b + f * L < 1 makes rows with NO cells (set_ampl_for_row, utils.rs:17-66): legal in the reference as long as nobody
+    indexes them (gap_global_abpoa.rs:59, :203, :254-346), a panic when the end-cell selection does (:205-215). Both mode-2
+    kernels (the register-blocked one and the striped one used for long reads) against the oracle."""
+    import os
+    done = 0
+    for seed in range(3000, 3200):
+        rng = np.random.default_rng(seed)
+        g = synth.make_graph(int(rng.integers(60, 400)), 3, seed=seed, mean_seg=int(rng.integers(3, 12)), p_snp=0.25, p_indel=0.15)
+        reads = synth.make_reads(g, 2, int(rng.integers(10, 120)), err=float(rng.choice([0.0, 0.05, 0.2])), seed=seed + 1)
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        args = ["-m", "2", "-b", "0", "-f", "0.0", str(fa), str(gfa)]
+        done += _same(args, f"seed {seed} blocked kernel") == 0
+        os.environ["RG_FORCE_STRIPED"] = "1"
+        try:
+            _same(args, f"seed {seed} striped kernel")
+        finally:
+            del os.environ["RG_FORCE_STRIPED"]
+    assert done >= 3   # a few of these inputs align (the others panic in the reference: exit code 101 on both sides)
