@@ -149,6 +149,7 @@ struct ShardOut {
     std::vector<std::string> pre, record;
     int32_t emitted = 0; // leading reads of the shard whose output is valid: the reference prints read by read, so everything
                          // before the first read it panics on has already been written when it dies
+    std::string tail;    // what the reference had already printed for the read it dies on (warning lines)
     int code = 0;        // 0 ok, 101 reference panic, 3 device / library error
     std::string err;
 };
@@ -180,7 +181,7 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
     const bool amb_strand = a.amb_strand == "true";
     struct Batch {
         std::vector<std::string> warn, record;
-        std::vector<int32_t> score;
+        std::vector<int32_t> score, status;
         std::vector<uint32_t> best_path;
         int32_t panic_at = INT32_MAX;   // shard index of the first read the reference panics on
     };
@@ -202,7 +203,9 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
         bt.record.resize(nb);
         bt.score.resize(nb);
         bt.best_path.resize(nb);
+        bt.status.resize(nb);
         for (int32_t k = 0; k < nb; k++) {
+            bt.status[k] = res.reads[k].status;
             bt.best_path[k] = res.reads[k].best_path;
             bt.score[k] = res.reads[k].score;
             const int32_t i = lo + (idx.empty() ? k : idx[k]);   // index in the input file
@@ -289,6 +292,17 @@ void run_shard(const Args& a, const rg_scoring& sc, const rg_reads& reads, int d
         }
     }
     so.emitted = limit;
+    if (limit < n) {
+        // mode 2 prints its band warning (gap_global_abpoa.rs:226) before the traceback that panics (gaf_of_gap_abpoa); with
+        // -s the forward alignment of the read has been through all of that when the retry dies
+        const char* bw = "Band length probably too short, maybe try with larger b and f\n";
+        if (fwd.panic_at == limit) {
+            if (fwd.status[limit] & RG_READ_BAND_WARNING) so.tail = bw;
+        } else {
+            so.tail = fwd.warn[limit];
+            if (rev.status[rev_of[limit]] & RG_READ_BAND_WARNING) so.tail += bw;
+        }
+    }
     if (limit < n) panic("reference panic while aligning read " + std::to_string(lo + limit + 1) + " (see DESIGN.md, reference quirks)");
     for (int32_t i = 0; i < limit; i++) {
         // warning lines are println!'d to stdout by the reference even with -o; only the record goes to the file
@@ -389,6 +403,7 @@ extern "C" int rg_cli_main(int argc, const char** argv, char** out_text, char** 
             if (!write_gaf(a, shards[d].record[k], number, out)) return panic("unable to create file");
         }
         if (shards[d].code) {   // a panic (or a device error) ends the output where the sequential reference would have stopped
+            out += shards[d].tail;
             err += shards[d].err;
             return finish(shards[d].code);
         }

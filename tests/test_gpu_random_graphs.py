@@ -34,7 +34,7 @@ def _pathwise_case(seed):   # == tests/test_pyref_vs_oracle.py::_case
     return g, reads
 
 
-@pytest.mark.parametrize("block", range(40))   # blocks 0-10 are the seeds the Python restatement is diffed on, 11-39 more of the same
+@pytest.mark.parametrize("block", range(24))   # blocks 0-10 are the seeds the Python restatement is diffed on, 11-23 more of the same
 def test_pathwise_and_recombination_random_small_graphs(block, tmp_path):
     for seed in range(1000 + 20 * block, 1020 + 20 * block):
         g, reads = _pathwise_case(seed)
@@ -52,7 +52,7 @@ def test_pathwise_and_recombination_random_small_graphs(block, tmp_path):
                 _same(["-m", str(mode), str(fa), str(gfa)], f"seed {seed} mode {mode}")
 
 
-@pytest.mark.parametrize("block", range(16))   # blocks 0-3 are the seeds the Python restatement is diffed on
+@pytest.mark.parametrize("block", range(12))   # blocks 0-3 are the seeds the Python restatement is diffed on
 def test_mode2_random_small_graphs_random_bands(block, tmp_path):
     panics = 0
     for seed in range(3000 + 25 * block, 3025 + 25 * block):   # == test_pyref_vs_oracle.py::test_mode2_random_small_graphs
@@ -92,3 +92,63 @@ def test_mode2_zero_width_band_blocked_and_striped_kernels(tmp_path):
         finally:
             del os.environ["RG_FORCE_STRIPED"]
     assert done >= 3   # a few of these inputs align (the others panic in the reference: exit code 101 on both sides)
+
+
+@pytest.mark.parametrize("block", range(40))   # blocks 30 and 38 hold inputs whose traceback panics after the band warning
+def test_poa_modes_random_flags(block, tmp_path):
+    """Modes 0-3 with random band, scoring, matrix and strand flags on random small graphs (25 per block)."""
+    for seed in range(5000 + 25 * block, 5025 + 25 * block):
+        rng = np.random.default_rng(seed)
+        g = synth.make_graph(int(rng.integers(60, 500)), int(rng.integers(2, 6)), seed=seed, mean_seg=int(rng.integers(3, 14)),
+                             p_snp=0.25, p_indel=0.15)
+        reads = synth.make_reads(g, 3, int(rng.integers(10, 220)), err=float(rng.choice([0.0, 0.05, 0.2])), seed=seed + 1)
+        if rng.random() < 0.5:   # some reads from the reverse strand, so that -s true has something to find
+            comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+            reads[1] = "".join(comp[c] for c in reversed(reads[1]))
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        mode = int(rng.integers(0, 4))
+        args = ["-m", str(mode), "-b", str(int(rng.choice([1, 1, 2, 5, 20, 40, 300]))), "-f", str(float(rng.choice([0.0, 0.01, 0.1, 0.3])))]
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            args += ["-t", str(rng.choice(["HOXD70", "HOXD55"]))]
+        elif kind == 1:
+            args += ["-M", str(int(rng.choice([1, 2, 5, 30, 40]))), "-X", str(int(rng.choice([1, 4, 8, 30, 50])))]
+        if mode >= 2 and rng.random() < 0.6:
+            args += ["-O", str(int(rng.choice([0, 1, 4, 10, 30, 45]))), "-E", str(int(rng.choice([1, 2, 6, 30])))]
+        if rng.random() < 0.4:
+            args += ["-s", "true"]
+        _same(args + [str(fa), str(gfa)], f"seed {seed}: {' '.join(args)}")
+
+
+def _pathwise_flag_case(seed, tmp_path):
+    rng = np.random.default_rng(seed)
+    g = synth.make_graph(int(rng.integers(40, 260)), int(rng.integers(2, 13)), seed=seed, mean_seg=int(rng.integers(3, 12)),
+                         p_snp=0.3, p_indel=0.15)
+    reads = synth.make_reads(g, 3, int(rng.integers(8, 90)), err=float(rng.choice([0.0, 0.05, 0.15])), seed=seed + 1,
+                             mosaic_breaks=int(rng.integers(0, 4)))
+    gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+    gfa.write_text(g.gfa())
+    fa.write_text(synth.fasta(reads))
+    mode = int(rng.choice([4, 5, 6, 7, 8, 9, 8, 9]))
+    args = ["-m", str(mode)]
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        args += ["-t", str(rng.choice(["HOXD70", "HOXD55"]))]
+    elif kind == 1:
+        args += ["-M", str(int(rng.choice([1, 2, 5, 20]))), "-X", str(int(rng.choice([1, 3, 4, 9])))]
+    if mode in (6, 7) and rng.random() < 0.6:
+        args += ["-O", str(int(rng.choice([0, 1, 4, 10]))), "-E", str(int(rng.choice([1, 2, 5])))]
+    if mode in (8, 9) and rng.random() < 0.7:
+        args += ["-R", str(int(rng.choice([0, 1, 4, 12]))), "-r", str(float(rng.choice([0.0, 0.01, 0.1, 0.5]))),
+                 "-B", str(float(rng.choice([0.3, 0.6, 1.0])))]
+    return args + [str(fa), str(gfa)]
+
+
+@pytest.mark.parametrize("block", range(24))
+def test_pathwise_modes_random_flags(block, tmp_path):
+    """Modes 4-9 with random scoring, matrices, gap and recombination parameters, 2-12 paths (25 graphs per block)."""
+    for seed in range(7000 + 25 * block, 7025 + 25 * block):
+        args = _pathwise_flag_case(seed, tmp_path)
+        _same(args, f"seed {seed}: {' '.join(args[:-2])}")
