@@ -152,3 +152,30 @@ def test_pathwise_modes_random_flags(block, tmp_path):
     for seed in range(7000 + 25 * block, 7025 + 25 * block):
         args = _pathwise_flag_case(seed, tmp_path)
         _same(args, f"seed {seed}: {' '.join(args[:-2])}")
+
+
+def _mid_case(seed, tmp_path):
+    rng = np.random.default_rng(seed)
+    g = synth.make_graph(int(rng.integers(1000, 7000)), int(rng.integers(2, 9)), seed=seed)
+    rlen = int(rng.choice([60, 150, 300, 500, 800, 1000]))
+    reads = synth.make_reads(g, 4, rlen, err=float(rng.choice([0.0, 0.03, 0.1])), seed=seed + 1)
+    gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+    gfa.write_text(g.gfa())
+    fa.write_text(synth.fasta(reads))
+    mode = int(rng.choice([2, 2, 2, 2, 0, 1, 3]))
+    args = ["-m", str(mode), "-b", str(int(rng.choice([1, 2, 5, 16, 50, 300, 2000]))), "-f", str(float(rng.choice([0.0, 0.01, 0.05, 0.2])))]
+    if rng.random() < 0.5:
+        args += ["-M", str(int(rng.choice([1, 2, 5, 30, 35]))), "-X", str(int(rng.choice([1, 4, 8, 30, 35])))]
+    if mode >= 2 and rng.random() < 0.5:
+        args += ["-O", str(int(rng.choice([0, 1, 4, 10, 30, 35]))), "-E", str(int(rng.choice([1, 2, 6, 30])))]
+    return args + [str(fa), str(gfa)]
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_poa_mid_size_graphs_random_bands_and_scores(block, tmp_path):
+    """1-7 kbp graphs, reads of 60-1000 bases: long runs of packed full-band rows with gather rows in between (mode 2), band
+    amplitudes from 1 to the whole read — what decides whether the packed rows keep the exact column of the row maximum or a
+    lower bound — and scores on both sides of the packed rows' domain (|score| <= 30)."""
+    for seed in range(9000 + 8 * block, 9008 + 8 * block):
+        args = _mid_case(seed, tmp_path)
+        _same(args, f"seed {seed}: {' '.join(args[:-2])}")
