@@ -737,7 +737,8 @@ static int align_poa(rg_ctx* c, int mode) {
         cudaEventRecord(c->ev0, c->stream);
         if (blkC && trace_cap < full) return c->fail(RG_ERR_NOMEM, "not enough device memory for the blocked kernel's trace");
         int rc = lin ? launch_poa_lin(mode, blkC, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), c->stream)
-                 : blkC ? launch_gap_global_blk(blkC, c->dg, c->ds, ws, b, trace_bytes, (int)((slots + wpb - 1) / wpb), c->stream)
+                 : blkC ? launch_gap_global_blk(blkC, c->dg, c->ds, ws, b, trace_bytes,
+                                                (int)std::max<uint32_t>((slots + wpb - 1) / wpb, std::min<uint32_t>((uint32_t)c->sms * blocks_per_sm, slots)), c->stream)
                       : launch_poa(mode, c->dg, c->ds, ws, b, trace_bytes, (int)(slots / 8), ws_cols, c->stream);
         cudaEventRecord(c->ev1, c->stream);
         if (rc != 0 || cudaStreamSynchronize(c->stream) != cudaSuccess) return c->cuda_fail("alignment kernel");

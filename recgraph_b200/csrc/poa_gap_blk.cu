@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(BLK_WARPS * 32, RG_BLK_CTAS)
     __shared__ int32_t s_sc[48];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const uint32_t slot = blockIdx.x * BLK_WARPS + wib;
+    // slots go round the CTAs first: when trace memory allows fewer reads in flight than 12 per SM (large graphs), they
+    // spread over all SMs instead of filling a few
+    const uint32_t slot = (uint32_t)wib * gridDim.x + blockIdx.x;
     if (threadIdx.x < 48) s_sc[threadIdx.x] = (&sc.sc[0][0])[threadIdx.x];
     __syncthreads();
     if (slot >= ws.slots) return;
