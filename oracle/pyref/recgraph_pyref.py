@@ -18,6 +18,12 @@ and, for the headline mode 2 whose traceback the reference's unit tests do not p
   bitfield_path.rs:3-44                          the 32-bit trace cell with its 16-bit predecessor
   gaf_output.rs:96-253,867-892                   gaf_of_gap_abpoa, node_start, set_cigar_substring
 
+and for the other POA modes on an AVX2 machine (what the reference's CLI runs):
+  global_abpoa.rs:10-257, gaf_output.rs:753-865  mode 0: exec_simd lane by lane, f32 path values decoded through their text
+  local_poa.rs:10-179, gaf_output.rs:639-751     mode 1: exec_simd, gaf_of_local_poa_simd
+  gap_local_poa.rs:8-187, gaf_output.rs:502-637  mode 3: exec (get_best_d / get_best_u with their never-set `first`)
+  utils.rs:74-99,129-140                         set_left_right_x64, get_max_d_u_l
+
 `rev_align` is `align` mirrored in i and j (checked mechanically: sed 's/i + 1/i - 1/; s/j + 1/j - 1/' on lines 129-435
 diffs clean against 436-745 apart from the border cases), so one cell routine parameterised by direction serves both.
 HashMap iteration orders of the reference (predecessors of a node) are fixed to ascending predecessor index.
@@ -1232,6 +1238,488 @@ def run_mode2(fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, 
         v = F32(F32(extra_b) + F32(F32(extra_f) * F32(len(seq))))
         bta = 0 if not (v > 0) else int(v)
         text, _score = mode2_exec(seq, names[k], lnz, nwp, pred, sm, -gap_open, -gap_ext, bta, hofp)
+        out += text
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ modes 0 / 1 / 3
+def set_left_right_x64(left, right, seq_len):
+    """utils.rs:74-99 (usize arithmetic: a negative intermediate is the reference's subtract-overflow panic)"""
+    nr, nl = right, left
+    if nr < nl:
+        raise RuntimeError("attempt to subtract with overflow")
+    while (nr - nl) % 8 != 0:
+        if (nr - nl) % 2 == 0 and nr < seq_len:
+            nr += 1
+        elif nl > 0:
+            nl -= 1
+        else:
+            break
+    if nl == 0:
+        if nr == 0:
+            raise RuntimeError("attempt to subtract with overflow")
+        while (nr - 1) % 8 != 0 and nr < seq_len:
+            nr += 1
+    if nr == seq_len:
+        while (nr - nl) % 8 != 0 and nl > 1:
+            nl -= 1
+    return nl, nr
+
+
+def f32_scores(sm):
+    """score_matrix.rs:10-17"""
+    return {k: F32(v) for k, v in sm.items()}
+
+
+def _split_path_value(val):
+    """`val.to_string().split('.')`, integer part -> predecessor, fraction digits -> direction (gaf_output.rs:668-672)"""
+    parts = f32_display(val).split(".")
+    if len(parts) < 2:
+        raise RuntimeError("index out of bounds: the len is 1 but the index is 1")
+    return int(parts[0]), int(parts[1])
+
+
+def mode0_exec_simd(read, name, lnz, nwp, pred, sm, bta, hofp, r_values):
+    """global_abpoa.rs:10-257 (exec_simd, amb_mode = false), lane by lane; returns (stdout text, score)"""
+    n, L = len(lnz), len(read)
+    min_score = F32(F32(2.0) * F32(L)) * sm[(read[1], "-")]
+    m = np.full((n, L), min_score, dtype=F32)
+    path = np.full((n, L), -1.0, dtype=F32)
+    bsp = [0] * n
+    m[0][0] = 0.0
+    path[0][0] = 0.0
+    for i in range(1, n - 1):
+        if not nwp[i]:
+            m[i][0] = m[i - 1][0] + sm[(lnz[i], "-")]
+            path[i][0] = F32(i - 1) + F32(0.2)
+        else:
+            best_p = min(pred[i])
+            m[i][0] = m[best_p][0] + sm[(lnz[i], "-")]
+            path[i][0] = F32(best_p) + F32(0.2)
+    left, right = set_left_right_x64(*set_ampl_for_row(0, [], r_values[0], bsp, L, bta), L)
+    for j in range(1, right):
+        m[0][j] = m[0][j - 1] + sm[(read[j], "-")]
+        path[0][j] = F32(0.3)
+    for i in range(1, n - 1):
+        p_arr = pred[i] if nwp[i] else []
+        left, right = set_left_right_x64(*set_ampl_for_row(i, p_arr, r_values[i], bsp, L, bta), L)
+        best_col = left
+        start = 1 if left == 0 else left
+        if right == L:
+            if right < start:
+                raise RuntimeError("attempt to subtract with overflow")
+            end = ((right - start) // 8) * 8 + start
+        else:
+            end = right
+        us_update = sm[(lnz[i], "-")]
+        for j in range(start, end, 8):
+            if j + 7 >= L:
+                raise RuntimeError("index out of bounds (read[j + 7])")
+            res, pth = [], []
+            for k in range(8):      # the eight lanes; every input is a finished row
+                idx = j + k
+                ds_update = sm[(lnz[i], read[idx])]
+                if not nwp[i]:
+                    us = m[i - 1][idx] + us_update
+                    ds = m[i - 1][idx - 1] + ds_update
+                    take_d = ds > us
+                    res.append(ds if take_d else us)
+                    pth.append(F32(i - 1) + (F32(0.1) if take_d else F32(0.2)))
+                else:
+                    preds = pred[i]
+                    best_us, best_ds = m[preds[0]][idx], m[preds[0]][idx - 1]
+                    pbu = pbd = F32(preds[0])
+                    for q in preds[1:]:
+                        if m[q][idx] > best_us:
+                            best_us, pbu = m[q][idx], F32(q)
+                        if m[q][idx - 1] > best_ds:
+                            best_ds, pbd = m[q][idx - 1], F32(q)
+                    best_us = best_us + us_update
+                    best_ds = best_ds + ds_update
+                    take_d = best_ds > best_us
+                    res.append(best_ds if take_d else best_us)
+                    pth.append(pbd + F32(0.1) if take_d else pbu + F32(0.2))
+            for k in range(8):
+                m[i][j + k] = res[k]
+                path[i][j + k] = pth[k]
+            for idx in range(j, j + 8):
+                l = m[i][idx - 1] + sm[(read[j], "-")]     # read[j], not read[idx] (global_abpoa.rs:157)
+                if l > m[i][idx]:
+                    m[i][idx] = l
+                    path[i][idx] = F32(i) + F32(0.3)
+                if m[i][idx] >= m[i][best_col]:
+                    best_col = idx
+        if end < right:
+            for j in range(end, right):
+                if not nwp[i]:
+                    l = m[i][j - 1] + sm[(read[j], "-")]
+                    u = m[i - 1][j] + sm[(lnz[i], "-")]
+                    d = m[i - 1][j - 1] + sm[(lnz[i], read[j])]
+                    m[i][j] = max(l, u, d)
+                    if m[i][j] == d:
+                        path[i][j] = F32(i - 1) + F32(0.1)
+                    elif m[i][j] == u:
+                        path[i][j] = F32(i - 1) + F32(0.2)
+                    else:
+                        path[i][j] = F32(i) + F32(0.3)
+                else:
+                    u = d = F32(0)
+                    u_pred = d_pred = 0
+                    first = True
+                    for q in pred[i]:
+                        if first:
+                            u, d, u_pred, d_pred, first = m[q][j], m[q][j - 1], q, q, False
+                        if m[q][j] > u:
+                            u, u_pred = m[q][j], q
+                        if m[q][j - 1] > d:
+                            d, d_pred = m[q][j - 1], q
+                    u = u + sm[(lnz[i], "-")]
+                    d = d + sm[(read[j], lnz[i])]
+                    l = m[i][j - 1] + sm[(read[j], "-")]
+                    m[i][j] = max(l, u, d)
+                    if m[i][j] == d:
+                        path[i][j] = F32(d_pred) + F32(0.1)
+                    elif m[i][j] == u:
+                        path[i][j] = F32(u_pred) + F32(0.2)
+                    else:
+                        path[i][j] = F32(i) + F32(0.3)
+                if m[i][j] >= m[i][best_col]:
+                    best_col = j
+        bsp[i] = best_col
+    best_result, last_row, first = F32(0), 0, True
+    for q in pred[n - 1]:
+        if first:
+            best_result, last_row, first = m[q][L - 1], q, False
+        if m[q][L - 1] > best_result:
+            best_result, last_row = m[q][L - 1], q
+    return gaf_of_global_abpoa_simd(path, read, name, last_row, L - 1, hofp, lnz, best_result), int(best_result)
+
+
+def gaf_of_global_abpoa_simd(path, seq, name, last_row, last_col, hofp, lnz, best_score):
+    """gaf_output.rs:753-865 (amb_mode = false); returns the stdout text of the read"""
+    col, row = last_col, last_row
+    hia, cigar, path_sequence = [], [], []
+    path_length = residues = 0
+    out_ok = True
+    while path[row][col] != 0.0:
+        val = path[row][col]
+        if val == F32(-1.0):
+            out_ok = False
+            break
+        prd, d = _split_path_value(val)
+        if d == 1:
+            hia.append(hofp[row])
+            path_sequence.append(lnz[row])
+            row = prd
+            col -= 1
+            cigar.append("D" if lnz[row] == seq[col] else "d")   # compared AFTER the move (gaf_output.rs:793)
+            path_length += 1
+            residues += 1
+        elif d == 3:
+            col -= 1
+            cigar.append("L")
+        elif d == 2:
+            hia.append(hofp[row])
+            path_sequence.append(lnz[row])
+            row = prd
+            cigar.append("U")
+            path_length += 1
+        else:
+            raise RuntimeError("impossible value in poa path")
+    if not out_ok:
+        return "band not enough for correct output\n" + gaf_string("", 0, 0, 0, " ", [0], 0, 0, 0, 0, "", "", "") + "\n"
+    cigar.reverse()
+    cigar_out = build_cigar(cigar)
+    path_sequence.reverse()
+    hia = dedup(hia)
+    hia.reverse()
+    comments = f"{cigar_out}, score: {f32_display(best_score)}\t{''.join(path_sequence)}"
+    return gaf_string(name, len(seq) - 1, col, last_col, "+", [int(x) for x in hia], path_length, node_start(hofp, row),
+                      node_start(hofp, last_row), residues, "*", "*", comments) + "\n"
+
+
+def mode1_exec_simd(read, name, lnz, nwp, pred, sm, hofp):
+    """local_poa.rs:10-179 (exec_simd, amb_mode = false), lane by lane; returns (stdout text, score as i32)"""
+    n, L = len(lnz), len(read)
+    m = np.zeros((n, L), dtype=F32)
+    path = np.zeros((n, L), dtype=F32)
+    if L % 8 != 0:
+        max_multiple = (L // 8) * 8
+    else:
+        if L < 8:
+            raise RuntimeError("attempt to subtract with overflow")
+        max_multiple = L - 8
+    best_row = best_col = 0
+    for i in range(1, n - 1):
+        us_update = sm[(lnz[i], "-")]
+        for j in range(1, max_multiple + 1, 8):
+            if j + 7 >= L:
+                raise RuntimeError("index out of bounds (read[j + 7])")
+            res, pth = [], []
+            for k in range(8):
+                idx = j + k
+                ds_update = sm[(lnz[i], read[idx])]
+                if not nwp[i]:
+                    us = m[i - 1][idx] + us_update
+                    ds = m[i - 1][idx - 1] + ds_update
+                    take_d = ds > us
+                    res.append(ds if take_d else us)
+                    pth.append(F32(i - 1) + (F32(0.1) if take_d else F32(0.2)))
+                else:
+                    preds = pred[i]
+                    best_us, best_ds = m[preds[0]][idx], m[preds[0]][idx - 1]
+                    pbu = pbd = F32(preds[0])
+                    for q in preds[1:]:
+                        if m[q][idx] > best_us:
+                            best_us, pbu = m[q][idx], F32(q)
+                        if m[q][idx - 1] > best_ds:
+                            best_ds, pbd = m[q][idx - 1], F32(q)
+                    best_us = best_us + us_update
+                    best_ds = best_ds + ds_update
+                    take_d = best_ds > best_us
+                    res.append(best_ds if take_d else best_us)
+                    pth.append(pbd + F32(0.1) if take_d else pbu + F32(0.2))
+            for k in range(8):
+                m[i][j + k] = res[k]
+                path[i][j + k] = pth[k]
+            for idx in range(j, min(j + 8, L)):
+                l = m[i][idx - 1] + sm[(read[j], "-")]
+                if l > m[i][idx]:
+                    m[i][idx] = l
+                    path[i][idx] = F32(i) + F32(0.3)
+                if m[i][idx] <= 0.0:
+                    m[i][idx] = 0.0
+                    path[i][idx] = 0.0
+                if m[i][idx] >= m[best_row][best_col]:
+                    best_row, best_col = i, idx
+        for j in range(max_multiple + 1, L):
+            if not nwp[i]:
+                l = m[i][j - 1] + sm[(read[j], "-")]
+                u = m[i - 1][j] + sm[(lnz[i], "-")]
+                d = m[i - 1][j - 1] + sm[(lnz[i], read[j])]
+                m[i][j] = max(l, u, d)
+                if m[i][j] < 0.0:
+                    m[i][j] = 0.0
+                    path[i][j] = 0.0
+                elif m[i][j] == d:
+                    path[i][j] = F32(i - 1) + F32(0.1)
+                elif m[i][j] == u:
+                    path[i][j] = F32(i - 1) + F32(0.2)
+                else:
+                    path[i][j] = F32(i) + F32(0.3)
+            else:
+                u = d = F32(0)
+                u_pred = d_pred = 0
+                first = True
+                for q in pred[i]:
+                    if first:
+                        u, d, u_pred, d_pred, first = m[q][j], m[q][j - 1], q, q, False
+                    if m[q][j] > u:
+                        u, u_pred = m[q][j], q
+                    if m[q][j - 1] > d:
+                        d, d_pred = m[q][j - 1], q
+                u = u + sm[(lnz[i], "-")]
+                d = d + sm[(read[j], lnz[i])]
+                l = m[i][j - 1] + sm[(read[j], "-")]
+                m[i][j] = max(l, u, d)        # no clamp at 0 on this branch (local_poa.rs:149-160)
+                if m[i][j] == d:
+                    path[i][j] = F32(d_pred) + F32(0.1)
+                elif m[i][j] == u:
+                    path[i][j] = F32(u_pred) + F32(0.2)
+                else:
+                    path[i][j] = F32(i) + F32(0.3)
+            if m[i][j] >= m[best_row][best_col]:
+                best_row, best_col = i, j
+    return gaf_of_local_poa_simd(path, read, name, best_row, best_col, hofp), int(m[best_row][best_col])
+
+
+def _segment_cigar_walk(seq, name, last_row, last_col, hofp, step):
+    """The shared frame of gaf_of_local_poa_simd (gaf_output.rs:639-751) and gaf_of_gap_local_poa (:502-637): one CIGAR
+    per segment, flushed when the handle or the kind of move changes. `step(row, col)` returns None at the origin cell or
+    (kind, new_row, new_col, d_count, i_count, m_count, handle_pushes, path_len, residues)."""
+    col, row = last_col, last_row
+    hia, cigars = [], []
+    cigar = ""
+    cm = ci = cd = 0
+    curr_handle, last_dir = "", None
+    path_length = residues = 0
+    while True:
+        st = step(row, col)
+        if st is None:
+            break
+        kind = st[0]
+        if hofp[row] != curr_handle:
+            cigar = set_cigar_substring(cm, ci, cd, cigar)
+            cigars.insert(0, cigar)
+            cigar = ""
+            cm = ci = cd = 0
+        curr_handle = hofp[row]
+        if kind != last_dir:
+            cigar = set_cigar_substring(cm, ci, cd, cigar)
+            cm = ci = cd = 0
+        last_dir = kind
+        _k, nrow, ncol, dd, di, dm, pushes, plen, res = st
+        hia += pushes
+        row, col = nrow, ncol
+        cd += dd
+        ci += di
+        cm += dm
+        path_length += plen
+        residues += res
+    cigar = set_cigar_substring(cm, ci, cd, cigar)
+    cigars.insert(0, cigar)
+    hia = dedup(hia)
+    hia.reverse()
+    comments = ",".join(cigars[:len(cigars) - 1])
+    return gaf_string(name, len(seq) - 1, col, last_col, "+", [int(x) for x in hia], path_length, node_start(hofp, row),
+                      node_start(hofp, last_row), residues, "*", "*", comments) + "\n"
+
+
+def gaf_of_local_poa_simd(path, seq, name, last_row, last_col, hofp):
+    """gaf_output.rs:639-751 (amb_mode = false)"""
+    def step(row, col):
+        val = path[row][col]
+        if val == 0.0:
+            return None
+        prd, d = _split_path_value(val)
+        if d == 1:
+            return (1, prd, col - 1, 0, 0, 1, [hofp[row]], 1, 1)
+        if d == 3:
+            return (3, row, col - 1, 1, 0, 0, [], 0, 0)
+        if d == 2:
+            return (2, prd, col, 0, 1, 0, [hofp[row]], 1, 0)
+        raise RuntimeError("impossible value in poa path")
+    return _segment_cigar_walk(seq, name, last_row, last_col, hofp, step)
+
+
+def mode3_exec(seq, name, lnz, nwp, pred, sm, o, e, hofp):
+    """gap_local_poa.rs:8-187 (amb_mode = false); returns (stdout text, score)"""
+    n, L = len(lnz), len(seq)
+    m = [[0] * L for _ in range(n)]
+    x = [[0] * L for _ in range(n)]
+    y = [[0] * L for _ in range(n)]
+    O = cell(0, "O")
+    path = [[O] * L for _ in range(n)]     # rows the loops never reach keep bitvec![0; 32] = (0, 'O')
+    path_x = [[O] * L for _ in range(n)]
+    path_y = [[O] * L for _ in range(n)]
+    best_row = best_col = 0
+    for i in range(n - 1):
+        for j in range(L):
+            if i == 0 or j == 0:
+                path[i][j] = path_x[i][j] = path_y[i][j] = O
+            else:
+                l_x = x[i][j - 1] + e
+                l_m = m[i][j - 1] + o + e
+                if l_x > l_m:
+                    path_x[i][j] = cell(i, "X")
+                    l = l_x
+                else:
+                    path_x[i][j] = cell(i, "M")
+                    l = l_m
+                x[i][j] = l
+                if not nwp[i]:
+                    d = m[i - 1][j - 1] + sm[(seq[j], lnz[i])]
+                    d_idx = u_idx = i - 1
+                    u_y = y[i - 1][j] + e
+                    u_m = m[i - 1][j] + o + e
+                    if u_y > u_m:
+                        path_y[i][j] = cell(u_idx, "Y")
+                        u = u_y
+                    else:
+                        path_y[i][j] = cell(u_idx, "M")
+                        u = u_m
+                    y[i][j] = u
+                else:
+                    # get_best_d / get_best_u start from 0 / predecessor 0: their `first` flag is initialised to false
+                    # (gap_local_poa.rs:134,163), so the first predecessor never seeds the maximum
+                    d, d_idx = 0, 0
+                    for q in pred[i]:
+                        if m[q][j - 1] > d:
+                            d, d_idx = m[q][j - 1], q
+                    um, uy, um_idx, uy_idx = 0, 0, 0, 0
+                    for q in pred[i]:
+                        if m[q][j] + o > um:
+                            um, um_idx = m[q][j] + o, q
+                        if y[q][j] > uy:
+                            uy, uy_idx = y[q][j], q
+                    if um > uy:
+                        u, u_idx, from_m = um, um_idx, True
+                    else:
+                        u, u_idx, from_m = uy, uy_idx, False
+                    d += sm[(seq[j], lnz[i])]
+                    u += e
+                    y[i][j] = u
+                    path_y[i][j] = cell(u_idx, "M" if from_m else "Y")
+                if d < 0 and l < 0 and u < 0:
+                    m[i][j] = 0
+                    path[i][j] = O
+                else:
+                    # utils::get_max_d_u_l (utils.rs:129-140)
+                    if d < u:
+                        best_val, dr = (l, "L") if u < l else (u, "U")
+                    else:
+                        best_val, dr = (l, "L") if d < l else (d, "D")
+                    if dr == "D" and lnz[i] != seq[j]:
+                        dr = "d"
+                    m[i][j] = best_val
+                    path[i][j] = cell(d_idx if dr in "Dd" else (u_idx if dr == "U" else i), dr)
+            if m[i][j] > m[best_row][best_col]:
+                best_row, best_col = i, j
+    return gaf_of_gap_local_poa(path, path_x, path_y, seq, name, best_row, best_col, hofp), m[best_row][best_col]
+
+
+def gaf_of_gap_local_poa(path, path_x, path_y, seq, name, last_row, last_col, hofp):
+    """gaf_output.rs:502-637 (amb_mode = false). The X / Y chains are walked inside ONE step of the outer loop."""
+    def step(row, col):
+        prd, d = path[row][col]
+        if d == "O":
+            return None
+        if d == "D":
+            return ("D", prd, col - 1, 0, 0, 1, [hofp[row]], 1, 1)
+        if d == "d":
+            return ("D", prd, col - 1, 0, 0, 1, [hofp[row]], 1, 0)      # compared upper-cased (:539)
+        if d == "L":
+            if path_x[row][col][1] == "X":
+                cnt = 0
+                while path_x[row][col][1] == "X":
+                    cnt += 1
+                    col -= 1
+                return ("L", row, col, cnt, 0, 0, [], 0, 0)
+            return ("L", row, col - 1, 1, 0, 0, [], 0, 0)
+        if d == "U":
+            if path_y[row][col][1] == "Y":
+                pushes, cnt = [], 0
+                while path_y[row][col][1] == "Y":
+                    q = path_y[row][col][0]
+                    pushes.append(hofp[row])
+                    row = q
+                    cnt += 1
+                return ("U", row, col, 0, cnt, 0, pushes, cnt, 0)
+            return ("U", prd, col, 0, 1, 0, [hofp[row]], 1, 0)
+        raise RuntimeError("impossible value in poa path")
+    return _segment_cigar_walk(seq, name, last_row, last_col, hofp, step)
+
+
+def run_poa(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01, max_reads=None):
+    """main.rs:47-101 (mode 0), :103-169 (mode 1), :215-252 (mode 3) on an AVX2 machine, without -s; returns stdout"""
+    seqs, names = read_fasta(fasta_text)
+    segs, _paths = read_gfa(gfa_text)
+    lnz, nwp, pred, hofp = create_graph_struct(segs, read_gfa_links(gfa_text))
+    sm = score_matrix_match_mis(match, -mismatch)
+    smf = f32_scores(sm)
+    r_values = set_r_values(nwp, pred, len(lnz)) if mode == 0 else None
+    out = ""
+    for k, seq in enumerate(seqs):
+        if max_reads is not None and k >= max_reads:
+            break
+        if mode == 0:
+            v = F32(F32(extra_b) + F32(F32(extra_f) * F32(len(seq))))
+            bta = 0 if not (v > 0) else int(v)
+            text, _ = mode0_exec_simd(seq, names[k], lnz, nwp, pred, smf, bta, hofp, r_values)
+        elif mode == 1:
+            text, _ = mode1_exec_simd(seq, names[k], lnz, nwp, pred, smf, hofp)
+        else:
+            text, _ = mode3_exec(seq, names[k], lnz, nwp, pred, sm, -gap_open, -gap_ext, hofp)
         out += text
     return out
 

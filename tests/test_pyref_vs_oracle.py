@@ -2,7 +2,9 @@
 checker of the CUDA path) against a SECOND, independent restatement written in Python from the Rust sources only
 (oracle/pyref/recgraph_pyref.py) — pathwise DP of modes 4 / 5, `align` / `rev_align` / `absolute_scores` /
 `best_alignment` of modes 8 / 9, `build_alignment`, the four `gaf_output_*` builders, path-length helpers and GAF text.
-Byte-identical stdout on the example and on 220 random small graphs (single source and sink)."""
+Byte-identical stdout on the example and on 220 random small graphs (single source and sink); the same for the
+headline mode 2 and for modes 0 / 1 / 3 (the AVX2 routines the reference's CLI runs, with their GAF builders) on 100 random
+graphs each with random band / gap / score flags."""
 import importlib.util
 import os
 
@@ -97,3 +99,44 @@ def test_mode2_random_small_graphs(block, tmp_path):
             continue
         assert rc == 0, err
         assert got == exp, f"seed {seed} -b {b} -f {f}:\n PY : {got[:400]}\n C++: {exp[:400]}"
+
+
+# ------------------------------------------------------------------------------------------------- modes 0 / 1 / 3
+@pytest.mark.parametrize("mode", [0, 1, 3])
+def test_poa_modes_example(mode, tmp_path):
+    """exec_simd of modes 0 / 1 (AVX2 semantics, f32 path values decoded through their decimal text), gap_local_poa::exec,
+    and their GAF builders: first example reads, default and one alternative parameter set per mode."""
+    fa_text = open(os.path.join(EXAMPLE, "reads.fa")).read()
+    gfa_text = open(os.path.join(EXAMPLE, "graph.gfa")).read()
+    fa = tmp_path / "r.fa"
+    fa.write_text("\n".join(fa_text.splitlines()[:8]) + "\n")
+    alt = {0: ({"extra_b": 50}, ["-b", "50"]), 1: ({"match": 3, "mismatch": 2}, ["-M", "3", "-X", "2"]),
+           3: ({"gap_open": 10, "gap_ext": 1}, ["-O", "10", "-E", "1"])}[mode]
+    for kw, extra in (({}, []), alt):
+        got = pyref.run_poa(mode, fa.read_text(), gfa_text, **kw)
+        assert got == _oracle(mode, str(fa), os.path.join(EXAMPLE, "graph.gfa"), extra), (mode, extra)
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_poa_modes_random_small_graphs(block, tmp_path):
+    """25 graphs per block x modes 0 (random -b / -f), 1 and 3 (random -O / -E), random match / mismatch scores."""
+    for seed in range(4000 + 25 * block, 4025 + 25 * block):
+        rng = np.random.default_rng(seed)
+        g = synth.make_graph(int(rng.integers(60, 300)), 3, seed=seed, mean_seg=int(rng.integers(3, 12)), p_snp=0.25, p_indel=0.15)
+        reads = synth.make_reads(g, 2, int(rng.integers(10, 100)), err=float(rng.choice([0.0, 0.05, 0.2])), seed=seed + 1)
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        M, X = int(rng.choice([1, 2, 5])), int(rng.choice([1, 4, 7]))
+        b, f = int(rng.choice([1, 2, 5, 30])), float(rng.choice([0.0, 0.01, 0.1, 0.5]))
+        O, E = int(rng.choice([0, 1, 4, 10])), int(rng.choice([1, 2, 5]))
+        for mode, kw, extra in ((0, {"extra_b": b, "extra_f": f}, ["-b", str(b), "-f", str(f)]), (1, {}, []),
+                                (3, {"gap_open": O, "gap_ext": E}, ["-O", str(O), "-E", str(E)])):
+            rc, exp, err = oracle_lib.run_cli(["-m", str(mode), "-M", str(M), "-X", str(X)] + extra + [str(fa), str(gfa)])
+            try:
+                got = pyref.run_poa(mode, fa.read_text(), gfa.read_text(), match=M, mismatch=X, **kw)
+            except (RuntimeError, IndexError, KeyError) as ex:   # inputs on which the reference panics
+                assert rc == 101, f"seed {seed} mode {mode}: pyref says the reference panics ({ex!r}), the oracle exits with {rc}"
+                continue
+            assert rc == 0, f"seed {seed} mode {mode}: {err}"
+            assert got == exp, f"seed {seed} mode {mode} -M {M} -X {X} {extra}:\n PY : {got[:400]}\n C++: {exp[:400]}"
