@@ -23,6 +23,9 @@ and for the other POA modes on an AVX2 machine (what the reference's CLI runs):
   local_poa.rs:10-179, gaf_output.rs:639-751     mode 1: exec_simd, gaf_of_local_poa_simd
   gap_local_poa.rs:8-187, gaf_output.rs:502-637  mode 3: exec (get_best_d / get_best_u with their never-set `first`)
   utils.rs:74-99,129-140                         set_left_right_x64, get_max_d_u_l
+and the -s true flows of modes 0-3 (main.rs:47-252):
+  global_abpoa.rs:260-566, gaf_output.rs:254-382 the scalar exec of mode 0's retry, gaf_of_global_abpoa
+  sequences.rs:64-82, utils.rs:144-165           rev_and_compl, the reversed handle map, strand '-', selection rules
 
 `rev_align` is `align` mirrored in i and j (checked mechanically: sed 's/i + 1/i - 1/; s/j + 1/j - 1/' on lines 129-435
 diffs clean against 436-745 apart from the border cases), so one cell routine parameterised by direction serves both.
@@ -32,6 +35,7 @@ f32 arithmetic uses numpy.float32 so that every operation rounds as in Rust.
 import numpy as np
 
 F32 = np.float32
+_STRAND = ["+"]   # strand field of the POA GAF builders: '-' while a builder runs with amb_mode = true (-s retries)
 
 
 # ------------------------------------------------------------------------------------------------ inputs
@@ -1221,7 +1225,7 @@ def gaf_of_gap_abpoa(path, path_x, path_y, seq, name, ampl, last_row, last_col, 
     hia = dedup(hia)
     hia.reverse()
     comments = ",".join(cigars[:-1])
-    return gaf_string(name, len(seq) - 1, col, last_col + ampl[last_row][0], "+", [int(h) for h in hia], path_length,
+    return gaf_string(name, len(seq) - 1, col, last_col + ampl[last_row][0], _STRAND[0], [int(h) for h in hia], path_length,
                       node_start(hofp, row), node_start(hofp, last_row), residues, "*", "*", comments)
 
 
@@ -1434,7 +1438,7 @@ def gaf_of_global_abpoa_simd(path, seq, name, last_row, last_col, hofp, lnz, bes
     hia = dedup(hia)
     hia.reverse()
     comments = f"{cigar_out}, score: {f32_display(best_score)}\t{''.join(path_sequence)}"
-    return gaf_string(name, len(seq) - 1, col, last_col, "+", [int(x) for x in hia], path_length, node_start(hofp, row),
+    return gaf_string(name, len(seq) - 1, col, last_col, _STRAND[0], [int(x) for x in hia], path_length, node_start(hofp, row),
                       node_start(hofp, last_row), residues, "*", "*", comments) + "\n"
 
 
@@ -1571,7 +1575,7 @@ def _segment_cigar_walk(seq, name, last_row, last_col, hofp, step):
     hia = dedup(hia)
     hia.reverse()
     comments = ",".join(cigars[:len(cigars) - 1])
-    return gaf_string(name, len(seq) - 1, col, last_col, "+", [int(x) for x in hia], path_length, node_start(hofp, row),
+    return gaf_string(name, len(seq) - 1, col, last_col, _STRAND[0], [int(x) for x in hia], path_length, node_start(hofp, row),
                       node_start(hofp, last_row), residues, "*", "*", comments) + "\n"
 
 
@@ -1698,6 +1702,260 @@ def gaf_of_gap_local_poa(path, path_x, path_y, seq, name, last_row, last_col, ho
             return ("U", prd, col, 0, 1, 0, [hofp[row]], 1, 0)
         raise RuntimeError("impossible value in poa path")
     return _segment_cigar_walk(seq, name, last_row, last_col, hofp, step)
+
+
+def _at(row, idx):
+    """checked indexing (a Rust Vec panics where a Python list would wrap around)"""
+    if idx < 0 or idx >= len(row):
+        raise RuntimeError("index out of bounds")
+    return row[idx]
+
+
+def mode0_exec_scalar(seq, name, lnz, nwp, pred, sm, bta, hofp):
+    """global_abpoa.rs:260-427 (the scalar exec: what the -s retry of mode 0 runs); returns (stdout text of the call, score)"""
+    n, L = len(lnz), len(seq)
+    r_values = set_r_values(nwp, pred, n)
+    bsp = [0] * n
+    m, path = [[] for _ in range(n)], [[] for _ in range(n)]
+    ampl = [(0, 0)] * n
+
+    def jpos(p, i, j):
+        lp, li = ampl[p][0], ampl[i][0]
+        return j + (li - lp) if lp < li else j - (lp - li)
+
+    def min_pred(i):
+        return i - 1 if not nwp[i] else min(pred[i])
+
+    for i in range(n - 1):
+        p_arr0 = pred[i] if nwp[i] else []
+        left, right = set_ampl_for_row(i, p_arr0, r_values[i], bsp, L, bta)
+        ampl[i] = (left, right)
+        if right < left:
+            raise RuntimeError("attempt to subtract with overflow")
+        w = right - left
+        m[i] = [0] * w
+        path[i] = [cell(0, "O")] * w
+        best_val_pos = 0
+        for j in range(w):
+            if i == 0 and j == 0:
+                m[i][j] = 0
+                path[i][j] = cell(0, "O")
+            elif i == 0:
+                m[i][j] = m[i][j - 1] + sm[("-", seq[j + left])]
+                path[i][j] = cell(i, "L")
+            elif j == 0 and left == 0:
+                best_p = min_pred(i)
+                m[i][j] = _at(m[best_p], j) + sm[("-", lnz[i])]
+                path[i][j] = cell(best_p, "U")
+            else:
+                p_arr = pred[i] if nwp[i] else [i - 1]
+                if j > 0:      # get_best_l
+                    l, l_pred = m[i][j - 1] + sm[(seq[j + left], "-")], i
+                else:
+                    l, l_pred = sm[(seq[j + left], "-")] * (i + left + j), min_pred(i)
+                # get_best_u (global_abpoa.rs:529-566)
+                u = u_idx = None
+                for q in p_arr:
+                    if ampl[q][0] <= j + left < ampl[q][1]:
+                        cu = _at(m[q], jpos(q, i, j))
+                        if u is None or cu > u:
+                            u, u_idx = cu, q
+                if u is None:
+                    u, u_pred = sm[(lnz[i], "-")] * (i + left + j), min_pred(i)
+                else:
+                    u, u_pred = u + sm[(lnz[i], "-")], u_idx
+                # get_best_d (:487-526)
+                d = d_idx = None
+                for q in p_arr:
+                    if ampl[q][0] < j + left <= ampl[q][1]:
+                        cd = _at(m[q], jpos(q, i, j) - 1)
+                        if d is None or cd > d:
+                            d, d_idx = cd, q
+                if d is None:
+                    d, d_pred = sm[(lnz[i], "-")] * (i + left), min_pred(i)
+                else:
+                    d, d_pred = d + sm[(lnz[i], seq[j + left])], d_idx
+                if d < u:
+                    best_val, dr = (l, "L") if u < l else (u, "U")
+                else:
+                    best_val, dr = (l, "L") if d < l else (d, "D")
+                if dr == "D" and seq[j + left] != lnz[i]:
+                    dr = "d"
+                m[i][j] = best_val
+                path[i][j] = cell(d_pred if dr in "Dd" else (u_pred if dr == "U" else l_pred), dr)
+            if m[i][j] >= m[i][best_val_pos]:
+                best_val_pos = j
+        bsp[i] = best_val_pos + left
+    last_row = n - 2
+    if not m[last_row]:
+        raise RuntimeError("attempt to subtract with overflow")
+    last_col = len(m[last_row]) - 1
+    for q in pred[n - 1]:
+        if ampl[q][1] - ampl[q][0] < 1:
+            raise RuntimeError("attempt to subtract with overflow")
+        tmp = (ampl[q][1] - ampl[q][0]) - 1
+        if m[q][tmp] > m[last_row][last_col]:
+            last_row, last_col = q, tmp
+    out = ""
+    # band_ampl_enough (:428-476)
+    i, j, ok = last_row, last_col, True
+    while _at(path[i], j)[1] != "O":
+        left, right = ampl[i]
+        if i == 0 or (j == 0 and left == 0):
+            break
+        if (j == 0 and left != 0) or (j == right - left - 1 and right != L):
+            ok = False
+            break
+        prd, dr = path[i][j]
+        jp = jpos(prd, i, j)
+        if jp < 0:
+            raise RuntimeError("attempt to subtract with overflow")
+        if dr in "Dd":
+            i, j = prd, jp - 1
+        elif dr == "L":
+            j -= 1
+        elif dr == "U":
+            i, j = prd, jp
+        else:
+            raise RuntimeError("explicit panic")
+        if j < 0:
+            raise RuntimeError("attempt to subtract with overflow")
+    if not ok:
+        out += "Band length probably too short, maybe try with larger b and f\n"
+    return out + gaf_of_global_abpoa(path, seq, name, ampl, last_row, last_col, hofp), m[last_row][last_col]
+
+
+def gaf_of_global_abpoa(path, seq, name, ampl, last_row, last_col, hofp):
+    """gaf_output.rs:254-382"""
+    col, row = last_col, last_row
+    hia, cigars = [], []
+    cigar = ""
+    cm = ci = cd = 0
+    curr_handle, last_dir = "", " "
+    path_length = residues = 0
+    while _at(path[row], col)[1] != "O":
+        prd, dr = path[row][col]
+        if hofp[row] != curr_handle:
+            cigar = set_cigar_substring(cm, ci, cd, cigar)
+            cigars.insert(0, cigar)
+            cigar = ""
+            cm = ci = cd = 0
+        curr_handle = hofp[row]
+        if dr.upper() != last_dir.upper():
+            cigar = set_cigar_substring(cm, ci, cd, cigar)
+            cm = ci = cd = 0
+        last_dir = dr
+        p_left = ampl[prd][0]
+        if ampl[row][0] < p_left:
+            j_pos = col - (p_left - ampl[row][0])
+            if j_pos < 0:
+                raise RuntimeError("attempt to subtract with overflow")
+        else:
+            j_pos = col + (ampl[row][0] - p_left)
+        if dr in "Dd":
+            hia.append(hofp[row])
+            row, col = prd, j_pos - 1
+            cm += 1
+            path_length += 1
+            if dr == "D":
+                residues += 1
+        elif dr == "L":
+            col -= 1
+            cd += 1
+        elif dr == "U":
+            hia.append(hofp[row])
+            row, col = prd, j_pos
+            ci += 1
+            path_length += 1
+        else:
+            raise RuntimeError("impossible value in poa path")
+        if col < 0:
+            raise RuntimeError("attempt to subtract with overflow")
+    cigar = set_cigar_substring(cm, ci, cd, cigar)
+    cigars.insert(0, cigar)
+    hia = dedup(hia)
+    hia.reverse()
+    return gaf_string(name, len(seq) - 1, col, last_col + ampl[last_row][0], _STRAND[0], [int(h) for h in hia], path_length,
+                      node_start(hofp, row), node_start(hofp, last_row), residues, "*", "*", ",".join(cigars[:len(cigars) - 1])) + "\n"
+
+
+def rev_and_compl(seq):
+    """sequences.rs:64-82"""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    return ["$"] + [comp[c] for c in reversed(seq[1:])]
+
+
+def reverse_handle_map(nwp, segs):
+    """utils::create_handle_pos_in_lnz(.., amb_mode = true) (utils.rs:144-165, graph.rs:128-143): the sorted handles
+    reversed (and flipped: the id stays), consumed in lnz order"""
+    ids = sorted(segs, reverse=True)
+    hofp = {0: "-1"}
+    cur = 0
+    for i in range(1, len(nwp) - 1):
+        if nwp[i]:
+            cur += 1
+        hofp[i] = str(ids[cur - 1])
+    return hofp
+
+
+def run_poa_amb(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01):
+    """main.rs:47-252 with -s true on an AVX2 machine (modes 0-3): the forward call, the reverse-complement retry where the
+    mode asks for it, the selection rule of each mode; returns stdout"""
+    seqs, names = read_fasta(fasta_text)
+    segs, _paths = read_gfa(gfa_text)
+    lnz, nwp, pred, hofp = create_graph_struct(segs, read_gfa_links(gfa_text))
+    hofp_rev = reverse_handle_map(nwp, segs)
+    sm = score_matrix_match_mis(match, -mismatch)
+    smf = f32_scores(sm)
+    r_values = set_r_values(nwp, pred, len(lnz))
+    out = ""
+
+    def split(text):      # warnings println!'d during the call, and the record main writes afterwards
+        lines = text.splitlines(keepends=True)
+        return "".join(lines[:-1]), lines[-1]
+
+    def with_strand(strand, fn):
+        _STRAND[0] = strand
+        try:
+            return fn()
+        finally:
+            _STRAND[0] = "+"
+
+    for k, seq in enumerate(seqs):
+        v = F32(F32(extra_b) + F32(F32(extra_f) * F32(len(seq))))
+        bta = 0 if not (v > 0) else int(v)
+        rseq = None
+        if mode == 0:
+            ftext, fs = mode0_exec_simd(seq, names[k], lnz, nwp, pred, smf, bta, hofp, r_values)
+            retry = fs < 0
+            if retry:
+                rtext, rs = with_strand("-", lambda: mode0_exec_scalar(rev_and_compl(seq), names[k], lnz, nwp, pred, sm, bta, hofp_rev))
+                take_rev = rs > fs
+        elif mode == 1:
+            ftext, fs = mode1_exec_simd(seq, names[k], lnz, nwp, pred, smf, hofp)
+            retry = True
+            rtext, rs = with_strand("-", lambda: mode1_exec_simd(rev_and_compl(seq), names[k], lnz, nwp, pred, smf, hofp_rev))
+            take_rev = not (fs < rs)      # main.rs:160-164 writes the FORWARD record when it is the lower one
+        elif mode == 2:
+            ftext, fs = mode2_exec(seq, names[k], lnz, nwp, pred, sm, -gap_open, -gap_ext, bta, hofp)
+            retry = fs < 0
+            if retry:
+                rtext, rs = with_strand("-", lambda: mode2_exec(rev_and_compl(seq), names[k], lnz, nwp, pred, sm, -gap_open, -gap_ext,
+                                                                bta, hofp_rev))
+                take_rev = rs > fs
+        else:
+            ftext, fs = mode3_exec(seq, names[k], lnz, nwp, pred, sm, -gap_open, -gap_ext, hofp)
+            retry = True
+            rtext, rs = mode3_exec(rev_and_compl(seq), names[k], lnz, nwp, pred, sm, -gap_open, -gap_ext, hofp_rev)   # amb_mode = false, main.rs:242
+            take_rev = rs > fs
+        fw, fg = split(ftext)
+        out += fw
+        if retry:
+            rw, rgaf = split(rtext)
+            out += rw + (rgaf if take_rev else fg)
+        else:
+            out += fg
+    return out
 
 
 def run_poa(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01, max_reads=None):

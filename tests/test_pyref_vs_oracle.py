@@ -140,3 +140,43 @@ def test_poa_modes_random_small_graphs(block, tmp_path):
                 continue
             assert rc == 0, f"seed {seed} mode {mode}: {err}"
             assert got == exp, f"seed {seed} mode {mode} -M {M} -X {X} {extra}:\n PY : {got[:400]}\n C++: {exp[:400]}"
+
+
+# ------------------------------------------------------------------------------------------------- -s true (modes 0-3)
+def _amb_case(seed, tmp_path):
+    rng = np.random.default_rng(seed)
+    g = synth.make_graph(int(rng.integers(60, 300)), 3, seed=seed, mean_seg=int(rng.integers(3, 12)), p_snp=0.25, p_indel=0.15)
+    reads = synth.make_reads(g, 3, int(rng.integers(10, 100)), err=float(rng.choice([0.0, 0.05, 0.2])), seed=seed + 1)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    reads[1] = "".join(comp[c] for c in reversed(reads[1]))      # one read from the other strand
+    gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+    gfa.write_text(g.gfa())
+    fa.write_text(synth.fasta(reads))
+    return fa, gfa, rng
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_ambiguous_strand_random_small_graphs(block, tmp_path):
+    """-s true: rev_and_compl, the scalar global_abpoa::exec + gaf_of_global_abpoa of mode 0's retry, the reversed handle
+    map, strand '-', and each mode's selection rule (mode 1 keeps the lower score, mode 3 keeps strand '+')."""
+    for seed in range(6000 + 20 * block, 6020 + 20 * block):
+        fa, gfa, rng = _amb_case(seed, tmp_path)
+        b, f = int(rng.choice([1, 5, 30, 200])), float(rng.choice([0.0, 0.01, 0.3]))
+        O, E = int(rng.choice([0, 4, 10])), int(rng.choice([1, 2, 5]))
+        for mode in (0, 1, 2, 3):
+            extra = ["-s", "true"]
+            kw = {}
+            if mode in (0, 2):
+                extra += ["-b", str(b), "-f", str(f)]
+                kw.update(extra_b=b, extra_f=f)
+            if mode in (2, 3):
+                extra += ["-O", str(O), "-E", str(E)]
+                kw.update(gap_open=O, gap_ext=E)
+            rc, exp, err = oracle_lib.run_cli(["-m", str(mode)] + extra + [str(fa), str(gfa)])
+            try:
+                got = pyref.run_poa_amb(mode, fa.read_text(), gfa.read_text(), **kw)
+            except (RuntimeError, IndexError, KeyError) as ex:
+                assert rc == 101, f"seed {seed} mode {mode}: pyref says the reference panics ({ex!r}), the oracle exits with {rc}"
+                continue
+            assert rc == 0, f"seed {seed} mode {mode}: {err}"
+            assert got == exp, f"seed {seed} mode {mode} {extra}:\n PY : {got[:500]}\n C++: {exp[:500]}"
