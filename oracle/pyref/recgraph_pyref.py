@@ -26,6 +26,9 @@ and for the other POA modes on an AVX2 machine (what the reference's CLI runs):
 and the -s true flows of modes 0-3 (main.rs:47-252):
   global_abpoa.rs:260-566, gaf_output.rs:254-382 the scalar exec of mode 0's retry, gaf_of_global_abpoa
   sequences.rs:64-82, utils.rs:144-165           rev_and_compl, the reversed handle map, strand '-', selection rules
+and the experimental affine pathwise modes 6 / 7:
+  pathwise_alignment_gap.rs:4-574, pathwise_alignment_gap_semi.rs:5-473   exec (delta-encoded dpm / x / y), best_ending_node
+  pathwise_alignment_output.rs:186-451           build_alignment_gap, build_alignment_semiglobal_gap; main.rs:271-288
 
 `rev_align` is `align` mirrored in i and j (checked mechanically: sed 's/i + 1/i - 1/; s/j + 1/j - 1/' on lines 129-435
 diffs clean against 436-745 apart from the border cases), so one cell routine parameterised by direction serves both.
@@ -1979,6 +1982,347 @@ def run_poa(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext
         else:
             text, _ = mode3_exec(seq, names[k], lnz, nwp, pred, sm, -gap_open, -gap_ext, hofp)
         out += text
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ modes 6 / 7
+def gap_pathwise_exec(seq, g, sm, o, e, semi):
+    """pathwise_alignment_gap.rs:4-574 (semi = False) / pathwise_alignment_gap_semi.rs:5-473 (semi = True): the two files
+    share the interior cell code word for word (diff: the `(_, 0)` arm and the ending). Returns (cigar line, best path).
+    The three tensors hold the reference's delta encoding: the alpha path's entry is absolute, every other entry is
+    relative to it."""
+    lnz, nwp, alphas, P, pn = g.lnz, g.nwp, g.alphas, g.P, g.pn
+    n, L = len(lnz), len(seq)
+    dpm = [[[0] * P for _ in range(L)] for _ in range(n)]
+    x = [[[0] * P for _ in range(L)] for _ in range(n)]
+    y = [[[0] * P for _ in range(L)] for _ in range(n)]
+
+    def fix_multiple_alphas(i, j, alphas_deltas, tensors):
+        # "remove multiple alpha": every group but the one of alphas[i] is re-expressed relative to alphas[i]
+        ai = alphas[i]
+        for a, delta in alphas_deltas.items():
+            if a != ai:
+                for t in tensors:
+                    t[i][j][a] -= t[i][j][ai]
+                for path in delta:
+                    if path != a:
+                        for t in tensors:
+                            t[i][j][path] += t[i][j][a]
+
+    for i in range(n - 1):
+        ai = alphas[i]
+        for j in range(L):
+            if i == 0 and j == 0:
+                continue
+            if semi and j == 0:
+                continue                      # `(_, 0) => dpm[0][0] = vec![0; path_number]`: no effect
+            if i == 0:
+                a0 = alphas[0]
+                y[i][j][a0] = o + e * j
+                dpm[i][j][a0] = y[i][j][a0]
+                for k in range(a0 + 1, P):
+                    y[i][j][k] = y[i][j - 1][k]
+                    dpm[i][j][k] = y[i][j][k]
+                continue
+            if j == 0:                        # first column of the global mode (pathwise_alignment_gap.rs:35-149)
+                if not nwp[i]:
+                    common = sorted(pn[i] & pn[i - 1])
+                    if alphas[i - 1] in common:
+                        for path in common:
+                            if path == ai:
+                                x[i][j][path] = o + e if i == 1 else x[i - 1][j][path] + e
+                            else:
+                                x[i][j][path] = x[i - 1][j][path]
+                            dpm[i][j][path] = x[i][j][path]
+                    else:
+                        x[i][j][ai] = x[i - 1][j][ai] + x[i - 1][j][alphas[i - 1]] + e if i != 1 else o + e
+                        dpm[i][j][ai] = x[i][j][ai]
+                        for path in common:
+                            if path != ai:
+                                x[i][j][path] = x[i - 1][j][path] - x[i - 1][j][ai]
+                                dpm[i][j][path] = x[i][j][path]
+                else:
+                    alphas_deltas = {}
+                    for q, q_paths in preds_and_paths(g, i):
+                        common = sorted(pn[i] & q_paths)
+                        aq = alphas[q]
+                        if aq in common:
+                            alphas_deltas[aq] = common
+                            x[i][j][aq] = o + e if q == 0 else x[q][j][aq] + e
+                            dpm[i][j][aq] = x[i][j][aq]
+                            for path in common:
+                                if path != aq:
+                                    x[i][j][path] = x[q][j][path]
+                                    dpm[i][j][path] = x[i][j][path]
+                        else:
+                            if not common:
+                                raise RuntimeError("position(|is_in| is_in).unwrap() on None")
+                            ta = ai if ai in common else common[0]
+                            alphas_deltas[ta] = common
+                            x[i][j][ta] = o + e if q == 0 else x[q][j][ta] + x[q][j][aq] + e
+                            dpm[i][j][ta] = x[i][j][ta]
+                            for path in common:
+                                if path != ta:
+                                    x[i][j][path] = x[q][j][path] - x[q][j][ta]
+                                    dpm[i][j][path] = x[i][j][path]
+                    # here only x is adjusted and dpm re-copied from it (:134-147)
+                    for a, delta in alphas_deltas.items():
+                        if a != ai:
+                            x[i][j][a] -= x[i][j][ai]
+                            dpm[i][j][a] = x[i][j][a]
+                            for path in delta:
+                                if path != a:
+                                    x[i][j][path] += x[i][j][a]
+                                    dpm[i][j][path] = x[i][j][path]
+                continue
+            s = sm[(lnz[i], seq[j])]
+            if not nwp[i]:
+                ap = alphas[i - 1]
+                common = sorted(pn[i] & pn[i - 1])
+                same = ap in common
+                # set y
+                if same:
+                    u_y = y[i - 1][j][ap] + e
+                    u_dpm = dpm[i - 1][j][ap] + o + e
+                else:
+                    u_y = y[i - 1][j][ap] + y[i - 1][j][ai] + e
+                    u_dpm = dpm[i - 1][j][ap] + dpm[i - 1][j][ai] + o + e
+                src = dpm if u_dpm >= u_y else y
+                for path in common:
+                    if path != ai:
+                        y[i][j][path] = src[i - 1][j][path] if same else src[i - 1][j][path] - src[i - 1][j][ai]
+                y[i][j][ai] = u_dpm if u_dpm >= u_y else u_y
+                u = y[i][j][ai]
+                # set x
+                l_x = x[i][j - 1][ai] + e
+                l_dpm = dpm[i][j - 1][ai] + o + e
+                src = dpm if l_dpm >= l_x else x
+                for path in common:
+                    if path != ai:
+                        x[i][j][path] = src[i][j - 1][path]
+                x[i][j][ai] = l_dpm if l_dpm >= l_x else l_x
+                l = x[i][j][ai]
+                # set dpm
+                d = dpm[i - 1][j - 1][ap] + s if same else dpm[i - 1][j - 1][ap] + dpm[i - 1][j - 1][ai] + s
+                best = max(d, u, l)
+                dpm[i][j][ai] = best
+                for path in common:
+                    if path != ai:
+                        if best == d:
+                            dpm[i][j][path] = dpm[i - 1][j - 1][path] if same else dpm[i - 1][j - 1][path] - dpm[i - 1][j - 1][ai]
+                        elif best == u:
+                            dpm[i][j][path] = y[i][j][path]
+                        else:
+                            dpm[i][j][path] = x[i][j][path]
+                continue
+            # several predecessors: every incoming edge keeps its own alpha first
+            alphas_deltas = {}
+            for q, q_paths in preds_and_paths(g, i):
+                common = sorted(pn[i] & q_paths)
+                aq = alphas[q]
+                if aq in common:
+                    alphas_deltas[aq] = common
+                    u_y = y[q][j][aq] + e
+                    u_dpm = dpm[q][j][aq] + o + e
+                    if u_dpm >= u_y:
+                        for path in common:
+                            if path != aq:
+                                y[i][j][path] = dpm[q][j][path]
+                        y[i][j][aq] = u_dpm
+                    else:
+                        for path in common:
+                            if path != ai:            # alphas[i], not alphas[p] (pathwise_alignment_gap.rs:338)
+                                y[i][j][path] = y[q][j][path]
+                        y[i][j][aq] = u_y
+                    u = y[i][j][aq]
+                    if aq == ai:
+                        l_x = x[i][j - 1][aq] + e
+                        l_dpm = dpm[i][j - 1][aq] + o + e
+                    else:
+                        l_x = x[i][j - 1][aq] + x[i][j - 1][ai] + e
+                        l_dpm = dpm[i][j - 1][ai] + dpm[i][j - 1][aq] + o + e
+                    src = dpm if l_dpm >= l_x else x
+                    for path in common:
+                        if path != aq:
+                            x[i][j][path] = src[i][j - 1][path] if aq == ai else src[i][j - 1][path] - src[i][j - 1][aq]
+                    x[i][j][aq] = l_dpm if l_dpm >= l_x else l_x
+                    l = x[i][j][aq]
+                    d = dpm[q][j - 1][aq] + s
+                    best = max(d, u, l)
+                    dpm[i][j][aq] = best
+                    for path in common:
+                        if path != aq:
+                            if best == d:
+                                dpm[i][j][path] = dpm[q][j - 1][path]
+                            elif best == u:
+                                dpm[i][j][path] = y[i][j][path]
+                            else:
+                                dpm[i][j][path] = x[i][j][path]
+                else:
+                    if not common:
+                        raise RuntimeError("position(|is_in| is_in).unwrap() on None")
+                    ta = ai if ai in common else common[0]
+                    alphas_deltas[ta] = common
+                    u_y = y[q][j][aq] + y[q][j][ta] + e
+                    u_dpm = dpm[q][j][aq] + dpm[q][j][ta] + o + e
+                    src = dpm if u_dpm >= u_y else y
+                    for path in common:
+                        if path != ta:
+                            y[i][j][path] = src[q][j][path] - src[q][j][ta]
+                    y[i][j][ta] = u_dpm if u_dpm >= u_y else u_y
+                    u = y[i][j][ta]
+                    if ai == ta:
+                        l_x = x[i][j - 1][ai] + e
+                        l_dpm = dpm[i][j - 1][ai] + o + e
+                    else:
+                        l_x = x[i][j - 1][ai] + x[i][j - 1][ta] + e
+                        l_dpm = dpm[i][j - 1][ai] + dpm[i][j - 1][ta] + o + e
+                    src = dpm if l_dpm >= l_x else x
+                    for path in common:
+                        if path != ta:
+                            x[i][j][path] = src[i][j - 1][path] if ta == ai else src[i][j - 1][path] - src[i][j - 1][ta]
+                    x[i][j][ta] = l_dpm if l_dpm >= l_x else l_x
+                    l = x[i][j][ta]
+                    d = dpm[q][j - 1][aq] + dpm[q][j - 1][ta] + s
+                    best = max(d, u, l)
+                    dpm[i][j][ta] = best
+                    for path in common:
+                        if path != ta:
+                            if best == d:
+                                dpm[i][j][path] = dpm[q][j - 1][path] - dpm[q][j - 1][ta]
+                            elif best == u:
+                                dpm[i][j][path] = y[i][j][path]
+                            else:
+                                dpm[i][j][path] = x[i][j][path]
+            fix_multiple_alphas(i, j, alphas_deltas, (dpm, x, y))
+
+    if not semi:
+        results = [0] * P
+        for q, paths in preds_and_paths(g, n - 1):
+            for path in sorted(paths):
+                if path == alphas[q]:
+                    results[path] = dpm[q][L - 1][path]
+                else:
+                    results[path] = dpm[q][L - 1][path] + dpm[q][L - 1][alphas[q]]
+        best_path = max((sc, path) for path, sc in enumerate(results))[1]
+        end = 0
+        for q, paths in preds_and_paths(g, n - 1):
+            if best_path in paths:
+                end = q
+    else:
+        # best_ending_node (pathwise_alignment_gap_semi.rs:448-473): every one of the P slots competes, the ones that
+        # are not on the node with whatever they hold
+        mx = None
+        end = best_path = 0
+        for i in range(n - 1):
+            ab = list(dpm[i][L - 1])
+            for path in sorted(pn[i]):
+                if path != alphas[i]:
+                    ab[path] = ab[path] + ab[alphas[i]]
+            sc, path = max((sc, path) for path, sc in enumerate(ab))
+            if mx is None or sc > mx:
+                mx, end, best_path = sc, i, path
+    return _build_alignment_gap(dpm, x, y, g, best_path, end, semi), best_path
+
+
+def _build_alignment_gap(dpm, x, y, g, bp, ending_node, semi):
+    """pathwise_alignment_output.rs:186-316 (build_alignment_gap) / :318-451 (build_alignment_semiglobal_gap): the walks
+    are identical, the tails differ. The gap-chain tests compare RAW tensor entries (`dpm[i][j][bp] < y[i][j][bp]`)."""
+    nwp, alphas = g.nwp, g.alphas
+
+    def absolute(t, i, j):
+        return t[i][j][bp] if alphas[i] == bp else t[i][j][bp] + t[i][j][alphas[i]]
+
+    def pred_on_path(i):
+        found = None
+        for q, paths in preds_and_paths(g, i):
+            if bp in paths:
+                found = q
+        return found
+
+    cigar = []
+    i = ending_node
+    j = len(dpm[i]) - 1
+    while i != 0 and j != 0:
+        curr = absolute(dpm, i, j)
+        predecessor = None
+        if not nwp[i]:
+            d, u, l = absolute(dpm, i - 1, j - 1), absolute(dpm, i - 1, j), absolute(dpm, i, j - 1)
+        else:
+            d = u = l = 0
+            for q, paths in preds_and_paths(g, i):
+                if bp in paths:
+                    predecessor = q
+                    d, u = absolute(dpm, q, j - 1), absolute(dpm, q, j)
+                    l = absolute(dpm, i, j - 1)
+        mx = max(d, u, l)
+        if mx == d:
+            cigar.append("d" if curr < d else "D")
+            i = i - 1 if predecessor is None else predecessor
+            j -= 1
+        elif mx == u:
+            cigar.append("U")
+            i = i - 1 if predecessor is None else predecessor
+            while dpm[i][j][bp] < y[i][j][bp]:
+                cigar.append("U")
+                if nwp[i]:
+                    q = pred_on_path(i)
+                    if q is None and predecessor is None:
+                        raise RuntimeError("called `Option::unwrap()` on a `None` value")
+                    if q is None:
+                        raise RuntimeError("the reference loops forever here (no predecessor on the best path)")
+                    predecessor = q
+                else:
+                    predecessor = i - 1
+                i = predecessor
+        else:
+            cigar.append("L")
+            j -= 1
+            while dpm[i][j][bp] < x[i][j][bp]:
+                cigar.append("L")
+                j -= 1
+                if j < 0:
+                    raise RuntimeError("attempt to subtract with overflow")
+    while j > 0:
+        cigar.append("L")
+        j -= 1
+    if not semi:
+        while i > 0:
+            cigar.append("U")
+            i -= 1
+        cigar.reverse()
+        if cigar:
+            cigar.pop()
+        return build_cigar(cigar)
+    cigar.reverse()
+
+    def count_back(i):
+        steps = 0
+        while i > 0:
+            if nwp[i]:
+                q = pred_on_path(i)
+                if q is None:
+                    raise RuntimeError("the reference loops forever here (no predecessor on the best path)")
+                i = q
+            else:
+                i -= 1
+            steps += 1
+        return steps
+    starting_node = count_back(i)
+    final_node = count_back(ending_node)
+    return f"{build_cigar(cigar)}\t({starting_node} {final_node})"
+
+
+def run_gap_pathwise(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2):
+    """main.rs:271-288 (modes 6 / 7); returns stdout"""
+    seqs, names = read_fasta(fasta_text)
+    segs, paths = read_gfa(gfa_text)
+    sm = score_matrix_match_mis(match, -mismatch)
+    g = create_path_graph(segs, paths)
+    out = ""
+    for k, seq in enumerate(seqs):
+        cigar, best_path = gap_pathwise_exec(seq, g, sm, -gap_open, -gap_ext, mode == 7)
+        out += f"{cigar}\nBest path sequence {k}: {best_path}\n"
     return out
 
 

@@ -4,7 +4,8 @@ checker of the CUDA path) against a SECOND, independent restatement written in P
 `best_alignment` of modes 8 / 9, `build_alignment`, the four `gaf_output_*` builders, path-length helpers and GAF text.
 Byte-identical stdout on the example and on 220 random small graphs (single source and sink); the same for the
 headline mode 2 and for modes 0 / 1 / 3 (the AVX2 routines the reference's CLI runs, with their GAF builders) on 100 random
-graphs each with random band / gap / score flags."""
+graphs each with random band / gap / score flags, for the -s true flows of modes 0-3, and for the experimental affine
+pathwise modes 6 / 7: every mode of the reference is read twice."""
 import importlib.util
 import os
 
@@ -180,3 +181,40 @@ def test_ambiguous_strand_random_small_graphs(block, tmp_path):
                 continue
             assert rc == 0, f"seed {seed} mode {mode}: {err}"
             assert got == exp, f"seed {seed} mode {mode} {extra}:\n PY : {got[:500]}\n C++: {exp[:500]}"
+
+
+# ------------------------------------------------------------------------------------------------- modes 6 / 7
+@pytest.mark.parametrize("mode", [6, 7])
+def test_gap_pathwise_example(mode, tmp_path):
+    fa_text = open(os.path.join(EXAMPLE, "reads.fa")).read()
+    gfa_text = open(os.path.join(EXAMPLE, "graph.gfa")).read()
+    fa = tmp_path / "r.fa"
+    fa.write_text("\n".join(fa_text.splitlines()[:4]) + "\n")
+    for kw, extra in (({}, []), ({"gap_open": 10, "gap_ext": 1}, ["-O", "10", "-E", "1"])):
+        got = pyref.run_gap_pathwise(mode, fa.read_text(), gfa_text, **kw)
+        assert got == _oracle(mode, str(fa), os.path.join(EXAMPLE, "graph.gfa"), extra), (mode, extra)
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_gap_pathwise_random_small_graphs(block, tmp_path):
+    """The experimental affine pathwise modes: the delta-encoded tensors of pathwise_alignment_gap(_semi).rs with their
+    `alphas[i]` / `alphas[p]` inconsistency, raw-entry gap tests of the builders, every-slot best_ending_node; 20 graphs
+    per block x modes 6, 7, random -O / -E."""
+    for seed in range(1000 + 20 * block, 1020 + 20 * block):
+        g, reads = _case(seed)
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        rng = np.random.default_rng(seed + 77)
+        O, E = int(rng.choice([0, 1, 4, 10])), int(rng.choice([1, 2, 5]))
+        for mode in (6, 7):
+            rc, exp, err = oracle_lib.run_cli(["-m", str(mode), "-O", str(O), "-E", str(E), str(fa), str(gfa)])
+            try:
+                got = pyref.run_gap_pathwise(mode, fa.read_text(), gfa.read_text(), gap_open=O, gap_ext=E)
+            except (RuntimeError, IndexError, KeyError) as ex:
+                assert rc == 101, f"seed {seed} mode {mode}: pyref says the reference panics / hangs ({ex!r}), the oracle exits with {rc}"
+                continue
+            if rc == 101:      # the oracle stops at the first read the reference dies on; everything before must agree
+                assert got.startswith(exp), f"seed {seed} mode {mode}: oracle died, pyref did not:\n PY : {got[:300]}\n C++: {exp[:300]}"
+                raise AssertionError(f"seed {seed} mode {mode}: the oracle reports a reference panic, pyref completes")
+            assert got == exp, f"seed {seed} mode {mode} -O {O} -E {E}:\n PY : {got[:400]}\n C++: {exp[:400]}"
