@@ -10,6 +10,10 @@ from recgraph_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
+# RG_RANDOM_SEED_OFFSET=<n> shifts every seed range below: the same tests on fresh graphs (bug hunting, not part of the fixed suite)
+import os as _os
+SEED0 = int(_os.environ.get("RG_RANDOM_SEED_OFFSET", "0"))
+
 
 def _both(args):
     from recgraph_b200 import run_cli
@@ -36,7 +40,7 @@ def _pathwise_case(seed):   # == tests/test_pyref_vs_oracle.py::_case
 
 @pytest.mark.parametrize("block", range(24))   # blocks 0-10 are the seeds the Python restatement is diffed on, 11-23 more of the same
 def test_pathwise_and_recombination_random_small_graphs(block, tmp_path):
-    for seed in range(1000 + 20 * block, 1020 + 20 * block):
+    for seed in range(SEED0 + 1000 + 20 * block, SEED0 + 1020 + 20 * block):
         g, reads = _pathwise_case(seed)
         gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
         gfa.write_text(g.gfa())
@@ -55,7 +59,7 @@ def test_pathwise_and_recombination_random_small_graphs(block, tmp_path):
 @pytest.mark.parametrize("block", range(12))   # blocks 0-3 are the seeds the Python restatement is diffed on
 def test_mode2_random_small_graphs_random_bands(block, tmp_path):
     panics = 0
-    for seed in range(3000 + 25 * block, 3025 + 25 * block):   # == test_pyref_vs_oracle.py::test_mode2_random_small_graphs
+    for seed in range(SEED0 + 3000 + 25 * block, SEED0 + 3025 + 25 * block):   # == test_pyref_vs_oracle.py::test_mode2_random_small_graphs
         rng = np.random.default_rng(seed)
         g = synth.make_graph(int(rng.integers(60, 400)), 3, seed=seed, mean_seg=int(rng.integers(3, 12)), p_snp=0.25, p_indel=0.15)
         reads = synth.make_reads(g, 2, int(rng.integers(10, 120)), err=float(rng.choice([0.0, 0.05, 0.2])), seed=seed + 1)
@@ -97,7 +101,7 @@ def test_mode2_zero_width_band_blocked_and_striped_kernels(tmp_path):
 @pytest.mark.parametrize("block", range(40))   # blocks 30 and 38 hold inputs whose traceback panics after the band warning
 def test_poa_modes_random_flags(block, tmp_path):
     """Modes 0-3 with random band, scoring, matrix and strand flags on random small graphs (25 per block)."""
-    for seed in range(5000 + 25 * block, 5025 + 25 * block):
+    for seed in range(SEED0 + 5000 + 25 * block, SEED0 + 5025 + 25 * block):
         rng = np.random.default_rng(seed)
         g = synth.make_graph(int(rng.integers(60, 500)), int(rng.integers(2, 6)), seed=seed, mean_seg=int(rng.integers(3, 14)),
                              p_snp=0.25, p_indel=0.15)
@@ -149,7 +153,7 @@ def _pathwise_flag_case(seed, tmp_path):
 @pytest.mark.parametrize("block", range(24))
 def test_pathwise_modes_random_flags(block, tmp_path):
     """Modes 4-9 with random scoring, matrices, gap and recombination parameters, 2-12 paths (25 graphs per block)."""
-    for seed in range(7000 + 25 * block, 7025 + 25 * block):
+    for seed in range(SEED0 + 7000 + 25 * block, SEED0 + 7025 + 25 * block):
         args = _pathwise_flag_case(seed, tmp_path)
         _same(args, f"seed {seed}: {' '.join(args[:-2])}")
 
@@ -176,6 +180,6 @@ def test_poa_mid_size_graphs_random_bands_and_scores(block, tmp_path):
     """1-7 kbp graphs, reads of 60-1000 bases: long runs of packed full-band rows with gather rows in between (mode 2), band
     amplitudes from 1 to the whole read — what decides whether the packed rows keep the exact column of the row maximum or a
     lower bound — and scores on both sides of the packed rows' domain (|score| <= 30)."""
-    for seed in range(9000 + 8 * block, 9008 + 8 * block):
+    for seed in range(SEED0 + 9000 + 8 * block, SEED0 + 9008 + 8 * block):
         args = _mid_case(seed, tmp_path)
         _same(args, f"seed {seed}: {' '.join(args[:-2])}")
