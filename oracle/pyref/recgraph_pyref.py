@@ -33,7 +33,9 @@ and the experimental affine pathwise modes 6 / 7:
 `rev_align` is `align` mirrored in i and j (checked mechanically: sed 's/i + 1/i - 1/; s/j + 1/j - 1/' on lines 129-435
 diffs clean against 436-745 apart from the border cases), so one cell routine parameterised by direction serves both.
 HashMap iteration orders of the reference (predecessors of a node) are fixed to ascending predecessor index.
-f32 arithmetic uses numpy.float32 so that every operation rounds as in Rust.
+f32 arithmetic uses numpy.float32 so that every operation rounds as in Rust. Integer overflow follows a RELEASE build (the
+reference is built with `cargo build --release`): it wraps; a RuntimeError is raised only where the wrapped value is certain to
+panic next (a `vec![..; huge]` capacity overflow, an index out of bounds) — bounds checks stay on in release builds.
 """
 import numpy as np
 
@@ -1251,10 +1253,10 @@ def run_mode2(fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, 
 
 # ------------------------------------------------------------------------------------------------ modes 0 / 1 / 3
 def set_left_right_x64(left, right, seq_len):
-    """utils.rs:74-99 (usize arithmetic: a negative intermediate is the reference's subtract-overflow panic)"""
+    """utils.rs:74-99. usize arithmetic of a RELEASE build (`cargo build --release`, no overflow checks: README, Cargo.toml):
+    `new_right - 1` with new_right = 0 wraps, and only its residue modulo 8 is used — Python's `%` of a negative number gives
+    the same residue, 2^64 being a multiple of 8."""
     nr, nl = right, left
-    if nr < nl:
-        raise RuntimeError("attempt to subtract with overflow")
     while (nr - nl) % 8 != 0:
         if (nr - nl) % 2 == 0 and nr < seq_len:
             nr += 1
@@ -1263,8 +1265,6 @@ def set_left_right_x64(left, right, seq_len):
         else:
             break
     if nl == 0:
-        if nr == 0:
-            raise RuntimeError("attempt to subtract with overflow")
         while (nr - 1) % 8 != 0 and nr < seq_len:
             nr += 1
     if nr == seq_len:
