@@ -152,3 +152,14 @@ def test_sharded_driver_two_devices(mode, tmp_path):
     o = tmp_path / "out.gaf"
     three = run_cli(["-m", mode, "--gpus", "2", "-o", str(o), str(fa), str(gfa)])
     assert three[0] == 0
+
+
+def test_mode0_zero_band_amplitude_is_refused_not_answered(tmp_path):
+    """b + f * L < 1 gives mode 0 rows of one cell or none; the device routines of mode 0 differ from the oracle there
+    (tools/one_off_mode0_b0.py), so that domain is refused (exit code 3, RG_ERR_UNSUPPORTED) instead of answered. Mode 2 handles
+    it exactly (tests/test_gpu_random_graphs.py::test_mode2_zero_width_band_blocked_and_striped_kernels)."""
+    from recgraph_b200 import run_cli
+    rc, out, err = run_cli(["-m", "0", "-b", "0", "-f", "0.0", EX[0], EX[1]])
+    assert rc == 3 and out == "" and "band amplitude of 0" in err, (rc, err[-200:])
+    rc, out, err = run_cli(["-m", "0", "-b", "1", "-f", "0.0", EX[0], EX[1]])
+    assert rc == 0, err[-200:]
