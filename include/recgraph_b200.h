@@ -60,7 +60,9 @@ typedef struct rg_scoring {
  * `exec` variants are RG_MODE_GLOBAL_SCALAR (global_abpoa::exec, global_abpoa.rs:260-427: the `-s` retry of mode 0,
  * main.rs:89-97) and RG_MODE_LOCAL_SCALAR (local_poa::exec, reached only on hosts without AVX2).
  * Device status: every mode runs on the GPU (6 / 7, experimental in the reference, keep its n x L x P tensors per read in
- * flight); inputs outside a kernel's documented domain return RG_ERR_UNSUPPORTED — there is no CPU fallback. */
+ * flight); inputs outside a kernel's documented domain return RG_ERR_UNSUPPORTED — there is no CPU fallback. The domain:
+ * characters A,C,G,T,N; in-degree <= 31 (modes 0/1/3) / 64 (mode 2); <= 128 paths; reads <= 1023 bases in modes 0/1/3 and
+ * <= 12 287 bases through the fast pathwise kernel; mode 0 needs a band amplitude b + f * read length >= 1. */
 enum {
     RG_MODE_GLOBAL = 0,
     RG_MODE_LOCAL = 1,
