@@ -975,6 +975,19 @@ def set_ampl_for_row(i, p_arr, r_val, bsp, seq_len, bta):
     return band_start, band_end
 
 
+class _Row(list):
+    """a Rust Vec: an index below 0 (a wrapped usize) is out of bounds and panics; a Python list would wrap it around"""
+    def __getitem__(self, k):
+        if isinstance(k, int) and k < 0:
+            raise IndexError("index out of bounds")
+        return list.__getitem__(self, k)
+
+    def __setitem__(self, k, v):
+        if isinstance(k, int) and k < 0:
+            raise IndexError("index out of bounds")
+        list.__setitem__(self, k, v)
+
+
 def cell(pred, d):
     """bitfield_path.rs:39-44: the predecessor is truncated to 16 bits"""
     return (pred & 0xffff, d)
@@ -998,10 +1011,11 @@ def mode2_exec(seq, name, lnz, nwp, pred, sm, o, e, bta, hofp):
         left, right = set_ampl_for_row(i, p_arr, r_values[i], bsp, L, bta)
         ampl[i] = (left, right)
         W = right - left
-        if W <= 0:
-            raise RuntimeError("empty band row (the reference panics)")
-        m[i], x[i], y[i] = [0] * W, [0] * W, [0] * W
-        path[i], path_x[i], path_y[i] = [(0, "O")] * W, [(0, "O")] * W, [(0, "O")] * W
+        if W < 0:
+            raise RuntimeError("vec![0; right - left] with a wrapped length: capacity overflow")
+        # W == 0: a row without cells is legal (gap_global_abpoa.rs:59-67); whoever indexes it later panics
+        m[i], x[i], y[i] = _Row([0] * W), _Row([0] * W), _Row([0] * W)
+        path[i], path_x[i], path_y[i] = _Row([(0, "O")] * W), _Row([(0, "O")] * W), _Row([(0, "O")] * W)
         best = 0
         for j in range(W):
             if i == 0 and j == 0:

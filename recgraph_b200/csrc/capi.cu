@@ -637,7 +637,7 @@ static int align_poa(rg_ctx* c, int mode) {
                 return c->fail(RG_ERR_UNSUPPORTED, "modes 0/1 need one gap score for all characters (true for every matrix the reference builds)");
     if (mode == RG_MODE_GLOBAL || mode == RG_MODE_GLOBAL_SCALAR) {
         // Band amplitude 0 (b + f * L < 1, main.rs:57): rows of one cell or none. Mode 2 handles them exactly as the reference
-        // (tests/test_gpu_random_graphs.py); the device routines of mode 0 were found to differ from the oracle there
+        // (tests/test_gpu_random_graphs.py); the device routines of mode 0 were found to differ from the expected output there
         // (tools/one_off_mode0_b0.py) and refuse that domain instead of answering.
         for (size_t i = 0; i + 1 < c->h_off.size(); i++) {
             const uint32_t L = (uint32_t)(c->h_off[i + 1] - c->h_off[i]) + 1;
