@@ -11,7 +11,7 @@ the CUDA path — is itself checked by a second reading of the reference for the
   pathwise_alignment_recombination.rs:9-897      exec, rev_align, align, absolute_scores, best_alignment, ending_node
   recombination_output.rs:12-782                 the four gaf_output_* builders
   utils.rs:221-323, gaf_output.rs:70-94          get_path_len_start_end, get_rec_path_len_start_end, GAFStruct::to_string
-  score_matrix.rs:35-51, sequences.rs:5-45, main.rs:253-312
+  score_matrix.rs:21-51,67-105 (match / mismatch and the two matrix files), sequences.rs:5-45, main.rs:253-312
 and, for the headline mode 2 whose traceback the reference's unit tests do not pin either:
   graph.rs:31-123, utils.rs:17-72,103-165      create_graph_struct, set_ampl_for_row, set_r_values, handle map
   gap_global_abpoa.rs:11-455                     exec, get_best_d / u / l, band_ampl_enough
@@ -87,6 +87,50 @@ def score_matrix_match_mis(m, x):
     sm[("N", "N")] = x
     del sm[("-", "-")]
     return sm
+
+
+# the two matrix files shipped with the reference (HOXD70.mtx, HOXD55.mtx), transcribed; note (G, T) != (T, G) in HOXD70
+_MTX = {
+    "HOXD70": """    A       C       G       T       N
+A   91      -114    -31     -123    0
+C   -114    100     -125    -31     0
+G   -31     -125    100     -114    0
+T   -123    -31     -144    91      0
+N   0       0       0       0       0
+""",
+    "HOXD55": """    A       C       G       T       N
+A   91      -90     -25     -100    0
+C   -90     100     -100    -25     0
+G   -25     -100    100     -90     0
+T   -100    -25     -90     91      0
+N   0       0       0       0       0
+""",
+}
+
+
+def score_matrix_from_matrix_file(name):
+    """score_matrix.rs:67-105: key (row character, column character)"""
+    matrix = [[e for e in line.split(" ") if e != ""] for line in _MTX[name].splitlines()]
+    matrix[0].insert(0, "X")
+    sm = {}
+    for i in range(1, len(matrix)):
+        for j in range(1, len(matrix[0])):
+            sm[(matrix[i][0][0], matrix[0][j][0])] = int(matrix[i][j])
+    for ch in "ACGTN":
+        sm[(ch, "-")] = -200
+        sm[("-", ch)] = -200
+    sm.pop(("-", "-"), None)
+    return sm
+
+
+def _scores(match, mismatch, matrix):
+    """score_matrix.rs:21-34"""
+    if matrix in ("HOXD70", "HOXD70.mtx"):
+        return score_matrix_from_matrix_file("HOXD70")
+    if matrix in ("HOXD55", "HOXD55.mtx"):
+        return score_matrix_from_matrix_file("HOXD55")
+    assert matrix in (None, "none"), "wrong matrix type"
+    return score_matrix_match_mis(match, -mismatch)
 
 
 # ------------------------------------------------------------------------------------------------ graph
@@ -1248,12 +1292,12 @@ def gaf_of_gap_abpoa(path, path_x, path_y, seq, name, ampl, last_row, last_col, 
                       node_start(hofp, row), node_start(hofp, last_row), residues, "*", "*", comments)
 
 
-def run_mode2(fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01, max_reads=None):
+def run_mode2(fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01, max_reads=None, matrix=None):
     """main.rs:171-214 without -s; returns stdout"""
     seqs, names = read_fasta(fasta_text)
     segs, _paths = read_gfa(gfa_text)
     lnz, nwp, pred, hofp = create_graph_struct(segs, read_gfa_links(gfa_text))
-    sm = score_matrix_match_mis(match, -mismatch)
+    sm = _scores(match, mismatch, matrix)
     out = ""
     for k, seq in enumerate(seqs):
         if max_reads is not None and k >= max_reads:
@@ -1915,14 +1959,14 @@ def reverse_handle_map(nwp, segs):
     return hofp
 
 
-def run_poa_amb(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01):
+def run_poa_amb(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01, matrix=None):
     """main.rs:47-252 with -s true on an AVX2 machine (modes 0-3): the forward call, the reverse-complement retry where the
     mode asks for it, the selection rule of each mode; returns stdout"""
     seqs, names = read_fasta(fasta_text)
     segs, _paths = read_gfa(gfa_text)
     lnz, nwp, pred, hofp = create_graph_struct(segs, read_gfa_links(gfa_text))
     hofp_rev = reverse_handle_map(nwp, segs)
-    sm = score_matrix_match_mis(match, -mismatch)
+    sm = _scores(match, mismatch, matrix)
     smf = f32_scores(sm)
     r_values = set_r_values(nwp, pred, len(lnz))
     out = ""
@@ -1975,12 +2019,12 @@ def run_poa_amb(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap
     return out
 
 
-def run_poa(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01, max_reads=None):
+def run_poa(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, extra_b=1, extra_f=0.01, max_reads=None, matrix=None):
     """main.rs:47-101 (mode 0), :103-169 (mode 1), :215-252 (mode 3) on an AVX2 machine, without -s; returns stdout"""
     seqs, names = read_fasta(fasta_text)
     segs, _paths = read_gfa(gfa_text)
     lnz, nwp, pred, hofp = create_graph_struct(segs, read_gfa_links(gfa_text))
-    sm = score_matrix_match_mis(match, -mismatch)
+    sm = _scores(match, mismatch, matrix)
     smf = f32_scores(sm)
     r_values = set_r_values(nwp, pred, len(lnz)) if mode == 0 else None
     out = ""
@@ -2327,11 +2371,11 @@ def _build_alignment_gap(dpm, x, y, g, bp, ending_node, semi):
     return f"{build_cigar(cigar)}\t({starting_node} {final_node})"
 
 
-def run_gap_pathwise(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2):
+def run_gap_pathwise(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4, gap_ext=2, matrix=None):
     """main.rs:271-288 (modes 6 / 7); returns stdout"""
     seqs, names = read_fasta(fasta_text)
     segs, paths = read_gfa(gfa_text)
-    sm = score_matrix_match_mis(match, -mismatch)
+    sm = _scores(match, mismatch, matrix)
     g = create_path_graph(segs, paths)
     out = ""
     for k, seq in enumerate(seqs):
@@ -2341,11 +2385,11 @@ def run_gap_pathwise(mode, fasta_text, gfa_text, match=2, mismatch=4, gap_open=4
 
 
 # ------------------------------------------------------------------------------------------------ driver
-def run(mode, fasta_text, gfa_text, match=2, mismatch=4, base_rec_cost=4, multi_rec_cost=0.1, rec_band_width=1.0, max_reads=None):
+def run(mode, fasta_text, gfa_text, match=2, mismatch=4, base_rec_cost=4, multi_rec_cost=0.1, rec_band_width=1.0, max_reads=None, matrix=None):
     """main.rs:253-312 for modes 4, 5, 8, 9 with match / mismatch scoring; returns stdout."""
     seqs, names = read_fasta(fasta_text)
     segs, paths = read_gfa(gfa_text)
-    sm = score_matrix_match_mis(match, -mismatch)
+    sm = _scores(match, mismatch, matrix)
     g = create_path_graph(segs, paths)
     out = []
     if mode in (8, 9):

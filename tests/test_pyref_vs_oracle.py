@@ -218,3 +218,32 @@ def test_gap_pathwise_random_small_graphs(block, tmp_path):
                 assert got.startswith(exp), f"seed {seed} mode {mode}: oracle died, pyref did not:\n PY : {got[:300]}\n C++: {exp[:300]}"
                 raise AssertionError(f"seed {seed} mode {mode}: the oracle reports a reference panic, pyref completes")
             assert got == exp, f"seed {seed} mode {mode} -O {O} -E {E}:\n PY : {got[:400]}\n C++: {exp[:400]}"
+
+
+# ------------------------------------------------------------------------------------------------- -t HOXD70 / HOXD55
+def test_matrix_files_random_small_graphs(tmp_path):
+    """score_matrix.rs:67-105 and every routine's (row, column) key order under a NON-symmetric matrix (HOXD70: (G, T) = -114,
+    (T, G) = -144): 12 graphs x both matrices x modes 0-5, 7, 9."""
+    sm = pyref.score_matrix_from_matrix_file("HOXD70")
+    assert sm[("A", "A")] == 91 and sm[("T", "G")] == -144 and ("-", "-") not in sm           # score_matrix.rs:118-131
+    assert pyref.score_matrix_from_matrix_file("HOXD55")[("T", "G")] == -90
+    for seed in range(8000, 8012):
+        g, reads = _case(seed)
+        gfa, fa = tmp_path / f"g{seed}.gfa", tmp_path / f"r{seed}.fa"
+        gfa.write_text(g.gfa())
+        fa.write_text(synth.fasta(reads))
+        F, G = fa.read_text(), gfa.read_text()
+        for mat in ("HOXD70", "HOXD55"):
+            runs = [(0, lambda: pyref.run_poa(0, F, G, matrix=mat)), (1, lambda: pyref.run_poa(1, F, G, matrix=mat)),
+                    (2, lambda: pyref.run_mode2(F, G, matrix=mat)), (3, lambda: pyref.run_poa(3, F, G, matrix=mat)),
+                    (4, lambda: pyref.run(4, F, G, matrix=mat)), (5, lambda: pyref.run(5, F, G, matrix=mat)),
+                    (7, lambda: pyref.run_gap_pathwise(7, F, G, matrix=mat)), (9, lambda: pyref.run(9, F, G, matrix=mat))]
+            for mode, fn in runs:
+                rc, exp, err = oracle_lib.run_cli(["-m", str(mode), "-t", mat, str(fa), str(gfa)])
+                try:
+                    got = fn()
+                except (RuntimeError, IndexError, KeyError) as ex:
+                    assert rc == 101, f"seed {seed} mode {mode} {mat}: pyref says the reference panics ({ex!r}), the oracle exits with {rc}"
+                    continue
+                assert rc == 0, f"seed {seed} mode {mode} {mat}: {err}"
+                assert got == exp, f"seed {seed} mode {mode} -t {mat}:\n PY : {got[:400]}\n C++: {exp[:400]}"
