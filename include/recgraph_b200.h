@@ -62,7 +62,7 @@ typedef struct rg_scoring {
  * Device status: every mode runs on the GPU (6 / 7, experimental in the reference, keep its n x L x P tensors per read in
  * flight); inputs outside a kernel's documented domain return RG_ERR_UNSUPPORTED — there is no CPU fallback. The domain:
  * characters A,C,G,T,N; in-degree <= 31 (modes 0/1/3) / 64 (mode 2); <= 128 paths; reads <= 1023 bases in modes 0/1/3 and
- * <= 12 287 bases through the fast pathwise kernel; mode 0 needs a band amplitude b + f * read length >= 1. */
+ * <= 12 287 bases through the fast pathwise kernel. */
 enum {
     RG_MODE_GLOBAL = 0,
     RG_MODE_LOCAL = 1,

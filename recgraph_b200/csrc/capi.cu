@@ -635,25 +635,6 @@ static int align_poa(rg_ctx* c, int mode) {
         for (int k = 1; k < 5; k++)
             if (c->scoring.score[k][5] != c->scoring.score[0][5])
                 return c->fail(RG_ERR_UNSUPPORTED, "modes 0/1 need one gap score for all characters (true for every matrix the reference builds)");
-    if (mode == RG_MODE_GLOBAL || mode == RG_MODE_GLOBAL_SCALAR) {
-        // Band amplitude 0 (b + f * L < 1, main.rs:57): rows of one cell or none. Mode 2 handles them exactly as the reference
-        // (tests/test_gpu_random_graphs.py); the device routines of mode 0 were found to differ from the expected output there
-        // (tools/one_off_mode0_b0.py) and refuse that domain instead of answering.
-        for (size_t i = 0; i + 1 < c->h_off.size(); i++) {
-            const uint32_t L = (uint32_t)(c->h_off[i + 1] - c->h_off[i]) + 1;
-            int64_t bta;
-            if (c->scoring.fixed_bta >= 0)
-                bta = c->scoring.fixed_bta;
-            else {
-                volatile float prod = c->scoring.extra_f * (float)L;
-                volatile float v = c->scoring.extra_b + prod;
-                const float vv = v;
-                bta = !(vv > 0.0f) ? 0 : (vv >= 1e9f ? (int64_t)1000000000 : (int64_t)vv);
-            }
-            if (bta == 0)
-                return c->fail(RG_ERR_UNSUPPORTED, "mode 0 with a band amplitude of 0 (b + f * read length < 1) is not supported on the device");
-        }
-    }
     if (mode == RG_MODE_GLOBAL_SCALAR || mode == RG_MODE_LOCAL_SCALAR)
         for (int k = 0; k < 5; k++)
             if (c->scoring.score[k][5] != c->scoring.score[0][5] || c->scoring.score[5][k] != c->scoring.score[0][5])

@@ -475,7 +475,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
                 if (GLOBAL) {
                     const int tmax = __reduce_max_sync(FULL, lane_best);
                     const unsigned eq = __ballot_sync(FULL, lane_best == tmax && lane_bcol >= 0);
-                    row_bsp = (uint32_t)__shfl_sync(FULL, lane_bcol, 31 - __clz(eq));
+                    // a row whose band holds column 0 only processes no cell: best_col keeps its initial value `left`
+                    // (global_abpoa.rs:80,160-162,222) — with a band amplitude of 0 that is every row
+                    row_bsp = eq ? (uint32_t)__shfl_sync(FULL, lane_bcol, 31 - __clz(eq)) : left;
                 } else {
                     const int tmax = __reduce_max_sync(FULL, lane_best);
                     const unsigned eq = __ballot_sync(FULL, lane_best == tmax && lane_bcol >= 0);

@@ -5,7 +5,7 @@ from recgraph_b200 import synth, run_cli
 from tests import oracle_lib
 d = pathlib.Path(tempfile.mkdtemp())
 bad = n = ok = 0
-for seed in range(800000, 800000 + int(sys.argv[1]) if len(sys.argv) > 1 else 800120):
+for seed in range(800000, 800000 + (int(sys.argv[1]) if len(sys.argv) > 1 else 120)):
     rng = np.random.default_rng(seed)
     g = synth.make_graph(int(rng.integers(60, 300)), 3, seed=seed, mean_seg=int(rng.integers(3, 12)), p_snp=0.25, p_indel=0.15)
     reads = synth.make_reads(g, 2, int(rng.integers(10, 100)), err=float(rng.choice([0.0, 0.05, 0.2])), seed=seed + 1)
